@@ -1,0 +1,96 @@
+"""ctypes binding of include/mclip.h (the C ABI).  No torch types cross this boundary: tensors are passed as
+`data_ptr()` integers and the stream as `torch.cuda.current_stream().cuda_stream`.
+
+There is NO CPU fallback: if the library is missing or the device is not a B200, calls raise."""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libmclip_b200.so")
+
+MAX_TENSORS, MAX_PAIRS = 4, 8
+
+
+class MclipError(RuntimeError):
+    pass
+
+
+class LossArgs(C.Structure):
+    _fields_ = [
+        ("world", C.c_int), ("rank", C.c_int), ("batch", C.c_int), ("dim", C.c_int),
+        ("n_tensors", C.c_int), ("n_pairs", C.c_int),
+        ("local", C.c_void_p * MAX_TENSORS),
+        ("grad", C.c_void_p * MAX_TENSORS),
+        ("pair_a", C.c_int * MAX_PAIRS), ("pair_b", C.c_int * MAX_PAIRS),
+        ("w_row", C.c_float * MAX_PAIRS), ("w_col", C.c_float * MAX_PAIRS), ("label_smoothing", C.c_float * MAX_PAIRS),
+        ("logit_scale", C.c_float),
+        ("workspace", C.c_void_p), ("workspace_bytes", C.c_longlong),
+        ("out", C.c_void_p),
+        ("gathered", C.c_void_p * MAX_TENSORS),
+        ("peer_gathered", C.c_void_p),
+        ("peer_flags", C.c_void_p),
+        ("my_flags", C.c_void_p),
+        ("epoch", C.c_longlong),
+    ]
+
+
+class GemmArgs(C.Structure):
+    _fields_ = [
+        ("a", C.c_void_p), ("lda", C.c_longlong), ("a_batch_stride", C.c_longlong),
+        ("b", C.c_void_p), ("ldb", C.c_longlong), ("b_batch_stride", C.c_longlong),
+        ("d", C.c_void_p), ("ldd", C.c_longlong), ("d_batch_stride", C.c_longlong),
+        ("m", C.c_int), ("n", C.c_int), ("k", C.c_int), ("batches", C.c_int),
+        ("bias", C.c_void_p),
+        ("residual", C.c_void_p), ("ldr", C.c_longlong), ("r_batch_stride", C.c_longlong),
+        ("act", C.c_int),
+        ("stats", C.c_void_p), ("stat_slots", C.c_int),
+    ]
+
+
+class WgradArgs(C.Structure):
+    _fields_ = [
+        ("a", C.c_void_p), ("lda", C.c_longlong),
+        ("b", C.c_void_p), ("ldb", C.c_longlong),
+        ("out", C.c_void_p), ("ldo", C.c_longlong), ("accumulate", C.c_int),
+        ("r", C.c_int), ("i", C.c_int), ("j", C.c_int),
+        ("workspace", C.c_void_p), ("workspace_bytes", C.c_longlong),
+    ]
+
+
+_lib = None
+
+
+def lib():
+    """Loads the shared library (building it first if nvcc is present and the sources changed)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH) or os.environ.get("MCLIP_REBUILD") == "1":
+        from . import build as _build
+        _build.build()
+    if not os.path.exists(LIB_PATH):
+        raise MclipError(f"{LIB_PATH} is missing: run `python mammo-clip_b200/build.py` (there is no fallback path)")
+    L = C.CDLL(LIB_PATH)
+    L.mclip_last_error.restype = C.c_char_p
+    L.mclip_loss_workspace_bytes.restype = C.c_longlong
+    L.mclip_gemm_wgrad_workspace_bytes.restype = C.c_longlong
+    for name in dir(L):
+        pass
+    _lib = L
+    return L
+
+
+def check(rc: int, what: str = ""):
+    if rc != 0:
+        msg = lib().mclip_last_error().decode(errors="replace")
+        raise MclipError(f"{what} failed ({rc}): {msg}")
+
+
+def stream_ptr():
+    import torch
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def ptr(t):
+    """Device pointer of a tensor (None -> NULL)."""
+    return None if t is None else C.c_void_p(t.data_ptr())

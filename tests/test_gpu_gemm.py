@@ -1,0 +1,81 @@
+"""tcgen05 GEMMs vs a plain PyTorch fp32 reference on the same bf16 inputs (tolerance: bf16 output rounding)."""
+import pytest
+import torch
+
+from conftest import rel_err
+
+pytestmark = pytest.mark.gpu
+
+
+def _mk(shape, seed, scale=1.0):
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    return (torch.randn(shape, generator=g, device="cuda") * scale).to(torch.bfloat16)
+
+
+# (batches, M, N, K): MBConv expand/project shapes incl. hostile channel counts, BERT shapes, ragged M
+TN_SHAPES = [
+    (1, 128, 64, 64), (1, 256, 16, 24), (1, 1000, 144, 24), (1, 4096, 240, 40), (1, 777, 40, 240),
+    (1, 4096, 768, 768), (1, 4096, 3072, 768), (1, 4096, 768, 3072), (1, 2784, 304, 1824), (1, 1392, 1056, 176),
+    (1, 33, 512, 2048), (1, 20000, 24, 144), (1, 300, 2048, 512), (1, 128, 1408, 352),
+]
+
+
+@pytest.mark.parametrize("bt,m,n,k", TN_SHAPES)
+def test_gemm_tn(bt, m, n, k):
+    from mammoclip_b200 import ops
+    a, w = _mk((m, k), 1), _mk((n, k), 2, 1.0 / k ** 0.5)
+    out = ops.gemm_tn(a, w)
+    torch.cuda.synchronize()
+    ref = a.float() @ w.float().T
+    err = rel_err(out.float(), ref)
+    assert err < 6e-3, f"gemm_tn {m}x{n}x{k}: rel err {err}"
+
+
+def test_gemm_tn_batched_per_sample_weights():
+    from mammoclip_b200 import ops
+    bt, m, n, k = 5, 300, 40, 240          # project conv with SE-gated per-sample weights; M not a tile multiple
+    a, w = _mk((bt, m, k), 3), _mk((bt, n, k), 4, 1.0 / k ** 0.5)
+    out = ops.gemm_tn(a, w)
+    ref = torch.einsum("bmk,bnk->bmn", a.float(), w.float())
+    assert rel_err(out.float(), ref) < 6e-3
+    out2 = ops.gemm_tn(a, w[0].contiguous())
+    ref2 = torch.einsum("bmk,nk->bmn", a.float(), w[0].float())
+    assert rel_err(out2.float(), ref2) < 6e-3
+
+
+@pytest.mark.parametrize("m,n,k", [(1000, 144, 24), (5000, 384, 64), (4096, 1824, 304), (257, 96, 16)])
+def test_gemm_tn_bn_stats(m, n, k):
+    from mammoclip_b200 import ops
+    a, w = _mk((m, k), 5), _mk((n, k), 6, 1.0 / k ** 0.5)
+    out, stats = ops.gemm_tn(a, w, want_stats=True)
+    s = stats.double().sum(0)
+    o = out.double()
+    assert rel_err(s[0], o.sum(0)) < 1e-4
+    assert rel_err(s[1], (o * o).sum(0)) < 1e-4
+
+
+def test_gemm_tn_epilogues():
+    from mammoclip_b200 import ops
+    m, n, k = 4096, 768, 768
+    a, w = _mk((m, k), 7), _mk((n, k), 8, 1.0 / k ** 0.5)
+    bias = torch.randn(n, device="cuda")
+    res = _mk((m, n), 9)
+    out = ops.gemm_tn(a, w, bias=bias, act=1)
+    ref = torch.nn.functional.gelu(a.float() @ w.float().T + bias)
+    assert rel_err(out.float(), ref) < 6e-3
+    out = ops.gemm_tn(a, w, bias=bias, residual=res)
+    ref = a.float() @ w.float().T + bias + res.float()
+    assert rel_err(out.float(), ref) < 6e-3
+
+
+@pytest.mark.parametrize("r,i,j", [(4096, 144, 24), (20000, 40, 240), (1000, 768, 768), (2784, 304, 1824), (100, 24, 24),
+                                   (8192, 3072, 768), (50000, 48, 48)])
+def test_gemm_wgrad(r, i, j):
+    from mammoclip_b200 import ops
+    a, b = _mk((r, i), 10), _mk((r, j), 11)
+    out = ops.gemm_wgrad(a, b)
+    ref = a.float().T @ b.float()
+    err = rel_err(out, ref)
+    assert err < 2e-3, f"wgrad {r}x{i}x{j}: rel err {err}"
+    out2 = ops.gemm_wgrad(a, b, out=out.clone(), accumulate=True)
+    assert rel_err(out2, 2 * ref) < 2e-3
