@@ -88,6 +88,128 @@ typedef struct mclip_wgrad_args {
 long long mclip_gemm_wgrad_workspace_bytes(int r, int i, int j);
 int mclip_gemm_wgrad(const mclip_wgrad_args* args, void* stream);
 
+/* ---- depthwise / stem convolutions ------------------------------------------------------------------------------
+ * mclip_dwconv_*: MBConvBlock._depthwise_conv (efficientnet_custom.py:66-73,109), a Conv2dStaticSamePadding
+ * (efficient_net_custom_utils.py:248-276) with groups == channels, k in {3,5}, stride in {1,2} and the STATIC
+ * (left,right,top,bottom) pads frozen at construction.  NHWC bf16.  When in_scale != NULL the input is the
+ * producer's pre-BatchNorm output and swish(in_scale*y + in_shift) is applied while loading (BN :106 + swish :107
+ * of the expand phase, or the stem's :273), zero padding after it.  stats: per-channel (sum, sum sq) partials of
+ * the output for the following BatchNorm (:110).  Backward yields, in one pass over (dy, in): dx = gradient
+ * w.r.t. the pre-activation input (already multiplied by swish'), the weight gradient, and the input BN's
+ * backward reduction partials (sum dv, sum dv*yhat). */
+typedef struct mclip_dwconv_args {
+  int n, h, w, c, ho, wo, k, stride;
+  int pad_left, pad_right, pad_top, pad_bottom;
+  const void* in;                 /* bf16 [n,h,w,c] */
+  const float* in_scale;          /* fp32 [c] or NULL */
+  const float* in_shift;
+  int in_act;                     /* 1: swish after the affine */
+  const float* weight;            /* fp32 [c,1,k,k] */
+  void* out;                      /* bf16 [n,ho,wo,c]                      (forward) */
+  float* stats; int stat_slots;   /* fp32 [stat_slots][2][c] or NULL; slots from mclip_dwconv_slots(args, backward) */
+  const void* dy;                 /* bf16 [n,ho,wo,c]                      (backward) */
+  void* dx;                       /* bf16 [n,h,w,c] */
+  float* dweight; int accumulate; /* fp32 [c,1,k,k] */
+  float* dw_partials;             /* fp32 [stat_slots][k*k][c] workspace */
+  float* bn_partials;             /* fp32 [stat_slots][2][c] (used iff in_scale != NULL) */
+  const float* in_mean;           /* fp32 [c] batch statistics of the input BatchNorm */
+  const float* in_invstd;
+} mclip_dwconv_args;
+int mclip_dwconv_slots(const mclip_dwconv_args* args, int backward);
+int mclip_dwconv_forward(const mclip_dwconv_args* args, void* stream);
+int mclip_dwconv_backward(const mclip_dwconv_args* args, void* stream);
+
+/* mclip_stem_*: EfficientNet._conv_stem (efficientnet_custom.py:174-176,273): dense 3x3 stride-2, 3 -> c channels,
+ * static pads; input fp32 with arbitrary element strides (the trainer passes NCHW-shaped NHWC memory,
+ * trainer_ddp.py:288-291); output bf16 NHWC + BN statistics partials.  No data gradient (images need none). */
+typedef struct mclip_stem_args {
+  int n, h, w, ho, wo, c;
+  int pad_left, pad_right, pad_top, pad_bottom;
+  const float* in; long long stride_n, stride_c, stride_h, stride_w;
+  const float* weight;            /* fp32 [c,3,3,3] */
+  void* out;                      /* bf16 [n,ho,wo,c] */
+  float* stats; int stat_slots;   /* slots = mclip_stem_slots(n,ho,wo) */
+  const void* dy;                 /* bf16 [n,ho,wo,c] (wgrad) */
+  float* dweight; int accumulate;
+  float* dw_partials;             /* fp32 [stat_slots][27][c] */
+} mclip_stem_args;
+int mclip_stem_slots(int n, int ho, int wo);
+int mclip_stem_forward(const mclip_stem_args* args, void* stream);
+int mclip_stem_wgrad(const mclip_stem_args* args, void* stream);
+
+/* ---- BatchNorm / swish / squeeze-excite / pooling passes ---------------------------------------------------------
+ * Producer kernels (GEMM, depthwise, stem) emit per-channel (sum, sum sq) partials; mclip_bn_finalize turns them
+ * into the affine a = gamma*invstd, b = beta - mean*a that CONSUMERS apply while loading, and performs the running
+ * statistics update of nn.BatchNorm2d(momentum=0.01, eps=1e-3) (efficientnet_custom.py:53-54,64,74,88,177,205):
+ * biased variance for normalisation, unbiased for running_var, num_batches_tracked += 1.  training == 0: the affine
+ * comes from the running statistics (eval mode). */
+typedef struct mclip_bn_args {
+  int c, slots, training;
+  long long count;                      /* elements per channel (N*H*W) */
+  const float* partials;                /* fp32 [slots][2][c] */
+  const float* gamma; const float* beta;
+  float* running_mean; float* running_var; long long* num_batches_tracked;
+  float momentum, eps;
+  float* scale; float* shift; float* mean; float* invstd;     /* fp32 [c] out */
+} mclip_bn_args;
+int mclip_bn_finalize(const mclip_bn_args* args, void* stream);
+
+/* One streaming pass over y[n,hw,c] (bf16): u = act(scale*y+shift) * rowscale[n] + residual ; optional bf16 output and
+ * per-(n,chunk) channel sums (average-pool partials).  Covers bn->swish->avg_pool (efficientnet_custom.py:110-115,
+ * 283,309) and _bn2 + drop_connect + skip (:123-131; rowscale = mask/keep_prob, efficient_net_custom_utils.py:145-154). */
+typedef struct mclip_ew_args {
+  int n, hw, c, act, chunks;
+  const void* y; const float* scale; const float* shift;
+  const float* rowscale; const void* residual;
+  void* out; float* pool_partials;      /* pool_partials fp32 [n][chunks][c], chunks = mclip_ew_chunks(n,hw,c) */
+} mclip_ew_args;
+int mclip_ew_chunks(int n, int hw, int c);
+int mclip_ew_forward(const mclip_ew_args* args, void* stream);
+int mclip_pool_finalize(const float* partials, int n, int chunks, int c, int hw, const float* mult, float* out, void* stream);
+
+/* Squeeze-excite FC stack (efficientnet_custom.py:114-119) and its backward; gate folded into per-sample weights. */
+typedef struct mclip_se_args {
+  int n, hw, c, cse, chunks, accumulate;
+  const float* pool_partials;           /* fp32 [n][chunks][c] (forward) */
+  const float* w1; const float* b1;     /* _se_reduce: [cse,c], [cse] */
+  const float* w2; const float* b2;     /* _se_expand: [c,cse], [c] */
+  float* pooled; float* z1; float* gate;          /* fp32 [n,c], [n,cse], [n,c] (saved for backward) */
+  const float* dgate_partials;          /* fp32 [n][chunks][c] (backward) */
+  float* dz2; float* dz1; float* dpool;           /* fp32 [n,c], [n,cse], [n,c] */
+  float* dw1; float* db1; float* dw2; float* db2;
+} mclip_se_args;
+int mclip_se_fc(const mclip_se_args* args, void* stream);
+int mclip_se_fc_backward(const mclip_se_args* args, void* stream);
+int mclip_se_scale_weights(const float* w, const float* gate, void* out_bf16, int n, int cout, int cexp, void* stream);
+
+/* Backward streaming passes (autograd of BatchNorm2d + MemoryEfficientSwish (efficient_net_custom_utils.py:64-80) +
+ * SE gating + drop-connect).  mode 0: BN-backward reduction partials [n*chunks][2][c] (sum dv, sum dv*yhat);
+ * mode 1: dY = scale*(dv - c1 - yhat*c2) (bf16); mode 2: A2 = gate*swish(scale*y+shift) (bf16) + dgate partials. */
+typedef struct mclip_ew_bwd_args {
+  int n, hw, c, act, mode, dv_given, chunks;
+  const void* y; const float* scale; const float* shift;
+  const void* du; const float* dvec; const float* gate; const float* dpool; const float* rowscale;
+  const float* mean; const float* invstd; const float* c1; const float* c2;
+  float* partials; void* out;
+} mclip_ew_bwd_args;
+int mclip_ew_backward(const mclip_ew_bwd_args* args, void* stream);
+int mclip_bn_bwd_finalize(const float* partials, int slots, int c, long long count, int training, float* dgamma, float* dbeta,
+                          int accumulate, float* c1, float* c2, void* stream);
+
+/* fp32 master weights -> bf16 GEMM operands (and their transposes for the data-gradient GEMMs), one launch per tower. */
+typedef struct mclip_prep_entry { const void* src; void* dst; void* dst_t; int rows, cols; } mclip_prep_entry;
+int mclip_weight_prep(const void* table_dev, int n_entries, void* stream);
+
+/* CLIP head helpers: cast, x/||x|| (clip.py:90-91) forward/backward, Linear bias gradient. */
+int mclip_cast_bf16(const float* in, void* out_bf16, long long n, void* stream);
+int mclip_l2norm_forward(const void* x_bf16, float* e, float* norm, int rows, int d, void* stream);
+int mclip_l2norm_backward(const float* e, const float* de, const float* norm, void* dx_bf16, int rows, int d, void* stream);
+int mclip_colsum(const void* x_bf16, float* out, int rows, int cols, long long ld, int accumulate, void* stream);
+
+/* AdamW over a flat fp32 buffer (breastclip/optimizer/__init__.py:23-31: torch.optim.AdamW on all parameters). */
+int mclip_adamw_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, long long n, float lr, float beta1,
+                     float beta2, float eps, float weight_decay, long long step, float grad_scale, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

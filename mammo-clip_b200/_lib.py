@@ -94,3 +94,68 @@ def stream_ptr():
 def ptr(t):
     """Device pointer of a tensor (None -> NULL)."""
     return None if t is None else C.c_void_p(t.data_ptr())
+
+
+class DwconvArgs(C.Structure):
+    _fields_ = [
+        ("n", C.c_int), ("h", C.c_int), ("w", C.c_int), ("c", C.c_int), ("ho", C.c_int), ("wo", C.c_int), ("k", C.c_int), ("stride", C.c_int),
+        ("pad_left", C.c_int), ("pad_right", C.c_int), ("pad_top", C.c_int), ("pad_bottom", C.c_int),
+        ("in_", C.c_void_p), ("in_scale", C.c_void_p), ("in_shift", C.c_void_p), ("in_act", C.c_int),
+        ("weight", C.c_void_p), ("out", C.c_void_p),
+        ("stats", C.c_void_p), ("stat_slots", C.c_int),
+        ("dy", C.c_void_p), ("dx", C.c_void_p), ("dweight", C.c_void_p), ("accumulate", C.c_int),
+        ("dw_partials", C.c_void_p), ("bn_partials", C.c_void_p), ("in_mean", C.c_void_p), ("in_invstd", C.c_void_p),
+    ]
+
+
+class StemArgs(C.Structure):
+    _fields_ = [
+        ("n", C.c_int), ("h", C.c_int), ("w", C.c_int), ("ho", C.c_int), ("wo", C.c_int), ("c", C.c_int),
+        ("pad_left", C.c_int), ("pad_right", C.c_int), ("pad_top", C.c_int), ("pad_bottom", C.c_int),
+        ("in_", C.c_void_p), ("stride_n", C.c_longlong), ("stride_c", C.c_longlong), ("stride_h", C.c_longlong), ("stride_w", C.c_longlong),
+        ("weight", C.c_void_p), ("out", C.c_void_p),
+        ("stats", C.c_void_p), ("stat_slots", C.c_int),
+        ("dy", C.c_void_p), ("dweight", C.c_void_p), ("accumulate", C.c_int), ("dw_partials", C.c_void_p),
+    ]
+
+
+class BnArgs(C.Structure):
+    _fields_ = [
+        ("c", C.c_int), ("slots", C.c_int), ("training", C.c_int), ("count", C.c_longlong),
+        ("partials", C.c_void_p), ("gamma", C.c_void_p), ("beta", C.c_void_p),
+        ("running_mean", C.c_void_p), ("running_var", C.c_void_p), ("num_batches_tracked", C.c_void_p),
+        ("momentum", C.c_float), ("eps", C.c_float),
+        ("scale", C.c_void_p), ("shift", C.c_void_p), ("mean", C.c_void_p), ("invstd", C.c_void_p),
+    ]
+
+
+class EwArgs(C.Structure):
+    _fields_ = [
+        ("n", C.c_int), ("hw", C.c_int), ("c", C.c_int), ("act", C.c_int), ("chunks", C.c_int),
+        ("y", C.c_void_p), ("scale", C.c_void_p), ("shift", C.c_void_p), ("rowscale", C.c_void_p), ("residual", C.c_void_p),
+        ("out", C.c_void_p), ("pool_partials", C.c_void_p),
+    ]
+
+
+class SeArgs(C.Structure):
+    _fields_ = [
+        ("n", C.c_int), ("hw", C.c_int), ("c", C.c_int), ("cse", C.c_int), ("chunks", C.c_int), ("accumulate", C.c_int),
+        ("pool_partials", C.c_void_p), ("w1", C.c_void_p), ("b1", C.c_void_p), ("w2", C.c_void_p), ("b2", C.c_void_p),
+        ("pooled", C.c_void_p), ("z1", C.c_void_p), ("gate", C.c_void_p),
+        ("dgate_partials", C.c_void_p), ("dz2", C.c_void_p), ("dz1", C.c_void_p), ("dpool", C.c_void_p),
+        ("dw1", C.c_void_p), ("db1", C.c_void_p), ("dw2", C.c_void_p), ("db2", C.c_void_p),
+    ]
+
+
+class EwBwdArgs(C.Structure):
+    _fields_ = [
+        ("n", C.c_int), ("hw", C.c_int), ("c", C.c_int), ("act", C.c_int), ("mode", C.c_int), ("dv_given", C.c_int), ("chunks", C.c_int),
+        ("y", C.c_void_p), ("scale", C.c_void_p), ("shift", C.c_void_p),
+        ("du", C.c_void_p), ("dvec", C.c_void_p), ("gate", C.c_void_p), ("dpool", C.c_void_p), ("rowscale", C.c_void_p),
+        ("mean", C.c_void_p), ("invstd", C.c_void_p), ("c1", C.c_void_p), ("c2", C.c_void_p),
+        ("partials", C.c_void_p), ("out", C.c_void_p),
+    ]
+
+
+class PrepEntry(C.Structure):
+    _fields_ = [("src", C.c_void_p), ("dst", C.c_void_p), ("dst_t", C.c_void_p), ("rows", C.c_int), ("cols", C.c_int)]

@@ -1,0 +1,584 @@
+// BatchNorm (train + eval), swish, squeeze-excite, pooling, residual / drop-connect: the HBM-bound passes between the
+// convolutions of MBConvBlock (efficientnet_custom.py:91-132) and of the stem / head (:273,283,309-312), forward and
+// backward.  All of them stream NHWC bf16 tensors with 16-byte vectors; a thread owns one 8-channel vector for the whole
+// kernel (per-channel parameters and accumulators live in registers) and strides over pixels.
+//
+//   reference op (file:line)                               kernel here
+//   nn.BatchNorm2d train: batch stats, running update      producer epilogue partials -> mclip_bn_finalize
+//     (efficientnet_custom.py:53-54,64,74,88,177,205)
+//   bn(x) -> swish -> adaptive_avg_pool2d (:110-115)       mclip_act_pool   (also writes the activated tensor U)
+//   _se_reduce -> swish -> _se_expand -> sigmoid (:116-119) mclip_se_fc      (+ mclip_se_scale_weights: gate folded into W_proj)
+//   _bn2, drop_connect, x + inputs (:123-131)               mclip_bn_apply
+//   swish -> _avg_pooling -> flatten -> dropout (:283,309-312)  mclip_act_pool + mclip_pool_finalize
+//   autograd of all of the above                            mclip_bn_bwd_reduce / _finalize / _apply, mclip_se_bwd_pass1, mclip_se_fc_bwd
+#include "common.cuh"
+#include "mclip_internal.h"
+
+#define EW_MAX_THREADS 384
+
+struct EwGeom {
+  int N, HW, C, CV, PL, chunks, pix_per_chunk;
+};
+
+static int ew_geom(int n, int hw, int c, EwGeom* g, int* threads) {
+  if (c % 8 != 0 || c / 8 > EW_MAX_THREADS) { mclip_set_error("elementwise: C=%d must be a multiple of 8 and <= %d", c, 8 * EW_MAX_THREADS); return MCLIP_ERR_INVALID; }
+  g->N = n; g->HW = hw; g->C = c; g->CV = c / 8;
+  g->PL = 256 / g->CV; if (g->PL < 1) g->PL = 1;
+  *threads = g->CV * g->PL;
+  long long want = (long long)mclip_num_sms() * 8;
+  int chunks = (int)((want + n - 1) / n);
+  int max_chunks = (hw + g->PL * 4 - 1) / (g->PL * 4);
+  if (chunks > max_chunks) chunks = max_chunks;
+  if (chunks < 1) chunks = 1;
+  g->pix_per_chunk = (hw + chunks - 1) / chunks;
+  g->chunks = (hw + g->pix_per_chunk - 1) / g->pix_per_chunk;
+  return MCLIP_OK;
+}
+
+extern "C" int mclip_ew_chunks(int n, int hw, int c) {
+  EwGeom g; int t;
+  if (ew_geom(n, hw, c, &g, &t)) return -1;
+  return g.chunks;
+}
+
+// block reduction over the PL pixel lanes of 8-channel vectors: out[cv*8+i] = sum over lanes
+__device__ __forceinline__ void ew_block_reduce8(float* smem, const float* v, int cv, int pl, int CV, int PL, float* dst, bool add_to = false) {
+  // smem: [PL][CV*8]
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < 8; ++i) smem[(size_t)pl * CV * 8 + cv * 8 + i] = v[i];
+  __syncthreads();
+  for (int i = threadIdx.x; i < CV * 8; i += blockDim.x) {
+    float s = 0.f;
+    for (int l = 0; l < PL; ++l) s += smem[(size_t)l * CV * 8 + i];
+    dst[i] = add_to ? dst[i] + s : s;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// BatchNorm statistics -> affine (a = gamma*invstd, b = beta - mean*a), running-stat update
+// ------------------------------------------------------------------------------------------------
+__global__ void mclip_bn_finalize_kernel(const float* __restrict__ partials, int slots, int C, double count, const float* __restrict__ gamma,
+                                         const float* __restrict__ beta, float* running_mean, float* running_var, long long* num_batches,
+                                         float momentum, float eps, int training, float* scale, float* shift, float* mean_out, float* invstd_out) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c == 0 && training && num_batches) *num_batches += 1;
+  if (c >= C) return;
+  float mean, invstd;
+  if (training) {
+    double s = 0.0, q = 0.0;
+    for (int k = 0; k < slots; ++k) { s += (double)partials[((size_t)k * 2 + 0) * C + c]; q += (double)partials[((size_t)k * 2 + 1) * C + c]; }
+    double m = s / count;
+    double var = q / count - m * m;
+    if (var < 0.0) var = 0.0;
+    mean = (float)m;
+    invstd = (float)(1.0 / sqrt(var + (double)eps));
+    if (running_mean) {
+      double unbiased = count > 1.0 ? var * count / (count - 1.0) : var;
+      running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * mean;
+      running_var[c] = (1.f - momentum) * running_var[c] + momentum * (float)unbiased;
+    }
+  } else {
+    mean = running_mean[c];
+    invstd = rsqrtf(running_var[c] + eps);
+  }
+  const float a = gamma[c] * invstd;
+  scale[c] = a;
+  shift[c] = beta[c] - mean * a;
+  mean_out[c] = mean;
+  invstd_out[c] = invstd;
+}
+
+extern "C" int mclip_bn_finalize(const mclip_bn_args* a, void* stream) {
+  MCLIP_REQUIRE(a && a->gamma && a->beta && a->scale && a->shift && a->mean && a->invstd, "mclip_bn_finalize: null operand");
+  MCLIP_REQUIRE(a->training ? (a->partials != nullptr && a->slots > 0 && a->count > 0) : (a->running_mean && a->running_var),
+                "mclip_bn_finalize: %s", a->training ? "training needs partials and a positive count" : "eval needs running statistics");
+  mclip_bn_finalize_kernel<<<ceil_div(a->c, 128), 128, 0, (cudaStream_t)stream>>>(a->partials, a->slots, a->c, (double)a->count, a->gamma, a->beta,
+                                                                               a->running_mean, a->running_var, a->num_batches_tracked,
+                                                                               a->momentum, a->eps, a->training, a->scale, a->shift, a->mean, a->invstd);
+  MCLIP_CHECK_LAUNCH();
+  return MCLIP_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// generic streaming pass (forward):  v = a*y+b ; u = act ? swish(v) : v ; u *= rowscale[n] ; u += residual
+//   optional: write u (bf16), accumulate per-(n,chunk) channel sums of u (pooling partials)
+// ------------------------------------------------------------------------------------------------
+struct EwFwdDev {
+  EwGeom g;
+  const bf16* y; const float* scale; const float* shift; int act;
+  const float* rowscale; const bf16* residual;
+  bf16* out; float* pool_part;     // pool_part: [N][chunks][C]
+};
+
+__global__ void __launch_bounds__(EW_MAX_THREADS) mclip_ew_fwd_kernel(const EwFwdDev p) {
+  extern __shared__ float ew_smem[];
+  const EwGeom& g = p.g;
+  const int cv = threadIdx.x % g.CV, pl = threadIdx.x / g.CV;
+  const int n = blockIdx.x / g.chunks, chunk = blockIdx.x % g.chunks;
+  const int p0 = chunk * g.pix_per_chunk, p1 = min(g.HW, p0 + g.pix_per_chunk);
+  float a[8], b[8], acc[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { a[i] = p.scale ? p.scale[cv * 8 + i] : 1.f; b[i] = p.shift ? p.shift[cv * 8 + i] : 0.f; acc[i] = 0.f; }
+  const float rs = p.rowscale ? p.rowscale[n] : 1.f;
+  const size_t base = (size_t)n * g.HW * g.C + (size_t)cv * 8;
+  for (int px = p0 + pl; px < p1; px += g.PL) {
+    const size_t off = base + (size_t)px * g.C;
+    float f[8];
+    unpack8(ldg_bf16x8(p.y + off), f);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      float v = fmaf(f[i], a[i], b[i]);
+      f[i] = (p.act ? swish_f(v) : v) * rs;
+    }
+    if (p.residual) {
+      float r[8];
+      unpack8(ldg_bf16x8(p.residual + off), r);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) f[i] += r[i];
+    }
+    bf16x8 pk = pack8(f);
+    if (p.out) stg_bf16x8(p.out + off, pk);
+    if (p.pool_part) {
+      float r[8];
+      unpack8(pk, r);        // pool what the consumer will read (bf16-rounded), like the reference's autocast tensors
+#pragma unroll
+      for (int i = 0; i < 8; ++i) acc[i] += r[i];
+    }
+  }
+  if (p.pool_part) ew_block_reduce8(ew_smem, acc, cv, pl, g.CV, g.PL, p.pool_part + ((size_t)n * g.chunks + chunk) * g.C);
+}
+
+extern "C" int mclip_ew_forward(const mclip_ew_args* a, void* stream) {
+  MCLIP_REQUIRE(a && a->y, "mclip_ew_forward: null input");
+  EwFwdDev p; int threads;
+  int rc = ew_geom(a->n, a->hw, a->c, &p.g, &threads);
+  if (rc) return rc;
+  if (a->pool_partials) MCLIP_REQUIRE(a->chunks == p.g.chunks, "mclip_ew_forward: chunks=%d, expected %d", a->chunks, p.g.chunks);
+  p.y = (const bf16*)a->y; p.scale = a->scale; p.shift = a->shift; p.act = a->act; p.rowscale = a->rowscale;
+  p.residual = (const bf16*)a->residual; p.out = (bf16*)a->out; p.pool_part = a->pool_partials;
+  const int smem = p.g.PL * p.g.C * 4;
+  mclip_ew_fwd_kernel<<<a->n * p.g.chunks, threads, smem, (cudaStream_t)stream>>>(p);
+  MCLIP_CHECK_LAUNCH();
+  return MCLIP_OK;
+}
+
+// pooled[n,c] = mult[n,c] * (sum_chunks part[n,chunk,c]) / HW          (head average pool + dropout mask)
+__global__ void mclip_pool_finalize_kernel(const float* __restrict__ part, int N, int chunks, int C, float inv_hw, const float* __restrict__ mult,
+                                           float* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N * C) return;
+  const int n = i / C, c = i % C;
+  float s = 0.f;
+  for (int k = 0; k < chunks; ++k) s += part[((size_t)n * chunks + k) * C + c];
+  s *= inv_hw;
+  out[i] = mult ? s * mult[i] : s;
+}
+
+extern "C" int mclip_pool_finalize(const float* partials, int n, int chunks, int c, int hw, const float* mult, float* out, void* stream) {
+  MCLIP_REQUIRE(partials && out && n > 0 && c > 0 && hw > 0, "mclip_pool_finalize: bad arguments");
+  mclip_pool_finalize_kernel<<<ceil_div((long long)n * c, 256), 256, 0, (cudaStream_t)stream>>>(partials, n, chunks, c, 1.0f / (float)hw, mult, out);
+  MCLIP_CHECK_LAUNCH();
+  return MCLIP_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// squeeze-excite FC stack, one CTA per sample
+//   s = pooled mean ; z1 = W1 s + b1 ; h = swish(z1) ; z2 = W2 h + b2 ; g = sigmoid(z2)
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) mclip_se_fc_kernel(const float* __restrict__ part, int chunks, int C, int Cse, float inv_hw,
+                                                          const float* __restrict__ W1, const float* __restrict__ b1, const float* __restrict__ W2,
+                                                          const float* __restrict__ b2, float* __restrict__ s_out, float* __restrict__ z1_out,
+                                                          float* __restrict__ gate) {
+  extern __shared__ float se_smem[];
+  float* s = se_smem;            // [C]
+  float* h = se_smem + C;        // [Cse]
+  const int n = blockIdx.x;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float v = 0.f;
+    for (int k = 0; k < chunks; ++k) v += part[((size_t)n * chunks + k) * C + c];
+    v *= inv_hw;
+    s[c] = v;
+    s_out[(size_t)n * C + c] = v;
+  }
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+  for (int j = warp; j < Cse; j += nw) {
+    float v = 0.f;
+    for (int c = lane; c < C; c += 32) v = fmaf(W1[(size_t)j * C + c], s[c], v);
+    v = warp_sum(v);
+    if (lane == 0) {
+      v += b1[j];
+      z1_out[(size_t)n * Cse + j] = v;
+      h[j] = v * sigmoid_precise(v);
+    }
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float v = b2[c];
+    for (int j = 0; j < Cse; ++j) v = fmaf(W2[(size_t)c * Cse + j], h[j], v);
+    gate[(size_t)n * C + c] = sigmoid_precise(v);
+  }
+}
+
+extern "C" int mclip_se_fc(const mclip_se_args* a, void* stream) {
+  MCLIP_REQUIRE(a && a->pool_partials && a->w1 && a->b1 && a->w2 && a->b2 && a->pooled && a->z1 && a->gate, "mclip_se_fc: null operand");
+  const int smem = (a->c + a->cse) * 4;
+  mclip_se_fc_kernel<<<a->n, 256, smem, (cudaStream_t)stream>>>(a->pool_partials, a->chunks, a->c, a->cse, 1.0f / (float)a->hw, a->w1, a->b1, a->w2, a->b2,
+                                                                 a->pooled, a->z1, a->gate);
+  MCLIP_CHECK_LAUNCH();
+  return MCLIP_OK;
+}
+
+// Wg[n,co,ce] = bf16( W[co,ce] * gate[n,ce] ) : the SE gate folded into per-sample project-conv weights
+__global__ void mclip_se_scale_weights_kernel(const float* __restrict__ W, const float* __restrict__ gate, bf16* __restrict__ out, int N, int Cout, int Cexp) {
+  const long long per = (long long)Cout * Cexp / 8;
+  const long long total = per * N;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int n = (int)(i / per);
+    const long long r = i % per;
+    const int ce = (int)((r * 8) % Cexp);
+    const float4* wp = reinterpret_cast<const float4*>(W + r * 8);
+    const float4* gp = reinterpret_cast<const float4*>(gate + (size_t)n * Cexp + ce);
+    float4 w0 = wp[0], w1 = wp[1], g0 = gp[0], g1 = gp[1];
+    float f[8] = {w0.x * g0.x, w0.y * g0.y, w0.z * g0.z, w0.w * g0.w, w1.x * g1.x, w1.y * g1.y, w1.z * g1.z, w1.w * g1.w};
+    *reinterpret_cast<bf16x8*>(out + i * 8) = pack8(f);
+  }
+}
+
+extern "C" int mclip_se_scale_weights(const float* w, const float* gate, void* out, int n, int cout, int cexp, void* stream) {
+  MCLIP_REQUIRE(w && gate && out && cexp % 8 == 0, "mclip_se_scale_weights: bad arguments");
+  long long total = (long long)n * cout * cexp / 8;
+  int grid = (int)((total + 255) / 256);
+  if (grid > mclip_num_sms() * 8) grid = mclip_num_sms() * 8;
+  mclip_se_scale_weights_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(w, gate, (bf16*)out, n, cout, cexp);
+  MCLIP_CHECK_LAUNCH();
+  return MCLIP_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// backward streaming passes.
+//   upstream gradient of the activation output u:   du = dU[n,px,c] (bf16)  or  dvec[n,c] (broadcast, head pool)
+//                                                   du = du * gate[n,c] + dpool[n,c]     (SE)      du *= rowscale[n] (drop-connect)
+//   dv = act ? du * swish'(a*y+b) : du      (mode dv_given: dU already holds dv)
+//   reduce : partial sums of dv and dv*yhat per channel                       (BatchNorm backward, two-pass)
+//   apply  : dY = a * (dv - c1 - yhat*c2)   with a = gamma*invstd, c1 = mean(dv), c2 = mean(dv*yhat)
+//   se1    : A2 = gate * u (bf16, operand of the project wgrad) and dgate partials sum_px dU*u
+// ------------------------------------------------------------------------------------------------
+struct EwBwdDev {
+  EwGeom g;
+  const bf16* y; const float* scale; const float* shift; int act; int dv_given;
+  const bf16* dU; const float* dvec; const float* gate; const float* dpool; const float* rowscale;
+  const float* mean; const float* invstd;
+  const float* c1; const float* c2;       // apply
+  float* part;                            // reduce: [N*chunks][2][C]; se1: [N][chunks][C]
+  bf16* out;                              // apply: dY ; se1: A2
+};
+
+template <int MODE>   // 0 reduce, 1 apply, 2 se pass 1
+__global__ void __launch_bounds__(EW_MAX_THREADS) mclip_ew_bwd_kernel(const EwBwdDev p) {
+  extern __shared__ float ew_smem[];
+  const EwGeom& g = p.g;
+  const int cv = threadIdx.x % g.CV, pl = threadIdx.x / g.CV;
+  const int n = blockIdx.x / g.chunks, chunk = blockIdx.x % g.chunks;
+  const int p0 = chunk * g.pix_per_chunk, p1 = min(g.HW, p0 + g.pix_per_chunk);
+  float a[8], b[8], mu[8], is[8], gt[8], dp[8], dvv[8], k1[8], k2[8], acc0[8], acc1[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int c = cv * 8 + i;
+    a[i] = p.scale ? p.scale[c] : 1.f; b[i] = p.shift ? p.shift[c] : 0.f;
+    mu[i] = p.mean ? p.mean[c] : 0.f; is[i] = p.invstd ? p.invstd[c] : 1.f;
+    gt[i] = p.gate ? p.gate[(size_t)n * g.C + c] : 1.f;
+    dp[i] = p.dpool ? p.dpool[(size_t)n * g.C + c] : 0.f;
+    dvv[i] = p.dvec ? p.dvec[(size_t)n * g.C + c] : 0.f;
+    k1[i] = (MODE == 1 && p.c1) ? p.c1[c] : 0.f; k2[i] = (MODE == 1 && p.c2) ? p.c2[c] : 0.f;
+    acc0[i] = acc1[i] = 0.f;
+  }
+  const float rs = p.rowscale ? p.rowscale[n] : 1.f;
+  const size_t base = (size_t)n * g.HW * g.C + (size_t)cv * 8;
+  for (int px = p0 + pl; px < p1; px += g.PL) {
+    const size_t off = base + (size_t)px * g.C;
+    float y[8], du[8];
+    unpack8(ldg_bf16x8(p.y + off), y);
+    if (p.dU) unpack8(ldg_bf16x8(p.dU + off), du);
+    else {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) du[i] = dvv[i];
+    }
+    if (MODE == 2) {
+      float o[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        float u = swish_f(fmaf(y[i], a[i], b[i]));
+        acc0[i] = fmaf(du[i], u, acc0[i]);
+        o[i] = u * gt[i];
+      }
+      stg_bf16x8(p.out + off, pack8(o));
+    } else {
+      float o[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        float dv;
+        if (p.dv_given) dv = du[i];
+        else {
+          float t = fmaf(du[i], gt[i], dp[i]) * rs;
+          dv = p.act ? t * swish_grad_f(fmaf(y[i], a[i], b[i])) : t;
+        }
+        const float yh = (y[i] - mu[i]) * is[i];
+        if (MODE == 0) { acc0[i] += dv; acc1[i] = fmaf(dv, yh, acc1[i]); }
+        else o[i] = a[i] * (dv - k1[i] - yh * k2[i]);
+      }
+      if (MODE == 1) stg_bf16x8(p.out + off, pack8(o));
+    }
+  }
+  if (MODE == 0) {
+    float* dst = p.part + (size_t)blockIdx.x * 2 * g.C;
+    ew_block_reduce8(ew_smem, acc0, cv, pl, g.CV, g.PL, dst);
+    ew_block_reduce8(ew_smem, acc1, cv, pl, g.CV, g.PL, dst + g.C);
+  } else if (MODE == 2) {
+    ew_block_reduce8(ew_smem, acc0, cv, pl, g.CV, g.PL, p.part + ((size_t)n * g.chunks + chunk) * g.C);
+  }
+}
+
+extern "C" int mclip_ew_backward(const mclip_ew_bwd_args* a, void* stream) {
+  MCLIP_REQUIRE(a && a->y && (a->du || a->dvec), "mclip_ew_backward: null input");
+  MCLIP_REQUIRE(a->mode >= 0 && a->mode <= 2, "mclip_ew_backward: mode %d", a->mode);
+  EwBwdDev p; int threads;
+  int rc = ew_geom(a->n, a->hw, a->c, &p.g, &threads);
+  if (rc) return rc;
+  if (a->mode != 1) MCLIP_REQUIRE(a->partials && a->chunks == p.g.chunks, "mclip_ew_backward: chunks=%d, expected %d", a->chunks, p.g.chunks);
+  if (a->mode != 0) MCLIP_REQUIRE(a->out, "mclip_ew_backward: null output");
+  p.y = (const bf16*)a->y; p.scale = a->scale; p.shift = a->shift; p.act = a->act; p.dv_given = a->dv_given;
+  p.dU = (const bf16*)a->du; p.dvec = a->dvec; p.gate = a->gate; p.dpool = a->dpool; p.rowscale = a->rowscale;
+  p.mean = a->mean; p.invstd = a->invstd; p.c1 = a->c1; p.c2 = a->c2; p.part = a->partials; p.out = (bf16*)a->out;
+  const int smem = p.g.PL * p.g.C * 4;
+  const int grid = a->n * p.g.chunks;
+  if (a->mode == 0) mclip_ew_bwd_kernel<0><<<grid, threads, smem, (cudaStream_t)stream>>>(p);
+  else if (a->mode == 1) mclip_ew_bwd_kernel<1><<<grid, threads, smem, (cudaStream_t)stream>>>(p);
+  else mclip_ew_bwd_kernel<2><<<grid, threads, smem, (cudaStream_t)stream>>>(p);
+  MCLIP_CHECK_LAUNCH();
+  return MCLIP_OK;
+}
+
+// BatchNorm backward, second half: dgamma, dbeta, and the two means used by the apply pass
+__global__ void mclip_bn_bwd_finalize_kernel(const float* __restrict__ partials, int slots, int C, double count, int training, float* dgamma, float* dbeta,
+                                             int accumulate, float* c1, float* c2) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  double s = 0.0, q = 0.0;
+  for (int k = 0; k < slots; ++k) { s += (double)partials[((size_t)k * 2 + 0) * C + c]; q += (double)partials[((size_t)k * 2 + 1) * C + c]; }
+  if (dgamma) dgamma[c] = accumulate ? dgamma[c] + (float)q : (float)q;
+  if (dbeta) dbeta[c] = accumulate ? dbeta[c] + (float)s : (float)s;
+  c1[c] = training ? (float)(s / count) : 0.f;
+  c2[c] = training ? (float)(q / count) : 0.f;
+}
+
+extern "C" int mclip_bn_bwd_finalize(const float* partials, int slots, int c, long long count, int training, float* dgamma, float* dbeta, int accumulate,
+                                     float* c1, float* c2, void* stream) {
+  MCLIP_REQUIRE(partials && c1 && c2 && slots > 0 && count > 0, "mclip_bn_bwd_finalize: bad arguments");
+  mclip_bn_bwd_finalize_kernel<<<ceil_div(c, 128), 128, 0, (cudaStream_t)stream>>>(partials, slots, c, (double)count, training, dgamma, dbeta, accumulate, c1, c2);
+  MCLIP_CHECK_LAUNCH();
+  return MCLIP_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// squeeze-excite backward
+//   k1 (per sample): dz2 = dg*g*(1-g) ; dh = W2^T dz2 ; dz1 = dh*swish'(z1) ; ds = W1^T dz1 ; dpool = ds/HW
+//   k2 (per output element): dW2 = sum_n dz2 h^T ; db2 = sum_n dz2 ; dW1 = sum_n dz1 s^T ; db1 = sum_n dz1
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) mclip_se_bwd1_kernel(const float* __restrict__ dg_part, int chunks, int C, int Cse, float inv_hw,
+                                                            const float* __restrict__ W1, const float* __restrict__ W2, const float* __restrict__ z1,
+                                                            const float* __restrict__ gate, float* __restrict__ dz2_out, float* __restrict__ dz1_out,
+                                                            float* __restrict__ dpool) {
+  extern __shared__ float se_smem[];
+  float* dz2 = se_smem;          // [C]
+  float* dz1 = se_smem + C;      // [Cse]
+  const int n = blockIdx.x;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float dg = 0.f;
+    for (int k = 0; k < chunks; ++k) dg += dg_part[((size_t)n * chunks + k) * C + c];
+    const float g = gate[(size_t)n * C + c];
+    const float v = dg * g * (1.f - g);
+    dz2[c] = v;
+    dz2_out[(size_t)n * C + c] = v;
+  }
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+  for (int j = warp; j < Cse; j += nw) {
+    float v = 0.f;
+    for (int c = lane; c < C; c += 32) v = fmaf(W2[(size_t)c * Cse + j], dz2[c], v);
+    v = warp_sum(v);
+    if (lane == 0) {
+      const float z = z1[(size_t)n * Cse + j];
+      const float s = sigmoid_precise(z);
+      v *= s * (1.f + z * (1.f - s));
+      dz1[j] = v;
+      dz1_out[(size_t)n * Cse + j] = v;
+    }
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float v = 0.f;
+    for (int j = 0; j < Cse; ++j) v = fmaf(W1[(size_t)j * C + c], dz1[j], v);
+    dpool[(size_t)n * C + c] = v * inv_hw;
+  }
+}
+
+__global__ void mclip_se_bwd2_kernel(int N, int C, int Cse, const float* __restrict__ dz2, const float* __restrict__ dz1, const float* __restrict__ z1,
+                                     const float* __restrict__ s, float* dW1, float* db1, float* dW2, float* db2, int accumulate) {
+  const int total = 2 * C * Cse + C + Cse;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    float v = 0.f;
+    float* dst;
+    if (i < C * Cse) {                       // dW2[c][j] = sum_n dz2[n,c] * h[n,j]
+      const int c = i / Cse, j = i % Cse;
+      for (int n = 0; n < N; ++n) { const float z = z1[(size_t)n * Cse + j]; v = fmaf(dz2[(size_t)n * C + c], z * sigmoid_precise(z), v); }
+      dst = dW2 + i;
+    } else if (i < 2 * C * Cse) {            // dW1[j][c] = sum_n dz1[n,j] * s[n,c]
+      const int k = i - C * Cse, j = k / C, c = k % C;
+      for (int n = 0; n < N; ++n) v = fmaf(dz1[(size_t)n * Cse + j], s[(size_t)n * C + c], v);
+      dst = dW1 + k;
+    } else if (i < 2 * C * Cse + C) {
+      const int c = i - 2 * C * Cse;
+      for (int n = 0; n < N; ++n) v += dz2[(size_t)n * C + c];
+      dst = db2 + c;
+    } else {
+      const int j = i - 2 * C * Cse - C;
+      for (int n = 0; n < N; ++n) v += dz1[(size_t)n * Cse + j];
+      dst = db1 + j;
+    }
+    *dst = accumulate ? *dst + v : v;
+  }
+}
+
+extern "C" int mclip_se_fc_backward(const mclip_se_args* a, void* stream) {
+  MCLIP_REQUIRE(a && a->dgate_partials && a->w1 && a->w2 && a->z1 && a->gate && a->pooled && a->dz2 && a->dz1 && a->dpool && a->dw1 && a->db1 && a->dw2 && a->db2,
+                "mclip_se_fc_backward: null operand");
+  const int smem = (a->c + a->cse) * 4;
+  mclip_se_bwd1_kernel<<<a->n, 256, smem, (cudaStream_t)stream>>>(a->dgate_partials, a->chunks, a->c, a->cse, 1.0f / (float)a->hw, a->w1, a->w2, a->z1, a->gate,
+                                                                   a->dz2, a->dz1, a->dpool);
+  MCLIP_CHECK_LAUNCH();
+  const int total = 2 * a->c * a->cse + a->c + a->cse;
+  int grid = ceil_div(total, 256);
+  mclip_se_bwd2_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(a->n, a->c, a->cse, a->dz2, a->dz1, a->z1, a->pooled, a->dw1, a->db1, a->dw2, a->db2, a->accumulate);
+  MCLIP_CHECK_LAUNCH();
+  return MCLIP_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// fp32 master weights -> bf16 operands (straight and transposed), table driven: one launch for a whole tower
+// ------------------------------------------------------------------------------------------------
+__global__ void mclip_weight_prep_kernel(const mclip_prep_entry* __restrict__ table, int n_entries) {
+  for (int e = blockIdx.y; e < n_entries; e += gridDim.y) {
+    const mclip_prep_entry t = table[e];
+    const long long total = (long long)t.rows * t.cols;
+    const float* src = (const float*)t.src;
+    bf16* dst = (bf16*)t.dst;
+    bf16* dstT = (bf16*)t.dst_t;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+      const bf16 v = __float2bfloat16_rn(src[i]);
+      if (dst) dst[i] = v;
+      if (dstT) { const long long r = i / t.cols, c = i % t.cols; dstT[c * t.rows + r] = v; }
+    }
+  }
+}
+
+extern "C" int mclip_weight_prep(const void* table_dev, int n_entries, void* stream) {
+  MCLIP_REQUIRE(table_dev && n_entries > 0, "mclip_weight_prep: empty table");
+  dim3 grid(16, n_entries < 1024 ? n_entries : 1024);
+  mclip_weight_prep_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const mclip_prep_entry*)table_dev, n_entries);
+  MCLIP_CHECK_LAUNCH();
+  return MCLIP_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// small row-wise ops of the CLIP head: fp32 -> bf16 cast, L2 normalisation fwd/bwd (clip.py:90-91), bias gradient
+// ------------------------------------------------------------------------------------------------
+__global__ void mclip_cast_bf16_kernel(const float* __restrict__ in, bf16* __restrict__ out, long long n) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) out[i] = __float2bfloat16_rn(in[i]);
+}
+extern "C" int mclip_cast_bf16(const float* in, void* out, long long n, void* stream) {
+  MCLIP_REQUIRE(in && out && n > 0, "mclip_cast_bf16: bad arguments");
+  int grid = (int)((n + 255) / 256); if (grid > mclip_num_sms() * 8) grid = mclip_num_sms() * 8;
+  mclip_cast_bf16_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(in, (bf16*)out, n);
+  MCLIP_CHECK_LAUNCH();
+  return MCLIP_OK;
+}
+
+// one warp per row: e = x / ||x||   (no epsilon, clip.py:90-91); x is bf16 (projection GEMM output)
+__global__ void mclip_l2norm_fwd_kernel(const bf16* __restrict__ x, float* __restrict__ e, float* __restrict__ norm, int rows, int D) {
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  float ss = 0.f;
+  for (int d = lane; d < D; d += 32) { float v = __bfloat162float(x[(size_t)row * D + d]); ss = fmaf(v, v, ss); }
+  ss = warp_sum(ss);
+  const float nrm = sqrtf(ss), inv = 1.0f / nrm;
+  for (int d = lane; d < D; d += 32) e[(size_t)row * D + d] = __bfloat162float(x[(size_t)row * D + d]) * inv;
+  if (lane == 0) norm[row] = nrm;
+}
+// dx = (de - e * <e,de>) / ||x||  -> bf16 (operand of the projection dgrad/wgrad GEMMs)
+__global__ void mclip_l2norm_bwd_kernel(const float* __restrict__ e, const float* __restrict__ de, const float* __restrict__ norm, bf16* __restrict__ dx,
+                                        int rows, int D) {
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  float dot = 0.f;
+  for (int d = lane; d < D; d += 32) dot = fmaf(e[(size_t)row * D + d], de[(size_t)row * D + d], dot);
+  dot = warp_sum(dot);
+  const float inv = 1.0f / norm[row];
+  for (int d = lane; d < D; d += 32) dx[(size_t)row * D + d] = __float2bfloat16_rn((de[(size_t)row * D + d] - e[(size_t)row * D + d] * dot) * inv);
+}
+extern "C" int mclip_l2norm_forward(const void* x, float* e, float* norm, int rows, int d, void* stream) {
+  MCLIP_REQUIRE(x && e && norm && rows > 0 && d > 0, "mclip_l2norm_forward: bad arguments");
+  mclip_l2norm_fwd_kernel<<<ceil_div(rows, 4), 128, 0, (cudaStream_t)stream>>>((const bf16*)x, e, norm, rows, d);
+  MCLIP_CHECK_LAUNCH();
+  return MCLIP_OK;
+}
+extern "C" int mclip_l2norm_backward(const float* e, const float* de, const float* norm, void* dx, int rows, int d, void* stream) {
+  MCLIP_REQUIRE(e && de && norm && dx && rows > 0 && d > 0, "mclip_l2norm_backward: bad arguments");
+  mclip_l2norm_bwd_kernel<<<ceil_div(rows, 4), 128, 0, (cudaStream_t)stream>>>(e, de, norm, (bf16*)dx, rows, d);
+  MCLIP_CHECK_LAUNCH();
+  return MCLIP_OK;
+}
+
+// column sums of a bf16 [rows, cols] matrix -> fp32 (bias gradients of Linear layers)
+__global__ void mclip_colsum_kernel(const bf16* __restrict__ x, float* __restrict__ out, int rows, int cols, long long ld, int accumulate) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= cols) return;
+  float s = 0.f;
+  for (int r = 0; r < rows; ++r) s += __bfloat162float(x[(size_t)r * ld + c]);
+  out[c] = accumulate ? out[c] + s : s;
+}
+extern "C" int mclip_colsum(const void* x, float* out, int rows, int cols, long long ld, int accumulate, void* stream) {
+  MCLIP_REQUIRE(x && out && rows > 0 && cols > 0, "mclip_colsum: bad arguments");
+  mclip_colsum_kernel<<<ceil_div(cols, 128), 128, 0, (cudaStream_t)stream>>>((const bf16*)x, out, rows, cols, ld, accumulate);
+  MCLIP_CHECK_LAUNCH();
+  return MCLIP_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// AdamW over one flat fp32 parameter buffer (torch.optim.AdamW semantics: decoupled weight decay,
+// bias-corrected moments; breastclip/optimizer/__init__.py:23-31 builds AdamW(lr, weight_decay) on all params)
+// ------------------------------------------------------------------------------------------------
+__global__ void mclip_adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v, long long n, float lr,
+                                   float beta1, float beta2, float eps, float wd, float bc1, float bc2_sqrt, float grad_scale) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const float gi = g[i] * grad_scale;
+    float pi = p[i] * (1.f - lr * wd);
+    const float mi = beta1 * m[i] + (1.f - beta1) * gi;
+    const float vi = beta2 * v[i] + (1.f - beta2) * gi * gi;
+    m[i] = mi; v[i] = vi;
+    const float denom = sqrtf(vi) / bc2_sqrt + eps;
+    pi -= (lr / bc1) * (mi / denom);
+    p[i] = pi;
+  }
+}
+extern "C" int mclip_adamw_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, long long n, float lr, float beta1, float beta2,
+                                float eps, float weight_decay, long long step, float grad_scale, void* stream) {
+  MCLIP_REQUIRE(param && grad && exp_avg && exp_avg_sq && n > 0 && step >= 1, "mclip_adamw_step: bad arguments");
+  const float bc1 = 1.f - powf(beta1, (float)step);
+  const float bc2 = sqrtf(1.f - powf(beta2, (float)step));
+  int grid = (int)((n + 255) / 256); if (grid > mclip_num_sms() * 8) grid = mclip_num_sms() * 8;
+  mclip_adamw_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(param, grad, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps, weight_decay, bc1, bc2, grad_scale);
+  MCLIP_CHECK_LAUNCH();
+  return MCLIP_OK;
+}

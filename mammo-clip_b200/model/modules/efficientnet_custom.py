@@ -1,0 +1,382 @@
+"""EfficientNet-B0..B7 image encoder on hand-written sm_100a kernels, drop-in for the reference class.
+
+Mirrors `breastclip/model/modules/efficientnet_custom.py` (EfficientNet :143-411, MBConvBlock :36-140): same constructor
+entry points (`from_name`, `from_pretrained`), same `forward` contract (tensor -> pooled [B,out_dim]; dict with "image"
+-> (pooled, raw_features), :287-313), same state-dict keys and tensor shapes (checkpoints interchange).
+All arithmetic runs in libmclip_b200.so through one torch.autograd.Function spanning the whole tower; activations are
+NHWC bf16, only PRE-BatchNorm conv outputs are kept for backward (BN+swish are re-applied on load).
+"""
+import math
+from dataclasses import dataclass
+from typing import List, Tuple
+
+import torch
+from torch import nn
+
+from ... import ops
+
+# ----------------------------------------------------------------------------------------------- geometry
+# (repeats, kernel, stride, expand, in, out): efficient_net_custom_utils.py:502-510
+_STAGES = ((1, 3, 1, 1, 32, 16), (2, 3, 2, 6, 16, 24), (2, 5, 2, 6, 24, 40), (3, 3, 2, 6, 40, 80),
+           (3, 5, 1, 6, 80, 112), (4, 5, 2, 6, 112, 192), (1, 3, 1, 6, 192, 320))
+# name -> (width, depth, nominal res, dropout): efficient_net_custom_utils.py:466-478
+_PARAMS = {"efficientnet-b0": (1.0, 1.0, 224, 0.2), "efficientnet-b1": (1.0, 1.1, 240, 0.2), "efficientnet-b2": (1.1, 1.2, 260, 0.3),
+           "efficientnet-b3": (1.2, 1.4, 300, 0.3), "efficientnet-b4": (1.4, 1.8, 380, 0.4), "efficientnet-b5": (1.6, 2.2, 456, 0.4),
+           "efficientnet-b6": (1.8, 2.6, 528, 0.5), "efficientnet-b7": (2.0, 3.1, 600, 0.5)}
+VALID_MODELS = tuple(_PARAMS)
+BN_MOMENTUM, BN_EPS, DROP_CONNECT_RATE, SE_RATIO = 0.01, 1e-3, 0.2, 0.25
+
+
+def _round_filters(ch, width, divisor=8):
+    ch = ch * width
+    new = max(divisor, int(ch + divisor / 2) // divisor * divisor)
+    if new < 0.9 * ch:
+        new += divisor
+    return int(new)
+
+
+def _static_pad(size, k, s):
+    """(before, after, out) of Conv2dStaticSamePadding along one axis (efficient_net_custom_utils.py:255-271)."""
+    out = -(-size // s)
+    total = max((out - 1) * s + k - size, 0)
+    return total // 2, total - total // 2, out
+
+
+@dataclass
+class BlockGeom:
+    cin: int
+    cexp: int
+    cout: int
+    k: int
+    s: int
+    expand: bool
+    cse: int
+    pads: Tuple[int, int, int, int]     # (left, right, top, bottom), frozen from the NOMINAL resolution
+    skip: bool
+
+
+@dataclass
+class NetGeom:
+    stem_out: int
+    stem_pads: Tuple[int, int, int, int]
+    blocks: List[BlockGeom]
+    head_out: int
+    dropout: float
+
+
+def net_geometry(name: str) -> NetGeom:
+    width, depth, res, dropout = _PARAMS[name]
+    h = w = res
+    l, r, w2 = _static_pad(w, 3, 2)
+    t, b, h2 = _static_pad(h, 3, 2)
+    stem_pads = (l, r, t, b)
+    h, w = h2, w2
+    blocks = []
+    for rep, k, s, e, cin, cout in _STAGES:
+        cin, cout = _round_filters(cin, width), _round_filters(cout, width)
+        for i in range(int(math.ceil(depth * rep))):
+            bi, bs = (cin, s) if i == 0 else (cout, 1)
+            l, r, wo = _static_pad(w, k, bs)
+            t, b, ho = _static_pad(h, k, bs)
+            blocks.append(BlockGeom(bi, bi * e, cout, k, bs, e != 1, max(1, int(bi * SE_RATIO)), (l, r, t, b), bs == 1 and bi == cout))
+            h, w = ho, wo
+    return NetGeom(_round_filters(32, width), stem_pads, blocks, _round_filters(1280, width), dropout)
+
+
+# ----------------------------------------------------------------------------------------------- parameter holders
+class _ConvParams(nn.Module):
+    """Holds `weight` (OIHW, as nn.Conv2d) and optional `bias`; default init identical to nn.Conv2d."""
+
+    def __init__(self, cout, cin_per_group, k, bias=False):
+        super().__init__()
+        self.weight = nn.Parameter(torch.empty(cout, cin_per_group, k, k))
+        self.bias = nn.Parameter(torch.empty(cout)) if bias else None
+        nn.init.kaiming_uniform_(self.weight, a=math.sqrt(5))
+        if bias:
+            bound = 1 / math.sqrt(cin_per_group * k * k)
+            nn.init.uniform_(self.bias, -bound, bound)
+
+
+class _BNParams(nn.Module):
+    def __init__(self, c):
+        super().__init__()
+        self.weight = nn.Parameter(torch.ones(c))
+        self.bias = nn.Parameter(torch.zeros(c))
+        self.register_buffer("running_mean", torch.zeros(c))
+        self.register_buffer("running_var", torch.ones(c))
+        self.register_buffer("num_batches_tracked", torch.tensor(0, dtype=torch.long))
+        self.momentum, self.eps = BN_MOMENTUM, BN_EPS
+
+
+class MBConvBlock(nn.Module):
+    """Parameter container with the reference's attribute names (efficientnet_custom.py:50-89)."""
+
+    def __init__(self, g: BlockGeom):
+        super().__init__()
+        self.geom = g
+        if g.expand:
+            self._expand_conv = _ConvParams(g.cexp, g.cin, 1)
+            self._bn0 = _BNParams(g.cexp)
+        self._depthwise_conv = _ConvParams(g.cexp, 1, g.k)
+        self._bn1 = _BNParams(g.cexp)
+        self._se_reduce = _ConvParams(g.cse, g.cexp, 1, bias=True)
+        self._se_expand = _ConvParams(g.cexp, g.cse, 1, bias=True)
+        self._project_conv = _ConvParams(g.cout, g.cexp, 1)
+        self._bn2 = _BNParams(g.cout)
+
+
+# ----------------------------------------------------------------------------------------------- the engine
+def _bn_fin(part, count, bn: _BNParams, training):
+    return ops.bn_finalize(part, count, bn.weight, bn.bias, bn.running_mean, bn.running_var, bn.num_batches_tracked, training, bn.momentum, bn.eps)
+
+
+class _WeightCache:
+    """bf16 copies (and transposes) of the 1x1-conv weights, refreshed by ONE table-driven kernel per step."""
+
+    def __init__(self, net):
+        dev = net._conv_stem.weight.device
+        self.entries, self.bf16, self.bf16_t = [], {}, {}
+
+        def add(key, w, straight, transposed):
+            w2 = w.detach().view(w.shape[0], -1)
+            d = torch.empty_like(w2, dtype=torch.bfloat16) if straight else None
+            dt = torch.empty((w2.shape[1], w2.shape[0]), dtype=torch.bfloat16, device=dev) if transposed else None
+            self.entries.append((w2, d, dt))
+            self.bf16[key], self.bf16_t[key] = d, dt
+
+        for i, blk in enumerate(net._blocks):
+            if blk.geom.expand:
+                add(("e", i), blk._expand_conv.weight, True, True)
+            add(("p", i), blk._project_conv.weight, False, True)
+        add(("h",), net._conv_head.weight, True, True)
+        self.table = ops.weight_prep(self.entries, dev)
+        self.key = self._key(net)
+
+    @staticmethod
+    def _key(net):
+        return tuple(p.data_ptr() for p in net.parameters())
+
+    def refresh(self):
+        ops.weight_prep_run(self.table, len(self.entries))
+
+
+def _forward(net, images, training, drop_rowscales, dropout_mult, want_raw):
+    """Returns (features [N,Chead] fp32, saved state for backward, raw head activation or None)."""
+    geom = net.geom
+    n, _, h_in, w_in = images.shape
+    wc = net._weights()
+    wc.refresh()
+    S = {"images": images, "training": training, "blocks": []}
+    y, st = ops.stem_forward(images, net._conv_stem.weight, geom.stem_pads, want_stats=training)
+    h, w = y.shape[1], y.shape[2]
+    bn = _bn_fin(st, n * h * w, net._bn0, training)
+    S["stem"] = (y, bn)
+    pending = (y, bn)      # a pre-BN tensor whose BN+swish is applied by the consumer
+    x = None               # materialised block input [N,H,W,C] bf16
+    for i, blk in enumerate(net._blocks):
+        g = blk.geom
+        B = {"x_in": x, "h": h, "w": w}
+        if g.expand:
+            y0, st = ops.gemm_tn(x.view(n * h * w, g.cin), wc.bf16[("e", i)], want_stats=training)
+            y0 = y0.view(n, h, w, g.cexp)
+            bn0 = _bn_fin(st, n * h * w, blk._bn0, training)
+            B["y0"], B["bn0"] = y0, bn0
+            dw_in, dw_bn = y0, bn0
+        elif pending is not None:
+            dw_in, dw_bn = pending
+            B["from_stem"] = True
+        else:
+            dw_in, dw_bn = x, None
+        y1, st = ops.dwconv_forward(dw_in, blk._depthwise_conv.weight, g.k, g.s, g.pads, bn=dw_bn, want_stats=training)
+        ho, wo = y1.shape[1], y1.shape[2]
+        bn1 = _bn_fin(st, n * ho * wo, blk._bn1, training)
+        u, pool = ops.ew_forward(y1.view(n, ho * wo, g.cexp), bn=bn1, act=1, write=True, pool=True)
+        w1, w2 = blk._se_reduce.weight.view(g.cse, g.cexp), blk._se_expand.weight.view(g.cexp, g.cse)
+        pooled, z1, gate = ops.se_fc(pool, ho * wo, w1, blk._se_reduce.bias, w2, blk._se_expand.bias)
+        wg = ops.se_scale_weights(blk._project_conv.weight.view(g.cout, g.cexp), gate)
+        y2, st = ops.gemm_tn(u, wg, want_stats=training)                     # [N, ho*wo, cout], per-sample weights
+        del u, wg
+        bn2 = _bn_fin(st, n * ho * wo, blk._bn2, training)
+        rs = drop_rowscales.get(i) if (g.skip and drop_rowscales) else None
+        x_out, _ = ops.ew_forward(y2, bn=bn2, act=0, rowscale=rs, residual=x.view(n, h * w, g.cin) if g.skip else None)
+        B.update(y1=y1, bn1=bn1, pooled=pooled, z1=z1, gate=gate, y2=y2, bn2=bn2, rowscale=rs, ho=ho, wo=wo)
+        S["blocks"].append(B)
+        x, h, w, pending = x_out.view(n, ho, wo, g.cout), ho, wo, None
+    yh, st = ops.gemm_tn(x.view(n * h * w, x.shape[-1]), wc.bf16[("h",)], want_stats=training)
+    yh = yh.view(n, h * w, geom.head_out)
+    bnh = _bn_fin(st, n * h * w, net._bn1, training)
+    raw, pool = ops.ew_forward(yh, bn=bnh, act=1, write=want_raw, pool=True)
+    feat = ops.pool_finalize(pool, h * w, dropout_mult)
+    S.update(x_last=x, yh=yh, bnh=bnh, h=h, w=w, dropout_mult=dropout_mult)
+    if want_raw:
+        raw = raw.view(n, h, w, geom.head_out).permute(0, 3, 1, 2).float()
+    return feat, S, raw
+
+
+def _bn_backward(y3, bn, training, bnp: _BNParams, grads, prefix, act, du=None, dvec=None, gate=None, dpool=None, rowscale=None):
+    """Two-pass BatchNorm(+swish) backward over y3 [N,HW,C]; returns dY (bf16) and fills grads of gamma/beta."""
+    part = ops.ew_backward(0, y3, bn, act, du=du, dvec=dvec, gate=gate, dpool=dpool, rowscale=rowscale)
+    dg, db = torch.empty_like(bnp.weight), torch.empty_like(bnp.bias)
+    c1, c2 = ops.bn_bwd_finalize(part, bn.count, training, dg, db)
+    grads[prefix + ".weight"], grads[prefix + ".bias"] = dg, db
+    return ops.ew_backward(1, y3, bn, act, du=du, dvec=dvec, gate=gate, dpool=dpool, rowscale=rowscale, c1=c1, c2=c2)
+
+
+def _backward(net, S, dfeat):
+    """dfeat: [N,Chead] fp32.  Returns {state-dict key: gradient tensor} for every trainable parameter."""
+    geom, wc, training = net.geom, net._weights(), S["training"]
+    grads = {}
+    n, h, w = dfeat.shape[0], S["h"], S["w"]
+    dvec = dfeat * (1.0 / (h * w))
+    if S["dropout_mult"] is not None:
+        dvec = dvec * S["dropout_mult"]
+    dvec = dvec.contiguous()
+    x_last = S["x_last"]
+    dyh = _bn_backward(S["yh"], S["bnh"], training, net._bn1, grads, "_bn1", 1, dvec=dvec)
+    dyh2 = dyh.view(n * h * w, geom.head_out)
+    grads["_conv_head.weight"] = ops.gemm_wgrad(dyh2, x_last.view(n * h * w, -1)).view_as(net._conv_head.weight)
+    dx = ops.gemm_tn(dyh2, wc.bf16_t[("h",)]).view(x_last.shape)
+    del dyh, dyh2
+    for i in reversed(range(len(net._blocks))):
+        blk, B = net._blocks[i], S["blocks"][i]
+        g, pre = blk.geom, f"_blocks.{i}."
+        h, w, ho, wo = B["h"], B["w"], B["ho"], B["wo"]
+        dxo = dx.view(n, ho * wo, g.cout)
+        dy2 = _bn_backward(B["y2"], B["bn2"], training, blk._bn2, grads, pre + "_bn2", 0, du=dxo, rowscale=B["rowscale"])
+        da2 = ops.gemm_tn(dy2.view(n * ho * wo, g.cout), wc.bf16_t[("p", i)]).view(n, ho * wo, g.cexp)
+        y1 = B["y1"].view(n, ho * wo, g.cexp)
+        a2, dgp = ops.ew_backward(2, y1, B["bn1"], 1, du=da2, gate=B["gate"])
+        grads[pre + "_project_conv.weight"] = ops.gemm_wgrad(dy2.view(n * ho * wo, g.cout), a2.view(n * ho * wo, g.cexp)).view_as(blk._project_conv.weight)
+        del a2, dy2
+        w1, w2 = blk._se_reduce.weight.view(g.cse, g.cexp), blk._se_expand.weight.view(g.cexp, g.cse)
+        dw1, db1, dw2, db2 = (torch.empty_like(t) for t in (blk._se_reduce.weight, blk._se_reduce.bias, blk._se_expand.weight, blk._se_expand.bias))
+        dpool = ops.se_fc_backward(dgp, ho * wo, w1, w2, B["pooled"], B["z1"], B["gate"], dw1, db1, dw2, db2)
+        grads[pre + "_se_reduce.weight"], grads[pre + "_se_reduce.bias"] = dw1, db1
+        grads[pre + "_se_expand.weight"], grads[pre + "_se_expand.bias"] = dw2, db2
+        dy1 = _bn_backward(y1, B["bn1"], training, blk._bn1, grads, pre + "_bn1", 1, du=da2, gate=B["gate"], dpool=dpool)
+        del da2
+        dy1 = dy1.view(n, ho, wo, g.cexp)
+        ddw = torch.empty_like(blk._depthwise_conv.weight)
+        grads[pre + "_depthwise_conv.weight"] = ddw
+        if g.expand:
+            y0, bn0 = B["y0"], B["bn0"]
+            dv0, bnp = ops.dwconv_backward(y0, blk._depthwise_conv.weight, g.k, g.s, g.pads, dy1, ddw, bn=bn0)
+            dg0, db0 = torch.empty_like(blk._bn0.weight), torch.empty_like(blk._bn0.bias)
+            c1, c2 = ops.bn_bwd_finalize(bnp, bn0.count, training, dg0, db0)
+            grads[pre + "_bn0.weight"], grads[pre + "_bn0.bias"] = dg0, db0
+            dy0 = ops.ew_backward(1, y0.view(n, h * w, g.cexp), bn0, 0, du=dv0.view(n, h * w, g.cexp), dv_given=True, c1=c1, c2=c2)
+            del dv0
+            dy0 = dy0.view(n * h * w, g.cexp)
+            x_in = B["x_in"].view(n * h * w, g.cin)
+            grads[pre + "_expand_conv.weight"] = ops.gemm_wgrad(dy0, x_in).view_as(blk._expand_conv.weight)
+            dx = ops.gemm_tn(dy0, wc.bf16_t[("e", i)], residual=dx.view(n * h * w, g.cin) if g.skip else None).view(n, h, w, g.cin)
+            del dy0
+        elif B.get("from_stem"):
+            ys, bns = S["stem"]
+            dvs, bnp = ops.dwconv_backward(ys, blk._depthwise_conv.weight, g.k, g.s, g.pads, dy1, ddw, bn=bns)
+            dgs, dbs = torch.empty_like(net._bn0.weight), torch.empty_like(net._bn0.bias)
+            c1, c2 = ops.bn_bwd_finalize(bnp, bns.count, training, dgs, dbs)
+            grads["_bn0.weight"], grads["_bn0.bias"] = dgs, dbs
+            cs = geom.stem_out
+            dys = ops.ew_backward(1, ys.view(n, h * w, cs), bns, 0, du=dvs.view(n, h * w, cs), dv_given=True, c1=c1, c2=c2)
+            dws = torch.empty_like(net._conv_stem.weight)
+            ops.stem_wgrad(S["images"], dys.view(n, h, w, cs), geom.stem_pads, dws)
+            grads["_conv_stem.weight"] = dws
+            dx = None
+        else:
+            dxd, _ = ops.dwconv_backward(B["x_in"], blk._depthwise_conv.weight, g.k, g.s, g.pads, dy1, ddw, bn=None)
+            if g.skip:
+                dxd, _ = ops.ew_forward(dxd.view(n, h * w, g.cin), residual=dx.view(n, h * w, g.cin))
+            dx = dxd.view(n, h, w, g.cin)
+        del dy1
+    return grads
+
+
+class _EncoderFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, net, images, drop_rowscales, dropout_mult, want_raw, *params):
+        feat, S, raw = _forward(net, images, net.training, drop_rowscales, dropout_mult, want_raw)
+        ctx.net, ctx.S = net, S
+        if want_raw:
+            ctx.mark_non_differentiable(raw)
+            return feat, raw
+        return feat
+
+    @staticmethod
+    def backward(ctx, dfeat, *unused):
+        net = ctx.net
+        grads = _backward(net, ctx.S, dfeat.contiguous().float())
+        ctx.S = None
+        out = [grads.get(name) for name, _ in net.named_parameters()]
+        return (None, None, None, None, None, *out)
+
+
+class EfficientNet(nn.Module):
+    """Drop-in for the reference EfficientNet (efficientnet_custom.py:143).  `num_classes`, `include_top`, `advprop`,
+    `weights_path` are accepted for signature compatibility; this copy has no `_fc` either (:211 is commented out)."""
+
+    def __init__(self, model_name="efficientnet-b2", stochastic=True):
+        super().__init__()
+        if model_name not in VALID_MODELS:
+            raise ValueError("model_name should be one of: " + ", ".join(VALID_MODELS))
+        self.model_name = model_name
+        self.geom = net_geometry(model_name)
+        g = self.geom
+        self._conv_stem = _ConvParams(g.stem_out, 3, 3)
+        self._bn0 = _BNParams(g.stem_out)
+        self._blocks = nn.ModuleList([MBConvBlock(b) for b in g.blocks])
+        self._conv_head = _ConvParams(g.head_out, g.blocks[-1].cout, 1)
+        self._bn1 = _BNParams(g.head_out)
+        self.out_dim = g.head_out
+        self.stochastic = stochastic      # False: drop-connect / dropout off in train mode (parity runs)
+        self._wcache = None
+
+    @classmethod
+    def from_name(cls, model_name, in_channels=3, **override_params):
+        if in_channels != 3:
+            raise ValueError("the B200 stem kernel is specialised for 3 input channels")
+        return cls(model_name)
+
+    @classmethod
+    def from_pretrained(cls, model_name, weights_path=None, advprop=False, in_channels=3, num_classes=1000, **override_params):
+        """Reference :340-373 downloads ImageNet weights; offline, only a local `weights_path` state dict is honoured."""
+        model = cls.from_name(model_name, in_channels=in_channels)
+        if isinstance(weights_path, str):
+            sd = torch.load(weights_path, map_location="cpu")
+            sd = {k: v for k, v in sd.items() if not k.startswith("_fc.")}
+            model.load_state_dict(sd, strict=False)
+        return model
+
+    def _weights(self):
+        if self._wcache is None or self._wcache.key != _WeightCache._key(self):
+            self._wcache = _WeightCache(self)
+        return self._wcache
+
+    def _stochastic_inputs(self, n, device):
+        """Per-sample drop-connect scales mask/keep (efficient_net_custom_utils.py:145-154; rate = 0.2*idx/len, :277-279)
+        and the dropout multiplier of the pooled features (:312)."""
+        if not (self.training and self.stochastic):
+            return None, None
+        scales, nb = {}, len(self._blocks)
+        for i, blk in enumerate(self._blocks):
+            rate = DROP_CONNECT_RATE * float(i) / nb
+            if blk.geom.skip and rate > 0:
+                keep = 1.0 - rate
+                scales[i] = torch.floor(keep + torch.rand(n, device=device)) / keep
+        p = self.geom.dropout
+        mult = (torch.rand(n, self.out_dim, device=device) >= p).float() / (1.0 - p)
+        return scales, mult
+
+    def forward(self, inputs):
+        as_dict = isinstance(inputs, dict) and "image" in inputs
+        images = inputs["image"] if as_dict else inputs
+        if not images.is_cuda:
+            raise RuntimeError("mammoclip_b200.EfficientNet runs on a B200 only (no CPU fallback)")
+        images = images.float()
+        scales, mult = self._stochastic_inputs(images.shape[0], images.device)
+        params = [p for _, p in self.named_parameters()]
+        out = _EncoderFn.apply(self, images, scales, mult, as_dict, *params)
+        return out if as_dict else out
+
+    def extract_features(self, inputs):
+        return self.forward({"image": inputs})[1]

@@ -15,9 +15,9 @@ def _require_cuda(*tensors):
 
 # ------------------------------------------------------------------------------------------------ GEMMs
 
-def gemm_tn(a, b, out=None, bias=None, residual=None, act=0, want_stats=False):
+def gemm_tn(a, b, out=None, bias=None, residual=None, act=0, want_stats=None):
     """out[b,m,n] = epi(sum_k a[b,m,k] * w[b|0,n,k]).  a: [M,K] or [Bt,M,K] bf16; b: [N,K] or [Bt,N,K] bf16.
-    Returns out (bf16) or (out, stats[slots,2,N] fp32) when want_stats."""
+    want_stats=None: returns out (bf16).  want_stats=True/False: returns (out, stats[slots,2,N] fp32 or None)."""
     _require_cuda(a, b)
     assert a.dtype == torch.bfloat16 and b.dtype == torch.bfloat16
     a3 = a if a.dim() == 3 else a.unsqueeze(0)
@@ -45,7 +45,7 @@ def gemm_tn(a, b, out=None, bias=None, residual=None, act=0, want_stats=False):
         stats = torch.empty((slots, 2, n), dtype=torch.float32, device=a.device)
         g.stats, g.stat_slots = stats.data_ptr(), slots
     check(lib().mclip_gemm_tn(C.byref(g), stream_ptr()), "mclip_gemm_tn")
-    return (out, stats) if want_stats else out
+    return out if want_stats is None else (out, stats)
 
 
 _wgrad_ws = {}
@@ -111,3 +111,274 @@ def contrastive_loss_raw(local, pairs, scale, world=1, rank=0, symm=None):
         symm.fill_args(args, K)
     check(lib().mclip_contrastive_loss(C.byref(args), stream_ptr()), "mclip_contrastive_loss")
     return out, grads
+
+
+# ------------------------------------------------------------------------------------------------ conv / BN / SE passes
+from ._lib import BnArgs, DwconvArgs, EwArgs, EwBwdArgs, PrepEntry, SeArgs, StemArgs  # noqa: E402
+
+
+def _p(t):
+    return None if t is None else t.data_ptr()
+
+
+class BNState:
+    """Affine (scale, shift) that consumers apply on load + batch statistics kept for the backward pass."""
+    __slots__ = ("scale", "shift", "mean", "invstd", "count", "training")
+
+    def __init__(self, c, device):
+        buf = torch.empty(4, c, dtype=torch.float32, device=device)
+        self.scale, self.shift, self.mean, self.invstd = buf[0], buf[1], buf[2], buf[3]
+
+
+def bn_finalize(partials, count, gamma, beta, running_mean, running_var, num_batches, training, momentum=0.01, eps=1e-3):
+    c = gamma.numel()
+    st = BNState(c, gamma.device)
+    st.count, st.training = count, training
+    a = BnArgs()
+    a.c, a.training, a.count = c, int(training), count
+    if training:
+        a.slots, a.partials = partials.shape[0], partials.data_ptr()
+    a.gamma, a.beta = gamma.data_ptr(), beta.data_ptr()
+    a.running_mean, a.running_var = _p(running_mean), _p(running_var)
+    a.num_batches_tracked = _p(num_batches)
+    a.momentum, a.eps = momentum, eps
+    a.scale, a.shift, a.mean, a.invstd = st.scale.data_ptr(), st.shift.data_ptr(), st.mean.data_ptr(), st.invstd.data_ptr()
+    check(lib().mclip_bn_finalize(C.byref(a), stream_ptr()), "mclip_bn_finalize")
+    return st
+
+
+def stem_forward(images, weight, pads, want_stats=True):
+    """images: [N,3,H,W] fp32 (any strides); weight [C,3,3,3] fp32 -> (Y [N,Ho,Wo,C] bf16, stats)."""
+    _require_cuda(images, weight)
+    n, ci, h, w = images.shape
+    assert ci == 3 and images.dtype == torch.float32
+    pl, pr, pt, pb = pads
+    ho, wo = (h + pt + pb - 3) // 2 + 1, (w + pl + pr - 3) // 2 + 1
+    c = weight.shape[0]
+    out = torch.empty((n, ho, wo, c), dtype=torch.bfloat16, device=images.device)
+    a = StemArgs()
+    a.n, a.h, a.w, a.ho, a.wo, a.c = n, h, w, ho, wo, c
+    a.pad_left, a.pad_right, a.pad_top, a.pad_bottom = pl, pr, pt, pb
+    a.in_ = images.data_ptr()
+    a.stride_n, a.stride_c, a.stride_h, a.stride_w = images.stride()
+    a.weight, a.out = weight.data_ptr(), out.data_ptr()
+    stats = None
+    if want_stats:
+        slots = lib().mclip_stem_slots(n, ho, wo)
+        stats = torch.empty((slots, 2, c), dtype=torch.float32, device=images.device)
+        a.stats, a.stat_slots = stats.data_ptr(), slots
+    check(lib().mclip_stem_forward(C.byref(a), stream_ptr()), "mclip_stem_forward")
+    return out, stats
+
+
+def stem_wgrad(images, dy, pads, dweight):
+    n, _, h, w = images.shape
+    _, ho, wo, c = dy.shape
+    pl, pr, pt, pb = pads
+    a = StemArgs()
+    a.n, a.h, a.w, a.ho, a.wo, a.c = n, h, w, ho, wo, c
+    a.pad_left, a.pad_right, a.pad_top, a.pad_bottom = pl, pr, pt, pb
+    a.in_ = images.data_ptr()
+    a.stride_n, a.stride_c, a.stride_h, a.stride_w = images.stride()
+    a.weight = dweight.data_ptr()        # unused by the wgrad kernel, must be non-null
+    slots = lib().mclip_stem_slots(n, ho, wo)
+    part = torch.empty((slots, 27, c), dtype=torch.float32, device=dy.device)
+    a.stat_slots, a.dy, a.dweight, a.accumulate, a.dw_partials = slots, dy.data_ptr(), dweight.data_ptr(), 0, part.data_ptr()
+    check(lib().mclip_stem_wgrad(C.byref(a), stream_ptr()), "mclip_stem_wgrad")
+    return dweight
+
+
+def _dw_args(x, weight, k, stride, pads, bn):
+    n, h, w, c = x.shape
+    pl, pr, pt, pb = pads
+    a = DwconvArgs()
+    a.n, a.h, a.w, a.c, a.k, a.stride = n, h, w, c, k, stride
+    a.ho, a.wo = (h + pt + pb - k) // stride + 1, (w + pl + pr - k) // stride + 1
+    a.pad_left, a.pad_right, a.pad_top, a.pad_bottom = pl, pr, pt, pb
+    a.in_ = x.data_ptr()
+    if bn is not None:
+        a.in_scale, a.in_shift, a.in_act = bn.scale.data_ptr(), bn.shift.data_ptr(), 1
+    a.weight = weight.data_ptr()
+    return a
+
+
+def dwconv_forward(x, weight, k, stride, pads, bn=None, want_stats=True):
+    """x: [N,H,W,C] bf16 (pre-BN output of the producer when `bn` is given: swish(bn(x)) is applied on load)."""
+    _require_cuda(x, weight)
+    a = _dw_args(x, weight, k, stride, pads, bn)
+    out = torch.empty((a.n, a.ho, a.wo, a.c), dtype=torch.bfloat16, device=x.device)
+    a.out = out.data_ptr()
+    stats = None
+    if want_stats:
+        slots = lib().mclip_dwconv_slots(C.byref(a), 0)
+        stats = torch.empty((slots, 2, a.c), dtype=torch.float32, device=x.device)
+        a.stats, a.stat_slots = stats.data_ptr(), slots
+    check(lib().mclip_dwconv_forward(C.byref(a), stream_ptr()), "mclip_dwconv_forward")
+    return out, stats
+
+
+def dwconv_backward(x, weight, k, stride, pads, dy, dweight, bn=None):
+    """Returns (dx, bn_partials).  dx = d/d(pre-activation x) when `bn` is given (swish' applied), else d/dx."""
+    a = _dw_args(x, weight, k, stride, pads, bn)
+    dx = torch.empty_like(x)
+    slots = lib().mclip_dwconv_slots(C.byref(a), 1)
+    dwp = torch.empty((slots, k * k, a.c), dtype=torch.float32, device=x.device)
+    a.stat_slots, a.dy, a.dx, a.dweight, a.accumulate, a.dw_partials = slots, dy.data_ptr(), dx.data_ptr(), dweight.data_ptr(), 0, dwp.data_ptr()
+    bnp = None
+    if bn is not None:
+        bnp = torch.empty((slots, 2, a.c), dtype=torch.float32, device=x.device)
+        a.bn_partials, a.in_mean, a.in_invstd = bnp.data_ptr(), bn.mean.data_ptr(), bn.invstd.data_ptr()
+    check(lib().mclip_dwconv_backward(C.byref(a), stream_ptr()), "mclip_dwconv_backward")
+    return dx, bnp
+
+
+def ew_chunks(n, hw, c):
+    r = lib().mclip_ew_chunks(n, hw, c)
+    if r < 1:
+        raise _lib.MclipError(f"mclip_ew_chunks({n},{hw},{c}) failed")
+    return r
+
+
+def ew_forward(y, bn=None, act=0, rowscale=None, residual=None, write=True, pool=False):
+    """y: [N,HW,C] bf16.  Returns (out or None, pool_partials or None)."""
+    n, hw, c = y.shape
+    a = EwArgs()
+    a.n, a.hw, a.c, a.act = n, hw, c, act
+    a.y = y.data_ptr()
+    if bn is not None:
+        a.scale, a.shift = bn.scale.data_ptr(), bn.shift.data_ptr()
+    a.rowscale, a.residual = _p(rowscale), _p(residual)
+    out = torch.empty_like(y) if write else None
+    a.out = _p(out)
+    part = None
+    if pool:
+        a.chunks = ew_chunks(n, hw, c)
+        part = torch.empty((n, a.chunks, c), dtype=torch.float32, device=y.device)
+        a.pool_partials = part.data_ptr()
+    check(lib().mclip_ew_forward(C.byref(a), stream_ptr()), "mclip_ew_forward")
+    return out, part
+
+
+def pool_finalize(part, hw, mult=None):
+    n, chunks, c = part.shape
+    out = torch.empty((n, c), dtype=torch.float32, device=part.device)
+    check(lib().mclip_pool_finalize(ptr(part), n, chunks, c, hw, ptr(mult), ptr(out), stream_ptr()), "mclip_pool_finalize")
+    return out
+
+
+def se_fc(part, hw, w1, b1, w2, b2):
+    n, chunks, c = part.shape
+    cse = w1.shape[0]
+    dev = part.device
+    pooled = torch.empty((n, c), dtype=torch.float32, device=dev)
+    z1 = torch.empty((n, cse), dtype=torch.float32, device=dev)
+    gate = torch.empty((n, c), dtype=torch.float32, device=dev)
+    a = SeArgs()
+    a.n, a.hw, a.c, a.cse, a.chunks = n, hw, c, cse, chunks
+    a.pool_partials, a.w1, a.b1, a.w2, a.b2 = part.data_ptr(), w1.data_ptr(), b1.data_ptr(), w2.data_ptr(), b2.data_ptr()
+    a.pooled, a.z1, a.gate = pooled.data_ptr(), z1.data_ptr(), gate.data_ptr()
+    check(lib().mclip_se_fc(C.byref(a), stream_ptr()), "mclip_se_fc")
+    return pooled, z1, gate
+
+
+def se_fc_backward(dg_part, hw, w1, w2, pooled, z1, gate, dw1, db1, dw2, db2):
+    n, chunks, c = dg_part.shape
+    cse = w1.shape[0]
+    dev = dg_part.device
+    dz2 = torch.empty((n, c), dtype=torch.float32, device=dev)
+    dz1 = torch.empty((n, cse), dtype=torch.float32, device=dev)
+    dpool = torch.empty((n, c), dtype=torch.float32, device=dev)
+    a = SeArgs()
+    a.n, a.hw, a.c, a.cse, a.chunks, a.accumulate = n, hw, c, cse, chunks, 0
+    a.w1, a.w2, a.pooled, a.z1, a.gate = w1.data_ptr(), w2.data_ptr(), pooled.data_ptr(), z1.data_ptr(), gate.data_ptr()
+    a.dgate_partials, a.dz2, a.dz1, a.dpool = dg_part.data_ptr(), dz2.data_ptr(), dz1.data_ptr(), dpool.data_ptr()
+    a.dw1, a.db1, a.dw2, a.db2 = dw1.data_ptr(), db1.data_ptr(), dw2.data_ptr(), db2.data_ptr()
+    check(lib().mclip_se_fc_backward(C.byref(a), stream_ptr()), "mclip_se_fc_backward")
+    return dpool
+
+
+def se_scale_weights(w, gate):
+    """w: [Cout,Cexp] fp32, gate [N,Cexp] fp32 -> [N,Cout,Cexp] bf16."""
+    cout, cexp = w.shape[0], w.shape[1]
+    n = gate.shape[0]
+    out = torch.empty((n, cout, cexp), dtype=torch.bfloat16, device=w.device)
+    check(lib().mclip_se_scale_weights(ptr(w), ptr(gate), ptr(out), n, cout, cexp, stream_ptr()), "mclip_se_scale_weights")
+    return out
+
+
+def ew_backward(mode, y, bn, act, du=None, dvec=None, gate=None, dpool=None, rowscale=None, dv_given=False, c1=None, c2=None):
+    """mode 0 -> partials [N*chunks,2,C]; mode 1 -> dY bf16; mode 2 -> (A2 bf16, dgate partials [N,chunks,C])."""
+    n, hw, c = y.shape
+    a = EwBwdArgs()
+    a.n, a.hw, a.c, a.act, a.mode, a.dv_given = n, hw, c, act, mode, int(dv_given)
+    a.y = y.data_ptr()
+    if bn is not None:
+        a.scale, a.shift, a.mean, a.invstd = bn.scale.data_ptr(), bn.shift.data_ptr(), bn.mean.data_ptr(), bn.invstd.data_ptr()
+    a.du, a.dvec, a.gate, a.dpool, a.rowscale, a.c1, a.c2 = _p(du), _p(dvec), _p(gate), _p(dpool), _p(rowscale), _p(c1), _p(c2)
+    part = out = None
+    if mode != 1:
+        a.chunks = ew_chunks(n, hw, c)
+        shape = (n * a.chunks, 2, c) if mode == 0 else (n, a.chunks, c)
+        part = torch.empty(shape, dtype=torch.float32, device=y.device)
+        a.partials = part.data_ptr()
+    if mode != 0:
+        out = torch.empty_like(y)
+        a.out = out.data_ptr()
+    check(lib().mclip_ew_backward(C.byref(a), stream_ptr()), "mclip_ew_backward")
+    return part if mode == 0 else out if mode == 1 else (out, part)
+
+
+def bn_bwd_finalize(partials, count, training, dgamma, dbeta):
+    slots, _, c = partials.shape
+    cc = torch.empty((2, c), dtype=torch.float32, device=partials.device)
+    check(lib().mclip_bn_bwd_finalize(ptr(partials), slots, c, C.c_longlong(count), int(training), ptr(dgamma), ptr(dbeta), 0,
+                                      ptr(cc[0]), ptr(cc[1]), stream_ptr()), "mclip_bn_bwd_finalize")
+    return cc[0], cc[1]
+
+
+def weight_prep(entries, device):
+    """entries: list of (src fp32 2-D, dst bf16 or None, dst_t bf16 or None). Returns the device table (keep it alive)."""
+    import numpy as np
+    arr = (PrepEntry * len(entries))()
+    for i, (src, dst, dst_t) in enumerate(entries):
+        arr[i].src, arr[i].dst, arr[i].dst_t = src.data_ptr(), _p(dst), _p(dst_t)
+        arr[i].rows, arr[i].cols = src.shape[0], src[0].numel()
+    raw = np.frombuffer(bytes(arr), dtype=np.uint8).copy()
+    return torch.from_numpy(raw).to(device)
+
+
+def weight_prep_run(table, n_entries):
+    check(lib().mclip_weight_prep(ptr(table), n_entries, stream_ptr()), "mclip_weight_prep")
+
+
+def cast_bf16(x):
+    out = torch.empty(x.shape, dtype=torch.bfloat16, device=x.device)
+    check(lib().mclip_cast_bf16(ptr(x), ptr(out), C.c_longlong(x.numel()), stream_ptr()), "mclip_cast_bf16")
+    return out
+
+
+def l2norm_forward(x):
+    rows, d = x.shape
+    e = torch.empty((rows, d), dtype=torch.float32, device=x.device)
+    nrm = torch.empty((rows,), dtype=torch.float32, device=x.device)
+    check(lib().mclip_l2norm_forward(ptr(x), ptr(e), ptr(nrm), rows, d, stream_ptr()), "mclip_l2norm_forward")
+    return e, nrm
+
+
+def l2norm_backward(e, de, nrm):
+    rows, d = e.shape
+    dx = torch.empty((rows, d), dtype=torch.bfloat16, device=e.device)
+    check(lib().mclip_l2norm_backward(ptr(e), ptr(de), ptr(nrm), ptr(dx), rows, d, stream_ptr()), "mclip_l2norm_backward")
+    return dx
+
+
+def colsum(x, out):
+    rows, cols = x.shape
+    check(lib().mclip_colsum(ptr(x), ptr(out), rows, cols, C.c_longlong(x.stride(0)), 0, stream_ptr()), "mclip_colsum")
+    return out
+
+
+def adamw_step(param, grad, exp_avg, exp_avg_sq, lr, beta1, beta2, eps, weight_decay, step, grad_scale=1.0):
+    check(lib().mclip_adamw_step(ptr(param), ptr(grad), ptr(exp_avg), ptr(exp_avg_sq), C.c_longlong(param.numel()), C.c_float(lr), C.c_float(beta1),
+                                 C.c_float(beta2), C.c_float(eps), C.c_float(weight_decay), C.c_longlong(step), C.c_float(grad_scale), stream_ptr()),
+          "mclip_adamw_step")

@@ -1,0 +1,164 @@
+"""Depthwise / stem / BN / SE kernels vs plain PyTorch fp32 references on the same (bf16-rounded) inputs."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+from conftest import rel_err
+
+pytestmark = pytest.mark.gpu
+
+
+def _rand(shape, seed, scale=1.0, dtype=torch.bfloat16):
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    return (torch.randn(shape, generator=g, device="cuda") * scale).to(dtype)
+
+
+def _bn_state(c, seed):
+    from mammoclip_b200 import ops
+    st = ops.BNState(c, "cuda")
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    st.scale.copy_(torch.rand(c, generator=g, device="cuda") + 0.5)
+    st.shift.copy_(torch.randn(c, generator=g, device="cuda") * 0.3)
+    st.mean.copy_(torch.randn(c, generator=g, device="cuda") * 0.2)
+    st.invstd.copy_(torch.rand(c, generator=g, device="cuda") + 0.5)
+    st.count, st.training = 1, True
+    return st
+
+
+DW_CASES = [  # (N,H,W,C,k,s,pads(l,r,t,b), with_bn)
+    (2, 20, 24, 48, 3, 1, (1, 1, 1, 1), True), (2, 33, 17, 144, 3, 2, (0, 1, 0, 1), True), (1, 19, 23, 240, 5, 2, (1, 2, 1, 2), True),
+    (2, 24, 16, 384, 5, 1, (2, 2, 2, 2), True), (2, 31, 29, 64, 3, 2, (1, 1, 1, 1), True), (1, 29, 29, 88, 5, 2, (2, 2, 2, 2), True),
+    (3, 12, 40, 24, 3, 1, (1, 1, 1, 1), False), (1, 7, 7, 3072, 3, 1, (1, 1, 1, 1), True), (2, 57, 57, 16, 3, 1, (1, 1, 1, 1), False),
+]
+
+
+def _dw_ref(x, w, k, s, pads, bn):
+    xf = x.float().permute(0, 3, 1, 2)
+    if bn is not None:
+        v = xf * bn.scale.view(1, -1, 1, 1) + bn.shift.view(1, -1, 1, 1)
+        xf = (v * torch.sigmoid(v)).to(torch.bfloat16).float()       # the kernel stages the activated tile as bf16
+    xf = xf.detach().requires_grad_(True)
+    y = F.conv2d(F.pad(xf, pads), w, stride=s, groups=w.shape[0])
+    return xf, y
+
+
+@pytest.mark.parametrize("n,h,w,c,k,s,pads,with_bn", DW_CASES)
+def test_dwconv_forward_backward(n, h, w, c, k, s, pads, with_bn):
+    from mammoclip_b200 import ops
+    x = _rand((n, h, w, c), 1)
+    wt = (_rand((c, 1, k, k), 2, 0.3, torch.float32)).contiguous()
+    bn = _bn_state(c, 3) if with_bn else None
+    y, stats = ops.dwconv_forward(x, wt, k, s, pads, bn=bn)
+    wref = wt.clone().requires_grad_(True)
+    xf, yref = _dw_ref(x, wref, k, s, pads, bn)
+    yr = yref.permute(0, 2, 3, 1)
+    assert y.shape == yr.shape
+    assert rel_err(y.float(), yr) < 8e-3
+    st = stats.double().sum(0)
+    yd = y.double().reshape(-1, c)
+    assert rel_err(st[0], yd.sum(0)) < 1e-4 and rel_err(st[1], (yd * yd).sum(0)) < 1e-4
+    # backward
+    dy = _rand(y.shape, 4)
+    dwt = torch.empty_like(wt)
+    dx, bnp = ops.dwconv_backward(x, wt, k, s, pads, dy, dwt, bn=bn)
+    yref.backward(dy.float().permute(0, 3, 1, 2))
+    assert rel_err(dwt, wref.grad) < 5e-3, "dweight"
+    dA = xf.grad.permute(0, 2, 3, 1)
+    if bn is None:
+        assert rel_err(dx.float(), dA) < 8e-3, "dx"
+    else:
+        v = x.float() * bn.scale + bn.shift
+        sg = torch.sigmoid(v)
+        dv = dA * (sg * (1 + v * (1 - sg)))
+        assert rel_err(dx.float(), dv) < 1e-2, "dv"
+        yh = (x.float() - bn.mean) * bn.invstd
+        p = bnp.double().sum(0)
+        dvq = dx.double().reshape(-1, c)
+        assert rel_err(p[0], dvq.sum(0)) < 1e-3
+        assert rel_err(p[1], (dvq * yh.double().reshape(-1, c)).sum(0)) < 1e-3
+
+
+@pytest.mark.parametrize("n,h,w,c,pads,nhwc", [(2, 64, 48, 32, (0, 1, 0, 1), True), (3, 31, 45, 48, (0, 1, 0, 1), False), (1, 96, 64, 40, (1, 1, 1, 1), True)])
+def test_stem(n, h, w, c, pads, nhwc):
+    from mammoclip_b200 import ops
+    g = torch.Generator(device="cuda").manual_seed(5)
+    img = torch.randn(n, h, w, 3, generator=g, device="cuda").permute(0, 3, 1, 2) if nhwc else torch.randn(n, 3, h, w, generator=g, device="cuda")
+    wt = _rand((c, 3, 3, 3), 6, 0.3, torch.float32)
+    y, stats = ops.stem_forward(img, wt, pads)
+    wref = wt.clone().requires_grad_(True)
+    yref = F.conv2d(F.pad(img, pads), wref, stride=2)
+    assert rel_err(y.float(), yref.permute(0, 2, 3, 1)) < 6e-3
+    st = stats.double().sum(0)
+    yd = y.double().reshape(-1, c)
+    assert rel_err(st[0], yd.sum(0)) < 1e-4 and rel_err(st[1], (yd * yd).sum(0)) < 1e-4
+    dy = _rand(y.shape, 7)
+    dwt = torch.empty_like(wt)
+    ops.stem_wgrad(img, dy, pads, dwt)
+    yref.backward(dy.float().permute(0, 3, 1, 2))
+    assert rel_err(dwt, wref.grad) < 2e-3
+
+
+@pytest.mark.parametrize("n,hw,c", [(2, 500, 144), (3, 1392, 1824), (1, 77, 3072), (4, 3000, 24), (2, 999, 1056)])
+def test_bn_and_elementwise(n, hw, c):
+    from mammoclip_b200 import ops
+    y = _rand((n, hw, c), 8)
+    # statistics -> finalize vs torch batch_norm
+    yf = y.float().reshape(-1, c)
+    part = torch.stack([yf.sum(0), (yf * yf).sum(0)])[None].contiguous()
+    gamma, beta = torch.rand(c, device="cuda") + 0.5, torch.randn(c, device="cuda") * 0.1
+    rm, rv, nb = torch.zeros(c, device="cuda"), torch.ones(c, device="cuda"), torch.zeros((), dtype=torch.long, device="cuda")
+    st = ops.bn_finalize(part, n * hw, gamma, beta, rm, rv, nb, True)
+    rm2, rv2 = torch.zeros(c, device="cuda"), torch.ones(c, device="cuda")
+    ref = F.batch_norm(yf, rm2, rv2, gamma, beta, True, 0.01, 1e-3)
+    assert rel_err(yf * st.scale + st.shift, ref) < 1e-4
+    assert rel_err(rm, rm2) < 1e-4 and rel_err(rv, rv2) < 1e-4 and nb.item() == 1
+    # forward pass: swish(bn(y)) * rowscale + residual, pooling partials
+    res, rs = _rand((n, hw, c), 9), torch.rand(n, device="cuda") + 0.5
+    out, pool = ops.ew_forward(y, bn=st, act=1, rowscale=rs, residual=res, pool=True)
+    v = y.float() * st.scale + st.shift
+    refo = v * torch.sigmoid(v) * rs.view(n, 1, 1) + res.float()
+    assert rel_err(out.float(), refo) < 8e-3
+    assert rel_err(pool.sum(1), out.float().sum(1)) < 1e-4
+    # backward passes vs autograd of the same expression
+    du = _rand((n, hw, c), 10)
+    gate, dpool = torch.rand(n, c, device="cuda"), torch.randn(n, c, device="cuda") * 0.01
+    yv = y.float().clone().requires_grad_(True)
+    g2, b2 = gamma.clone().requires_grad_(True), beta.clone().requires_grad_(True)
+    z = F.batch_norm(yv.reshape(-1, c), None, None, g2, b2, True, 0.0, 1e-3).reshape(n, hw, c)
+    u = z * torch.sigmoid(z)
+    up = (du.float() * gate.view(n, 1, c) + dpool.view(n, 1, c))
+    (u * up).sum().backward()
+    part = ops.ew_backward(0, y, st, 1, du=du, gate=gate, dpool=dpool)
+    dg, db = torch.empty(c, device="cuda"), torch.empty(c, device="cuda")
+    c1, c2 = ops.bn_bwd_finalize(part, n * hw, True, dg, db)
+    assert rel_err(dg, g2.grad) < 5e-3 and rel_err(db, b2.grad) < 5e-3
+    dy = ops.ew_backward(1, y, st, 1, du=du, gate=gate, dpool=dpool, c1=c1, c2=c2)
+    assert rel_err(dy.float(), yv.grad) < 1e-2
+    a2, dgp = ops.ew_backward(2, y, st, 1, du=du, gate=gate)
+    assert rel_err(a2.float(), (u * gate.view(n, 1, c)).detach()) < 8e-3
+    assert rel_err(dgp.sum(1), (du.float() * u.detach()).sum(1)) < 5e-3
+
+
+@pytest.mark.parametrize("n,c,cse,hw", [(4, 144, 6, 100), (2, 3072, 128, 50), (3, 48, 12, 64)])
+def test_se_fc(n, c, cse, hw):
+    from mammoclip_b200 import ops
+    part = torch.randn(n, 3, c, device="cuda")
+    w1, b1 = torch.randn(cse, c, device="cuda") * 0.1, torch.randn(cse, device="cuda") * 0.1
+    w2, b2 = torch.randn(c, cse, device="cuda") * 0.1, torch.randn(c, device="cuda") * 0.1
+    pooled, z1, gate = ops.se_fc(part, hw, w1, b1, w2, b2)
+    s = (part.sum(1) / hw).requires_grad_(True)
+    W1, B1, W2, B2 = (t.clone().requires_grad_(True) for t in (w1, b1, w2, b2))
+    z = s @ W1.T + B1
+    h = z * torch.sigmoid(z)
+    gr = torch.sigmoid(h @ W2.T + B2)
+    assert rel_err(gate, gr) < 1e-4 and rel_err(pooled, s) < 1e-5
+    dgp = torch.randn(n, 2, c, device="cuda")
+    gr.backward(dgp.sum(1))
+    dw1, db1, dw2, db2 = (torch.empty_like(t) for t in (w1, b1, w2, b2))
+    dpool = ops.se_fc_backward(dgp, hw, w1, w2, pooled, z1, gate, dw1, db1, dw2, db2)
+    assert rel_err(dpool, s.grad / hw) < 1e-3
+    for a, b in ((dw1, W1.grad), (db1, B1.grad), (dw2, W2.grad), (db2, B2.grad)):
+        assert rel_err(a, b) < 1e-3
+    wp = torch.randn(40, c, device="cuda")
+    wg = ops.se_scale_weights(wp, gate)
+    assert rel_err(wg.float(), wp[None] * gate[:, None, :]) < 5e-3
