@@ -42,6 +42,7 @@ typedef struct mclip_loss_args {
   int pair_a[MCLIP_LOSS_MAX_PAIRS], pair_b[MCLIP_LOSS_MAX_PAIRS];
   float w_row[MCLIP_LOSS_MAX_PAIRS], w_col[MCLIP_LOSS_MAX_PAIRS], label_smoothing[MCLIP_LOSS_MAX_PAIRS];
   float logit_scale;                           /* exp(logit_scale parameter), clip.py:100 */
+  const float* logit_scale_dev;                /* optional DEVICE scalar, used instead of logit_scale (no host sync) */
   void* workspace; long long workspace_bytes;  /* >= mclip_loss_workspace_bytes() */
   float* out;                                  /* [2 + 2*n_pairs] fp32 */
   /* world > 1 only: symmetric (peer-mapped) gather buffers, see mclip_symm_* below */
@@ -54,6 +55,13 @@ typedef struct mclip_loss_args {
 long long mclip_loss_workspace_bytes(int world, int batch, int dim, int n_pairs);
 int mclip_loss_grid(int world, int batch, int n_pairs);
 int mclip_contrastive_loss(const mclip_loss_args* args, void* stream);
+
+/* Peer-mapped buffers for world > 1 (cudaMalloc + CUDA IPC; handles are 64 bytes, exchanged by the host). */
+int mclip_ipc_alloc(long long bytes, void** out);          /* zero-filled */
+int mclip_ipc_free(void* p);
+int mclip_ipc_get_handle(void* p, void* handle64);
+int mclip_ipc_open_handle(const void* handle64, void** out);
+int mclip_ipc_close_handle(void* p);
 
 /* ---- tcgen05 GEMMs ---------------------------------------------------------------------------------------------
  * mclip_gemm_tn: D[b,m,n] = epi(sum_k A[b,m,k] B[b|0,n,k]), bf16 in/out, fp32 accumulate in TMEM.  This is the 1x1
@@ -71,6 +79,7 @@ typedef struct mclip_gemm_args {
   const void* residual; long long ldr, r_batch_stride;   /* bf16 [batches, m, n] or NULL */
   int act;                                        /* 0 none, 1 erf-GELU */
   float* stats; int stat_slots;                   /* NULL, or fp32 [stat_slots][2][n] with stat_slots from below */
+  const void* dropmask; float drop_scale;         /* uint8 keep-mask [batches*m, n] applied before the residual, or NULL */
 } mclip_gemm_args;
 int mclip_gemm_tn_stat_slots(int m, int n, int batches);
 int mclip_gemm_tn(const mclip_gemm_args* args, void* stream);
@@ -195,6 +204,25 @@ typedef struct mclip_ew_bwd_args {
 int mclip_ew_backward(const mclip_ew_bwd_args* args, void* stream);
 int mclip_bn_bwd_finalize(const float* partials, int slots, int c, long long count, int training, float* dgamma, float* dbeta,
                           int accumulate, float* c1, float* c2, void* stream);
+
+/* ---- BERT text tower (non-GEMM pieces) ---------------------------------------------------------------------------
+ * What HuggingfaceTextEncoder.forward (text_encoder.py:47-49) runs inside transformers' BertModel, post-LN BERT:
+ * embeddings + LayerNorm(eps 1e-12) + dropout; softmax(QK^T/8 + padding mask) (dropout) V per head; LayerNorm.
+ * All Linear layers go through mclip_gemm_tn (bias / erf-GELU / dropout mask / residual epilogues). */
+typedef struct mclip_bert_embed_args {
+  int batch, seq_len, hidden, vocab, max_positions;
+  const void* input_ids; const void* token_type_ids;      /* int64 [batch, seq_len] (token_type_ids may be NULL) */
+  const float* word; const float* pos; const float* type; /* fp32 embedding tables */
+  const float* gamma; const float* beta; float eps;
+  const void* dropmask; float drop_scale;                 /* uint8 [batch*seq_len, hidden] keep-mask or NULL; 1/(1-p) */
+  void* out;                                              /* bf16 [batch*seq_len, hidden] */
+} mclip_bert_embed_args;
+int mclip_bert_embed_ln(const mclip_bert_embed_args* args, void* stream);
+int mclip_layernorm(const void* x_bf16, const float* gamma, const float* beta, float eps, void* out_bf16, int rows, int hidden, void* stream);
+/* qkv: bf16 [batch*seq_len, 3*heads*head_dim] (Q | K | V); attention_mask int64 [batch, seq_len] (1 = attend);
+ * dropmask uint8 [batch, heads, seq_len, seq_len] or NULL; out bf16 [batch*seq_len, heads*head_dim]. */
+int mclip_bert_attention(const void* qkv, const void* attention_mask, const void* dropmask, float drop_scale, void* out,
+                         int batch, int seq_len, int heads, int head_dim, void* stream);
 
 /* fp32 master weights -> bf16 GEMM operands (and their transposes for the data-gradient GEMMs), one launch per tower. */
 typedef struct mclip_prep_entry { const void* src; void* dst; void* dst_t; int rows, cols; } mclip_prep_entry;

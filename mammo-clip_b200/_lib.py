@@ -24,6 +24,7 @@ class LossArgs(C.Structure):
         ("pair_a", C.c_int * MAX_PAIRS), ("pair_b", C.c_int * MAX_PAIRS),
         ("w_row", C.c_float * MAX_PAIRS), ("w_col", C.c_float * MAX_PAIRS), ("label_smoothing", C.c_float * MAX_PAIRS),
         ("logit_scale", C.c_float),
+        ("logit_scale_dev", C.c_void_p),
         ("workspace", C.c_void_p), ("workspace_bytes", C.c_longlong),
         ("out", C.c_void_p),
         ("gathered", C.c_void_p * MAX_TENSORS),
@@ -44,6 +45,7 @@ class GemmArgs(C.Structure):
         ("residual", C.c_void_p), ("ldr", C.c_longlong), ("r_batch_stride", C.c_longlong),
         ("act", C.c_int),
         ("stats", C.c_void_p), ("stat_slots", C.c_int),
+        ("dropmask", C.c_void_p), ("drop_scale", C.c_float),
     ]
 
 
@@ -159,3 +161,14 @@ class EwBwdArgs(C.Structure):
 
 class PrepEntry(C.Structure):
     _fields_ = [("src", C.c_void_p), ("dst", C.c_void_p), ("dst_t", C.c_void_p), ("rows", C.c_int), ("cols", C.c_int)]
+
+
+class BertEmbedArgs(C.Structure):
+    _fields_ = [
+        ("batch", C.c_int), ("seq_len", C.c_int), ("hidden", C.c_int), ("vocab", C.c_int), ("max_positions", C.c_int),
+        ("input_ids", C.c_void_p), ("token_type_ids", C.c_void_p),
+        ("word", C.c_void_p), ("pos", C.c_void_p), ("type", C.c_void_p),
+        ("gamma", C.c_void_p), ("beta", C.c_void_p), ("eps", C.c_float),
+        ("dropmask", C.c_void_p), ("drop_scale", C.c_float),
+        ("out", C.c_void_p),
+    ]

@@ -12,6 +12,8 @@
 // weights in registers, input tile staged in shared memory after the BN+swish transform.
 #include "common.cuh"
 #include "mclip_internal.h"
+#include <algorithm>
+using std::max;
 
 #define DW_THREADS 256
 #define DW_WARPS 8
@@ -372,7 +374,9 @@ static int dw_launch_bwd(DwDev& p, cudaStream_t stream, int slots_given) {
   int smem = (IH * IW + GH * GW) * DW_CCH * 2 + K * K * DW_CCH * 4;
   const int red_bytes = DW_WARPS * K * K * DW_CCH * 4;                // flush reuses the front of the buffer
   if (smem < red_bytes) smem = red_bytes;
-  p.tiles_x = ceil_div(p.Wo, TW); p.tiles_y = ceil_div(p.Ho, TH);
+  // the tile grid must cover every OUTPUT pixel (weight gradient) and every INPUT pixel (data gradient): with the
+  // reference's static pads, S*Ho can be smaller than H (e.g. H=33, k3 s2 pads (0,1) -> Ho=16 but input row 32 is read)
+  p.tiles_x = ceil_div(max(p.Wo, ceil_div(p.W, S)), TW); p.tiles_y = ceil_div(max(p.Ho, ceil_div(p.H, S)), TH);
   p.n_chunks = ceil_div(p.C, DW_CCH);
   p.slots = slots_given;
   auto kern = mclip_dwconv_bwd_kernel<K, S, TH, TW>;
@@ -385,8 +389,10 @@ static int dw_launch_bwd(DwDev& p, cudaStream_t stream, int slots_given) {
 
 static int dw_tiles(const mclip_dwconv_args* a, bool bwd) {
   int TH = a->stride == 1 ? 16 : 8, TW = 16;
-  if (bwd) TH /= 2;
-  return a->n * ceil_div(a->ho, TH) * ceil_div(a->wo, TW);
+  if (!bwd) return a->n * ceil_div(a->ho, TH) * ceil_div(a->wo, TW);
+  TH /= 2;
+  const int hy = max(a->ho, ceil_div(a->h, a->stride)), wx = max(a->wo, ceil_div(a->w, a->stride));
+  return a->n * ceil_div(hy, TH) * ceil_div(wx, TW);
 }
 
 extern "C" int mclip_dwconv_slots(const mclip_dwconv_args* a, int backward) {

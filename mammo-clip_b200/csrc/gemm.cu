@@ -32,6 +32,7 @@ struct GemmDev {
   long long res_ld, res_bs;
   int act;
   float* stats;     // [(gridDim.x / n_blocks) * 4][2][N]
+  const uint8_t* dropmask; float drop_scale;
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -186,6 +187,12 @@ mclip_gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
 #pragma unroll
             for (int i = 0; i < 16; ++i) v[i] = gelu_erf(v[i]);
           }
+          if (p.dropmask && row < p.M) {
+            const uint4 mk = *reinterpret_cast<const uint4*>(p.dropmask + ((size_t)b * p.M + row) * p.N + cc);   // N % 16 == 0 required
+            const uint32_t mw[4] = {mk.x, mk.y, mk.z, mk.w};
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[i] *= ((mw[i >> 2] >> ((i & 3) * 8)) & 0xffu) ? p.drop_scale : 0.f;
+          }
           if (p.residual && row < p.M) {
             const bf16* rp = p.residual + (size_t)b * p.res_bs + (size_t)row * p.res_ld + cc;
 #pragma unroll
@@ -288,6 +295,8 @@ extern "C" int mclip_gemm_tn(const mclip_gemm_args* g, void* stream_) {
   p.idesc = umma_idesc_bf16(GEMM_BM, p.block_n, 0, 0);
   p.bias = g->bias; p.residual = (const bf16*)g->residual; p.res_ld = g->ldr; p.res_bs = g->r_batch_stride; p.act = g->act;
   p.stats = g->stats;
+  p.dropmask = (const uint8_t*)g->dropmask; p.drop_scale = g->drop_scale;
+  if (g->dropmask) MCLIP_REQUIRE(g->n % 16 == 0, "mclip_gemm_tn: dropout mask needs N %% 16 == 0");
   const int stage_bytes = GEMM_BM * GEMM_BK * 2 + p.block_n * GEMM_BK * 2;
   const int fixed = GEMM_EPI_WARPS * 2 * GEMM_SLAB_BYTES + 256 + 1024;
   p.stages = (GEMM_SMEM_LIMIT - fixed) / stage_bytes;

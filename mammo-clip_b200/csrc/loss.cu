@@ -39,6 +39,7 @@ struct LossDev {
   int WB, nI32, nJ64;          // tiles of the full score matrix: rows in 32s, columns in 64s
   int nLB32;                   // 32-row blocks of the local B rows
   float scale;
+  const float* scale_dev;          // device scalar (takes precedence over `scale`)
   const float* local[MCLIP_LOSS_MAX_TENSORS];      // this rank's rows [B,D]
   const float* all[MCLIP_LOSS_MAX_TENSORS];        // gathered [W*B,D] (== local when W==1)
   float* const* peer_all;      // device table [W][K] of peers' gather buffers (W>1)
@@ -139,7 +140,9 @@ __device__ __forceinline__ float lse_combine(const float2* parts, int n) {
   return m + logf(l);
 }
 
-__global__ void __launch_bounds__(LOSS_THREADS) mclip_loss_kernel(const LossDev p) {
+__global__ void __launch_bounds__(LOSS_THREADS) mclip_loss_kernel(const LossDev p_in) {
+  LossDev p = p_in;
+  if (p.scale_dev) p.scale = *p.scale_dev;
   cg::grid_group grid = cg::this_grid();
   __shared__ __align__(16) float Xs[LT_K][LT_M + 4];
   __shared__ __align__(16) float Ys[LT_K][LT_N + 4];
@@ -396,6 +399,7 @@ extern "C" int mclip_contrastive_loss(const mclip_loss_args* a, void* stream_) {
   p.W = a->world; p.rank = a->rank; p.B = a->batch; p.D = a->dim; p.K = a->n_tensors; p.P = a->n_pairs;
   p.WB = loss_tiles(p.W, p.B, &p.nI32, &p.nJ64, &p.nLB32);
   p.scale = a->logit_scale;
+  p.scale_dev = a->logit_scale_dev;
   for (int k = 0; k < p.K; ++k) {
     MCLIP_REQUIRE(a->local[k] && a->grad[k], "tensor %d: null pointer", k);
     p.local[k] = a->local[k];

@@ -175,6 +175,11 @@ def _forward(net, images, training, drop_rowscales, dropout_mult, want_raw):
     x = None               # materialised block input [N,H,W,C] bf16
     for i, blk in enumerate(net._blocks):
         g = blk.geom
+        if g.expand and pending is not None:
+            # (never the case for B0-B7, whose first stage has expand_ratio 1) the expand GEMM needs a materialised input
+            x, _ = ops.ew_forward(pending[0].view(n, h * w, -1), bn=pending[1], act=1)
+            x, pending = x.view(n, h, w, -1), None
+            S["stem_materialised"] = True
         B = {"x_in": x, "h": h, "w": w}
         if g.expand:
             y0, st = ops.gemm_tn(x.view(n * h * w, g.cin), wc.bf16[("e", i)], want_stats=training)
@@ -289,6 +294,13 @@ def _backward(net, S, dfeat):
                 dxd, _ = ops.ew_forward(dxd.view(n, h * w, g.cin), residual=dx.view(n, h * w, g.cin))
             dx = dxd.view(n, h, w, g.cin)
         del dy1
+    if S.get("stem_materialised"):
+        ys, bns = S["stem"]
+        nn_, hs, ws, cs = ys.shape
+        dys = _bn_backward(ys.view(nn_, hs * ws, cs), bns, training, net._bn0, grads, "_bn0", 1, du=dx.view(nn_, hs * ws, cs))
+        dws = torch.empty_like(net._conv_stem.weight)
+        ops.stem_wgrad(S["images"], dys.view(nn_, hs, ws, cs), geom.stem_pads, dws)
+        grads["_conv_stem.weight"] = dws
     return grads
 
 
@@ -315,12 +327,12 @@ class EfficientNet(nn.Module):
     """Drop-in for the reference EfficientNet (efficientnet_custom.py:143).  `num_classes`, `include_top`, `advprop`,
     `weights_path` are accepted for signature compatibility; this copy has no `_fc` either (:211 is commented out)."""
 
-    def __init__(self, model_name="efficientnet-b2", stochastic=True):
+    def __init__(self, model_name="efficientnet-b2", stochastic=True, geometry=None):
         super().__init__()
         if model_name not in VALID_MODELS:
             raise ValueError("model_name should be one of: " + ", ".join(VALID_MODELS))
         self.model_name = model_name
-        self.geom = net_geometry(model_name)
+        self.geom = geometry if geometry is not None else net_geometry(model_name)   # `geometry`: truncated towers in tests
         g = self.geom
         self._conv_stem = _ConvParams(g.stem_out, 3, 3)
         self._bn0 = _BNParams(g.stem_out)

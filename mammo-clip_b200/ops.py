@@ -15,7 +15,7 @@ def _require_cuda(*tensors):
 
 # ------------------------------------------------------------------------------------------------ GEMMs
 
-def gemm_tn(a, b, out=None, bias=None, residual=None, act=0, want_stats=None):
+def gemm_tn(a, b, out=None, bias=None, residual=None, act=0, want_stats=None, dropmask=None, drop_scale=1.0):
     """out[b,m,n] = epi(sum_k a[b,m,k] * w[b|0,n,k]).  a: [M,K] or [Bt,M,K] bf16; b: [N,K] or [Bt,N,K] bf16.
     want_stats=None: returns out (bf16).  want_stats=True/False: returns (out, stats[slots,2,N] fp32 or None)."""
     _require_cuda(a, b)
@@ -39,6 +39,9 @@ def gemm_tn(a, b, out=None, bias=None, residual=None, act=0, want_stats=None):
         r3 = residual if residual.dim() == 3 else residual.unsqueeze(0)
         g.residual, g.ldr, g.r_batch_stride = r3.data_ptr(), r3.stride(1), r3.stride(0) if bt > 1 else 0
     g.act = act
+    if dropmask is not None:
+        assert dropmask.dtype == torch.uint8 and dropmask.is_contiguous() and dropmask.numel() == bt * m * n
+        g.dropmask, g.drop_scale = dropmask.data_ptr(), drop_scale
     stats = None
     if want_stats:
         slots = lib().mclip_gemm_tn_stat_slots(m, n, bt)
@@ -97,7 +100,11 @@ def contrastive_loss_raw(local, pairs, scale, world=1, rank=0, symm=None):
         args.local[k], args.grad[k] = t.data_ptr(), g.data_ptr()
     for i, (a, b, wr, wc, eps) in enumerate(pairs):
         args.pair_a[i], args.pair_b[i], args.w_row[i], args.w_col[i], args.label_smoothing[i] = a, b, wr, wc, eps
-    args.logit_scale = float(scale)
+    if torch.is_tensor(scale):
+        assert scale.is_cuda and scale.dtype == torch.float32 and scale.numel() == 1
+        args.logit_scale_dev = scale.data_ptr()
+    else:
+        args.logit_scale = float(scale)
     need = lib().mclip_loss_workspace_bytes(world, B, D, P)
     key = (dev.index, need)
     ws = _loss_ws.get(key)
@@ -382,3 +389,34 @@ def adamw_step(param, grad, exp_avg, exp_avg_sq, lr, beta1, beta2, eps, weight_d
     check(lib().mclip_adamw_step(ptr(param), ptr(grad), ptr(exp_avg), ptr(exp_avg_sq), C.c_longlong(param.numel()), C.c_float(lr), C.c_float(beta1),
                                  C.c_float(beta2), C.c_float(eps), C.c_float(weight_decay), C.c_longlong(step), C.c_float(grad_scale), stream_ptr()),
           "mclip_adamw_step")
+
+
+# ------------------------------------------------------------------------------------------------ BERT pieces
+from ._lib import BertEmbedArgs  # noqa: E402
+
+
+def bert_embed_ln(ids, tts, word, pos, typ, gamma, beta, eps, dropmask=None, drop_scale=1.0):
+    b, l = ids.shape
+    h = word.shape[1]
+    out = torch.empty((b * l, h), dtype=torch.bfloat16, device=ids.device)
+    a = BertEmbedArgs()
+    a.batch, a.seq_len, a.hidden, a.vocab, a.max_positions = b, l, h, word.shape[0], pos.shape[0]
+    a.input_ids, a.token_type_ids = ids.data_ptr(), _p(tts)
+    a.word, a.pos, a.type, a.gamma, a.beta, a.eps = word.data_ptr(), pos.data_ptr(), typ.data_ptr(), gamma.data_ptr(), beta.data_ptr(), eps
+    a.dropmask, a.drop_scale, a.out = _p(dropmask), drop_scale, out.data_ptr()
+    check(lib().mclip_bert_embed_ln(C.byref(a), stream_ptr()), "mclip_bert_embed_ln")
+    return out
+
+
+def layernorm(x, gamma, beta, eps):
+    rows, h = x.shape
+    out = torch.empty_like(x)
+    check(lib().mclip_layernorm(ptr(x), ptr(gamma), ptr(beta), C.c_float(eps), ptr(out), rows, h, stream_ptr()), "mclip_layernorm")
+    return out
+
+
+def bert_attention(qkv, attention_mask, batch, seq_len, heads, head_dim, dropmask=None, drop_scale=1.0):
+    out = torch.empty((batch * seq_len, heads * head_dim), dtype=torch.bfloat16, device=qkv.device)
+    check(lib().mclip_bert_attention(ptr(qkv), ptr(attention_mask), ptr(dropmask), C.c_float(drop_scale), ptr(out), batch, seq_len, heads, head_dim,
+                                     stream_ptr()), "mclip_bert_attention")
+    return out

@@ -161,6 +161,12 @@ def _bn(c):
     return nn.BatchNorm2d(c, momentum=BN_MOMENTUM, eps=BN_EPS)
 
 
+def _q(t, on):
+    """bf16 storage emulation: round to bf16 and back (what autocast does after every op in the reference's AMP path,
+    trainer_ddp.py:293-296, and what the CUDA path does at its storage points).  Off by default (pure fp32 oracle)."""
+    return t.to(torch.bfloat16).to(t.dtype) if on else t
+
+
 class OracleMBConv(nn.Module):
     """efficientnet_custom.py:36-132."""
 
@@ -177,32 +183,40 @@ class OracleMBConv(nn.Module):
         self._project_conv = _Conv(b.cexp, b.cout, 1, 1, 1, False, (0, 0, 0, 0))
         self._bn2 = _bn(b.cout)
 
-    def forward(self, x, drop_rate: float, drop_mask: Optional[torch.Tensor] = None):
+    def forward(self, x, drop_rate: float, drop_mask: Optional[torch.Tensor] = None, emulate: bool = False):
         inp = x
         if self.spec.expand:
-            x = swish(self._bn0(self._expand_conv(x)))                 # :104-107
-        x = swish(self._bn1(self._depthwise_conv(x)))                  # :109-111
-        sq = x.mean(dim=(2, 3), keepdim=True)                          # :115
-        sq = self._se_expand(swish(self._se_reduce(sq)))               # :116-118
-        x = torch.sigmoid(sq) * x                                      # :119
-        x = self._bn2(self._project_conv(x))                           # :122-123
+            y = F.conv2d(x, _q(self._expand_conv.weight, emulate)) if emulate else self._expand_conv(x)
+            x = _q(swish(self._bn0(_q(y, emulate))), emulate)            # :104-107
+        x = _q(self._depthwise_conv(x), emulate)                          # :109
+        x = _q(swish(self._bn1(x)), emulate)                              # :110-111
+        sq = x.mean(dim=(2, 3), keepdim=True)                             # :115
+        sq = self._se_expand(swish(self._se_reduce(sq)))                  # :116-118
+        if emulate:
+            # same algebra as :119,122 with the gate folded into per-sample project weights (the CUDA path's form)
+            wg = _q(self._project_conv.weight[None, :, :, 0, 0] * torch.sigmoid(sq)[:, None, :, 0, 0], True)
+            x = _q(torch.einsum("nchw,noc->nohw", x, wg), True)
+        else:
+            x = torch.sigmoid(sq) * x                                     # :119
+            x = self._project_conv(x)                                     # :122
+        x = self._bn2(x)                                                  # :123
         if self.spec.skip:
-            if drop_rate and self.training:                            # :129-130, utils:129-154
+            if drop_rate and self.training:                               # :129-130, utils:129-154
                 keep = 1.0 - drop_rate
                 if drop_mask is None:
                     drop_mask = torch.floor(keep + torch.rand(x.shape[0], 1, 1, 1, dtype=x.dtype, device=x.device))
                 x = x / keep * drop_mask.view(-1, 1, 1, 1).to(x.dtype)
-            x = x + inp                                                # :131
-        return x
+            x = x + inp                                                   # :131
+        return _q(x, emulate)
 
 
 class OracleEfficientNet(nn.Module):
-    """efficientnet_custom.py:143-313.  `drop_masks` / `dropout_mask` let a test inject the Bernoulli
-    draws so the stochastic train path can be compared bit-for-bit in distribution-free form."""
+    """efficientnet_custom.py:143-313.  `drop_masks` / `dropout_mask` let a test inject the Bernoulli draws so the
+    stochastic train path can be compared; `emulate_bf16` rounds stored activations / GEMM weights to bf16."""
 
-    def __init__(self, name: str):
+    def __init__(self, name: str, spec: Optional[NetSpec] = None):
         super().__init__()
-        sp = effnet_spec(name)
+        sp = spec if spec is not None else effnet_spec(name)     # `spec`: truncated towers for block-level tests
         self.spec = sp
         self._conv_stem = _Conv(3, sp.stem_out, 3, 2, 1, False, sp.stem_pad)
         self._bn0 = _bn(sp.stem_out)
@@ -211,14 +225,17 @@ class OracleEfficientNet(nn.Module):
         self._bn1 = _bn(sp.head_out)
         self.out_dim = sp.head_out
         self.stochastic = True   # set False to disable drop-connect/dropout in train mode (parity runs)
+        self.emulate_bf16 = False
 
     def extract_features(self, x, drop_masks=None):
-        x = swish(self._bn0(self._conv_stem(x)))                       # :273
+        e = self.emulate_bf16
+        x = _q(swish(self._bn0(_q(self._conv_stem(x), e))), e)           # :273
         n = len(self._blocks)
         for i, blk in enumerate(self._blocks):
             rate = DROP_CONNECT * float(i) / n if self.stochastic else 0.0   # :277-279
-            x = blk(x, rate, None if drop_masks is None else drop_masks.get(i))
-        return swish(self._bn1(self._conv_head(x)))                    # :283
+            x = blk(x, rate, None if drop_masks is None else drop_masks.get(i), e)
+        y = F.conv2d(x, _q(self._conv_head.weight, e)) if e else self._conv_head(x)
+        return _q(swish(self._bn1(_q(y, e))), e)                         # :283
 
     def forward(self, inputs, drop_masks=None, dropout_mask=None):
         as_dict = isinstance(inputs, dict) and "image" in inputs       # :298-305
