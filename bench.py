@@ -1,0 +1,312 @@
+#!/usr/bin/env python
+"""Benchmark of the Mammo-CLIP contrastive pre-training step (BASELINE.json metric: image-text pairs/sec).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c3|c2|c1]
+
+One step = forward (EfficientNet + BERT + projection heads + L2-norm) + fused InfoNCE (+ NVLink gather) + backward +
+gradient all-reduce (N>1) + AdamW, on synthetic data of the named shape with seeded random-init weights.
+  value : whole-job pairs/s with the batch already resident in HBM (CUDA events, barrier + sync on both sides, max over ranks)
+  e2e   : the same step through the public API with HOST buffers: pinned host -> device copy of images/tokens and a
+          device -> host read of the loss inside every timed step
+  roofline     : the dominant kernel class of the step (HBM bound), algorithmic bytes / event-timed duration, live
+  cpu_baseline : the oracle (PyTorch restatement of the reference path) on this box's host cores, bounded sample
+--impl reference times that CPU path alone (the reference is pure Python and cannot travel to the GPU box; the oracle
+is its pinned restatement, see oracle/port.py).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (encoder config string, oracle encoder name, BERT layers, per-GPU batch, H, W, L)
+    "c1": ("tf_efficientnetv2-detect", "efficientnet-b2", 2, 4, 224, 224, 32),
+    "c2": ("tf_efficientnetv2-detect", "efficientnet-b2", 12, 32, 912, 912, 64),
+    "c3": ("tf_efficientnet_b5_ns-detect", "efficientnet-b5", 12, 64, 1520, 912, 64),
+}
+# algorithmic work per pair of the training step (SURVEY.md §8d / BASELINE.md §4): image tower fwd+dgrad+wgrad
+ALGO = {"c1": (0.117e9, 3.9e9), "c2": (1.96e9, 66.2e9), "c3": (7.79e9, 393.7e9)}     # (bytes, flops) per pair
+
+
+def _peaks():
+    try:
+        p = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        return float(p["hbm_gbs"]), float(p.get("bf16_tflops_sustained", p["bf16_tflops"])), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return 6650.0, 1400.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region."""
+    Q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200", "-i", str(self.index)],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=lambda: self.lines.extend(self.proc.stdout), daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        self.t.join(timeout=2)
+        sm, mx, reasons = [], None, set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx = float(f[2])
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def _model_cfg(enc_cfg_name, layers, dropout=0.1):
+    from transformers import BertConfig
+    from mammoclip_b200.model.modules.text_encoder import BERT_BASE_CASED
+    bcfg = BertConfig(**dict(BERT_BASE_CASED, num_hidden_layers=layers, hidden_dropout_prob=dropout, attention_probs_dropout_prob=dropout))
+    cfg = {"name": "clip_custom",
+           "image_encoder": {"source": "cnn", "name": enc_cfg_name, "pretrained": True, "model_type": "cnn"},
+           "text_encoder": {"source": "huggingface", "name": "offline-bert", "pretrained": False, "gradient_checkpointing": False,
+                            "pooling": "eos", "cache_dir": "/tmp/none", "trust_remote_code": False, "config": bcfg},
+           "projection_head": {"name": "linear", "proj_dim": 512, "dropout": 0.1}, "temperature": 0.07}
+    loss_cfg = {"breast_clip_contrastive": {"label_smoothing": 0.0, "i2i_weight": 1.0, "t2t_weight": 0.5, "loss_ratio": 1.0}}
+    return cfg, loss_cfg
+
+
+def _synth_host(batch, h, w, L, rank):
+    """SURVEY §8d synthetic batch in pinned host memory: images [B,3,H,W] fp32 with NHWC strides, 3 identical channels."""
+    import torch
+    g = torch.Generator().manual_seed(1234 + rank)
+    img = torch.randn(batch, h, w, 1, generator=g).expand(batch, h, w, 3).contiguous().pin_memory()
+    lens = torch.randint(8, L + 1, (batch,), generator=g)
+    ids = torch.randint(1000, 28996, (batch, L), generator=g)
+    mask = (torch.arange(L)[None, :] < lens[:, None]).long()
+    ids[:, 0] = 101
+    ids[torch.arange(batch), lens - 1] = 102
+    ids = ids * mask
+    tok = {"input_ids": ids.pin_memory(), "token_type_ids": torch.zeros_like(ids).pin_memory(), "attention_mask": mask.pin_memory()}
+    return img, tok
+
+
+# ------------------------------------------------------------------------------------------------------------------
+def cpu_reference_run(workload, steps, warmup, sample_batch, report_sample=True):
+    """Times the oracle (CPU, fp32, all host threads) on `sample_batch` pairs per step of the named workload."""
+    import torch
+    from transformers import BatchEncoding
+    from oracle import port
+    enc_cfg, enc_name, layers, batch, h, w, L = WORKLOADS[workload]
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    torch.manual_seed(0)
+    model = port.OracleBreastClip(enc_name, num_hidden_layers=layers)
+    model.train()
+    opt = torch.optim.AdamW(model.parameters(), lr=5e-5, weight_decay=1e-4)
+    b = min(sample_batch, batch)
+    data = {"images": port.synth_images(b, h, w, seed=1234), "text_tokens": BatchEncoding(port.synth_tokens(b, L, seed=4321))}
+    times = []
+    for i in range(warmup + steps):
+        t0 = time.perf_counter()
+        opt.zero_grad(set_to_none=True)
+        out = model(data)
+        loss = port.contrastive_loss(**out, is_train=True, label_smoothing=0.0)
+        loss.backward()
+        opt.step()
+        if i >= warmup:
+            times.append(time.perf_counter() - t0)
+    sec = sum(times) / len(times)
+    return {"value": b / sec, "unit": "pairs/s", "cores": cores, "kind": "port",
+            "sample": f"{len(times)} step(s) of {b} pair(s) of {workload} ({enc_name}, {h}x{w}, L={L}, BERT {layers} layers), fwd+loss+bwd+AdamW, fp32, {sec:.2f} s/step"}, sec
+
+
+def run_reference(args):
+    """`--impl reference`: rank 0 times the CPU path; other ranks exit 0 without work."""
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
+    sample = 1 if args.workload == "c3" else 2 if args.workload == "c2" else 4
+    steps = max(1, min(args.steps, 8))
+    warm = max(0, min(args.warmup, 1))
+    base, sec = cpu_reference_run(args.workload, steps, warm, sample)
+    enc_cfg, enc_name, layers, batch, h, w, L = WORKLOADS[args.workload]
+    line = {"impl": "reference", "metric": "image-text pairs/sec", "value": base["value"], "unit": "pairs/s", "n_gpus": args.gpus, "steps": steps,
+            "warmup": warm, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic", "config": {"workload": f"{args.workload}: {enc_name} + BERT-{layers}L, {h}x{w}, L={L}, contrastive step on host cores",
+                                           "sample_pairs_per_step": sample},
+            "cpu_baseline": base, "e2e": {"value": base["value"], "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from transformers import BatchEncoding
+    from mammoclip_b200 import _lib
+    from mammoclip_b200.loss import build_loss
+    from mammoclip_b200.model import build_model
+    from mammoclip_b200.optim import FlatAdamW
+    from mammoclip_b200.util import GlobalEnv
+
+    rank, world, local = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("LOCAL_RANK", "0"))
+    if args.gpus > 1 and world == 1:
+        raise SystemExit("for --gpus N > 1 launch through torch.distributed.run (see the module docstring)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    GlobalEnv.reset()
+    _lib.check(_lib.lib().mclip_device_check(), "mclip_device_check")
+
+    enc_cfg, enc_name, layers, batch, h, w, L = WORKLOADS[args.workload]
+    if args.batch:
+        batch = args.batch
+    cfg, loss_cfg = _model_cfg(enc_cfg, layers)
+
+    class Tok:
+        vocab_size = 28996
+
+    torch.manual_seed(0)
+    model = build_model(cfg, loss_cfg, Tok()).to(dev).train()
+    loss_fn = build_loss(loss_cfg)
+    opt = FlatAdamW(model.parameters(), lr=5e-5, weight_decay=1e-4)
+    img_h, tok_h = _synth_host(batch, h, w, L, rank)
+    img_d = img_h.to(dev, non_blocking=True).permute(0, 3, 1, 2)
+    tok_d = BatchEncoding({k: v.to(dev, non_blocking=True) for k, v in tok_h.items()})
+    h2d_bytes = img_h.numel() * 4 + sum(v.numel() * 8 for v in tok_h.values())
+
+    def step(images, tokens):
+        opt.zero_grad()
+        out = model({"images": images, "text_tokens": tokens}, dev)
+        loss = loss_fn(**out, is_train=True)["total"]
+        loss.backward()
+        scale = opt.all_reduce_grads(world)
+        opt.step(grad_scale=scale)
+        return loss
+
+    def step_e2e():
+        images = img_h.to(dev, non_blocking=True).permute(0, 3, 1, 2)
+        tokens = BatchEncoding({k: v.to(dev, non_blocking=True) for k, v in tok_h.items()})
+        return step(images, tokens).item()          # device -> host read of the loss
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, n):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        a.record()
+        for _ in range(n):
+            fn()
+        b.record()
+        barrier()
+        ms = torch.tensor([a.elapsed_time(b)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return ms.item()
+
+    # ---- warm-up, then a calibration step that event-times every kernel class to find the dominant one ----
+    for _ in range(max(args.warmup, 3)):
+        step(img_d, tok_d)
+    torch.cuda.synchronize()
+    classes = ["mclip_gemm_tn", "mclip_gemm_wgrad", "mclip_dwconv_forward", "mclip_dwconv_backward", "mclip_ew_forward", "mclip_ew_backward",
+               "mclip_stem_forward", "mclip_stem_wgrad"]
+    _lib.PROF.enable(classes)
+    step(img_d, tok_d)
+    calib = _lib.PROF.summary()
+    dominant = max(calib, key=lambda k: calib[k][1]) if calib else "mclip_gemm_tn"
+    share = {k: round(v[1], 3) for k, v in calib.items()}
+
+    # ---- timed region: device-resident inputs; only the dominant class carries event pairs ----
+    _lib.PROF.reset()
+    _lib.PROF.enable([dominant])
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ms_total = timed(lambda: step(img_d, tok_d), args.steps)
+    clocks = sampler.stop() if rank == 0 else None
+    launches = _lib.PROF.launches()
+    dom = _lib.PROF.summary().get(dominant, (0, 0.0, 0))
+    _lib.PROF.enable([])
+
+    # ---- end-to-end: host buffers, H2D + D2H inside the timed region ----
+    step_e2e()
+    e2e_steps = max(2, min(args.steps, 10))
+    ms_e2e = timed(step_e2e, e2e_steps)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    ms_step = ms_total / args.steps
+    pairs = batch * world
+    value = pairs / (ms_step * 1e-3)
+    hbm_peak, tf_peak, peak_src = _peaks()
+    achieved = (dom[2] / 1e9) / (dom[1] * 1e-3) if dom[1] > 0 else 0.0
+    bytes_pair, flops_pair = ALGO[args.workload]
+    line = {
+        "metric": "image-text pairs/sec", "value": value, "unit": "pairs/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+        "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+        "config": {"workload": f"{args.workload}: {enc_name} + BERT-{layers}L (random init), batch {batch}/GPU, {h}x{w} 3-ch fp32 images, {L}-token text, "
+                               f"single-view InfoNCE, fwd+loss+bwd+grad-allreduce+AdamW, train mode (drop-connect/dropout on)",
+                   "l2": "inputs larger than L2 (images %.0f MB/step, activations GBs); no explicit flush" % (img_h.numel() * 4 / 1e6),
+                   "parallelism": f"dp{world}"},
+        "clocks": clocks,
+        "e2e": {"value": pairs / (ms_e2e / e2e_steps * 1e-3), "unit": "pairs/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4,
+                "steps": e2e_steps},
+        "gpu_launches": launches,
+        "roofline": {"bound": "hbm", "kernel": dominant, "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
+                     "traffic": None, "launches": dom[0], "avg_launch_ms": dom[1] / max(dom[0], 1), "peak_source": peak_src,
+                     "step_share_ms": share,
+                     "whole_step": {"algorithmic_gb_per_pair": bytes_pair / 1e9, "achieved_gbs": value / world * bytes_pair / 1e9,
+                                    "frac_of_hbm": value / world * bytes_pair / 1e9 / hbm_peak,
+                                    "tensor_tflops": value / world * flops_pair / 1e12, "frac_of_bf16": value / world * flops_pair / 1e12 / tf_peak}},
+    }
+    if world == 1 and not args.no_cpu:
+        sample = 1 if args.workload == "c3" else 2 if args.workload == "c2" else 4
+        line["cpu_baseline"], _ = cpu_reference_run(args.workload, 2 if args.workload == "c3" else 3, 1, sample)
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=8)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="c3", choices=list(WORKLOADS))
+    ap.add_argument("--batch", type=int, default=0, help="debug only: override the per-GPU batch of the workload")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

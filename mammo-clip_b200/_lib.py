@@ -88,6 +88,57 @@ def check(rc: int, what: str = ""):
         raise MclipError(f"{what} failed ({rc}): {msg}")
 
 
+# kernels launched per ABI call (for bench.py's `gpu_launches`); default 1
+LAUNCHES = {"mclip_gemm_wgrad": 2, "mclip_dwconv_backward": 2, "mclip_se_fc_backward": 2, "mclip_stem_wgrad": 2}
+
+
+class Profiler:
+    """Launch counter + optional CUDA-event timing per ABI entry point (events on torch's current stream, which is the
+    stream every kernel is launched on).  Timing is off unless `enable(names)` was called (bench.py roofline leg)."""
+
+    def __init__(self):
+        self.counts, self.timed, self.records = {}, None, {}
+
+    def reset(self):
+        self.counts, self.records = {}, {}
+
+    def enable(self, names):
+        self.timed = set(names) if names is not None else None
+        self.records = {}
+
+    def launches(self):
+        return sum(LAUNCHES.get(k, 1) * v for k, v in self.counts.items())
+
+    def summary(self):
+        """-> {name: (calls, total_ms, total_bytes)} for timed entry points (synchronises)."""
+        import torch
+        torch.cuda.synchronize()
+        out = {}
+        for name, recs in self.records.items():
+            ms = sum(a.elapsed_time(b) for a, b, _ in recs)
+            out[name] = (len(recs), ms, sum(n for _, _, n in recs))
+        return out
+
+
+PROF = Profiler()
+
+
+def call(name, *args, nbytes=0):
+    """Invoke C-ABI entry `name(*args, stream)`; raises MclipError on a non-zero return code."""
+    import torch
+    fn = getattr(lib(), name)
+    PROF.counts[name] = PROF.counts.get(name, 0) + 1
+    if PROF.timed is not None and name in PROF.timed:
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        rc = fn(*args, stream_ptr())
+        b.record()
+        PROF.records.setdefault(name, []).append((a, b, nbytes))
+    else:
+        rc = fn(*args, stream_ptr())
+    check(rc, name)
+
+
 def stream_ptr():
     import torch
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)

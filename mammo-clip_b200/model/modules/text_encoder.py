@@ -8,6 +8,12 @@ from torch import nn
 from transformers import AutoConfig, BertModel
 
 
+# Bio_ClinicalBERT == BERT-base-cased geometry (no hub access here: weights are random-init unless a local path is given)
+BERT_BASE_CASED = dict(vocab_size=28996, hidden_size=768, num_hidden_layers=12, num_attention_heads=12, intermediate_size=3072,
+                       max_position_embeddings=512, type_vocab_size=2, hidden_act="gelu", layer_norm_eps=1e-12,
+                       hidden_dropout_prob=0.1, attention_probs_dropout_prob=0.1)
+
+
 class HuggingfaceTextEncoder(nn.Module):
     def __init__(self, name="bert-base-uncased", vocab_size=None, pretrained=True, gradient_checkpointing=False,
                  cache_dir="~/.cache/huggingface/hub", local_files_only=False, trust_remote_code=False, config=None):

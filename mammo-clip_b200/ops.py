@@ -4,7 +4,7 @@ import ctypes as C
 import torch
 
 from . import _lib
-from ._lib import GemmArgs, LossArgs, WgradArgs, check, lib, ptr, stream_ptr
+from ._lib import GemmArgs, LossArgs, WgradArgs, call, check, lib, ptr, stream_ptr
 
 
 def _require_cuda(*tensors):
@@ -47,7 +47,7 @@ def gemm_tn(a, b, out=None, bias=None, residual=None, act=0, want_stats=None, dr
         slots = lib().mclip_gemm_tn_stat_slots(m, n, bt)
         stats = torch.empty((slots, 2, n), dtype=torch.float32, device=a.device)
         g.stats, g.stat_slots = stats.data_ptr(), slots
-    check(lib().mclip_gemm_tn(C.byref(g), stream_ptr()), "mclip_gemm_tn")
+    call("mclip_gemm_tn", C.byref(g), nbytes=2 * (bt * m * k + n * k * (bt if b_batched else 1) + bt * m * n * (2 if residual is not None else 1)))
     return out if want_stats is None else (out, stats)
 
 
@@ -74,7 +74,7 @@ def gemm_wgrad(a, b, out=None, accumulate=False):
     g.out, g.ldo, g.accumulate = out.data_ptr(), out.stride(0), int(accumulate)
     g.r, g.i, g.j = r, i, j
     g.workspace, g.workspace_bytes = ws.data_ptr(), ws.numel()
-    check(lib().mclip_gemm_wgrad(C.byref(g), stream_ptr()), "mclip_gemm_wgrad")
+    call("mclip_gemm_wgrad", C.byref(g), nbytes=2 * r * (i + j) + 4 * i * j)
     return out
 
 
@@ -116,7 +116,7 @@ def contrastive_loss_raw(local, pairs, scale, world=1, rank=0, symm=None):
     args.out = out.data_ptr()
     if world > 1:
         symm.fill_args(args, K)
-    check(lib().mclip_contrastive_loss(C.byref(args), stream_ptr()), "mclip_contrastive_loss")
+    call("mclip_contrastive_loss", C.byref(args))
     return out, grads
 
 
@@ -150,7 +150,7 @@ def bn_finalize(partials, count, gamma, beta, running_mean, running_var, num_bat
     a.num_batches_tracked = _p(num_batches)
     a.momentum, a.eps = momentum, eps
     a.scale, a.shift, a.mean, a.invstd = st.scale.data_ptr(), st.shift.data_ptr(), st.mean.data_ptr(), st.invstd.data_ptr()
-    check(lib().mclip_bn_finalize(C.byref(a), stream_ptr()), "mclip_bn_finalize")
+    call("mclip_bn_finalize", C.byref(a))
     return st
 
 
@@ -174,7 +174,7 @@ def stem_forward(images, weight, pads, want_stats=True):
         slots = lib().mclip_stem_slots(n, ho, wo)
         stats = torch.empty((slots, 2, c), dtype=torch.float32, device=images.device)
         a.stats, a.stat_slots = stats.data_ptr(), slots
-    check(lib().mclip_stem_forward(C.byref(a), stream_ptr()), "mclip_stem_forward")
+    call("mclip_stem_forward", C.byref(a), nbytes=4 * images.numel() + 2 * out.numel())
     return out, stats
 
 
@@ -191,7 +191,7 @@ def stem_wgrad(images, dy, pads, dweight):
     slots = lib().mclip_stem_slots(n, ho, wo)
     part = torch.empty((slots, 27, c), dtype=torch.float32, device=dy.device)
     a.stat_slots, a.dy, a.dweight, a.accumulate, a.dw_partials = slots, dy.data_ptr(), dweight.data_ptr(), 0, part.data_ptr()
-    check(lib().mclip_stem_wgrad(C.byref(a), stream_ptr()), "mclip_stem_wgrad")
+    call("mclip_stem_wgrad", C.byref(a), nbytes=4 * images.numel() + 2 * dy.numel())
     return dweight
 
 
@@ -220,7 +220,7 @@ def dwconv_forward(x, weight, k, stride, pads, bn=None, want_stats=True):
         slots = lib().mclip_dwconv_slots(C.byref(a), 0)
         stats = torch.empty((slots, 2, a.c), dtype=torch.float32, device=x.device)
         a.stats, a.stat_slots = stats.data_ptr(), slots
-    check(lib().mclip_dwconv_forward(C.byref(a), stream_ptr()), "mclip_dwconv_forward")
+    call("mclip_dwconv_forward", C.byref(a), nbytes=2 * (x.numel() + out.numel()))
     return out, stats
 
 
@@ -235,7 +235,7 @@ def dwconv_backward(x, weight, k, stride, pads, dy, dweight, bn=None):
     if bn is not None:
         bnp = torch.empty((slots, 2, a.c), dtype=torch.float32, device=x.device)
         a.bn_partials, a.in_mean, a.in_invstd = bnp.data_ptr(), bn.mean.data_ptr(), bn.invstd.data_ptr()
-    check(lib().mclip_dwconv_backward(C.byref(a), stream_ptr()), "mclip_dwconv_backward")
+    call("mclip_dwconv_backward", C.byref(a), nbytes=2 * (2 * x.numel() + dy.numel()))
     return dx, bnp
 
 
@@ -262,14 +262,14 @@ def ew_forward(y, bn=None, act=0, rowscale=None, residual=None, write=True, pool
         a.chunks = ew_chunks(n, hw, c)
         part = torch.empty((n, a.chunks, c), dtype=torch.float32, device=y.device)
         a.pool_partials = part.data_ptr()
-    check(lib().mclip_ew_forward(C.byref(a), stream_ptr()), "mclip_ew_forward")
+    call("mclip_ew_forward", C.byref(a), nbytes=2 * y.numel() * (1 + int(write) + int(residual is not None)))
     return out, part
 
 
 def pool_finalize(part, hw, mult=None):
     n, chunks, c = part.shape
     out = torch.empty((n, c), dtype=torch.float32, device=part.device)
-    check(lib().mclip_pool_finalize(ptr(part), n, chunks, c, hw, ptr(mult), ptr(out), stream_ptr()), "mclip_pool_finalize")
+    call("mclip_pool_finalize", ptr(part), n, chunks, c, hw, ptr(mult), ptr(out))
     return out
 
 
@@ -284,7 +284,7 @@ def se_fc(part, hw, w1, b1, w2, b2):
     a.n, a.hw, a.c, a.cse, a.chunks = n, hw, c, cse, chunks
     a.pool_partials, a.w1, a.b1, a.w2, a.b2 = part.data_ptr(), w1.data_ptr(), b1.data_ptr(), w2.data_ptr(), b2.data_ptr()
     a.pooled, a.z1, a.gate = pooled.data_ptr(), z1.data_ptr(), gate.data_ptr()
-    check(lib().mclip_se_fc(C.byref(a), stream_ptr()), "mclip_se_fc")
+    call("mclip_se_fc", C.byref(a))
     return pooled, z1, gate
 
 
@@ -300,7 +300,7 @@ def se_fc_backward(dg_part, hw, w1, w2, pooled, z1, gate, dw1, db1, dw2, db2):
     a.w1, a.w2, a.pooled, a.z1, a.gate = w1.data_ptr(), w2.data_ptr(), pooled.data_ptr(), z1.data_ptr(), gate.data_ptr()
     a.dgate_partials, a.dz2, a.dz1, a.dpool = dg_part.data_ptr(), dz2.data_ptr(), dz1.data_ptr(), dpool.data_ptr()
     a.dw1, a.db1, a.dw2, a.db2 = dw1.data_ptr(), db1.data_ptr(), dw2.data_ptr(), db2.data_ptr()
-    check(lib().mclip_se_fc_backward(C.byref(a), stream_ptr()), "mclip_se_fc_backward")
+    call("mclip_se_fc_backward", C.byref(a))
     return dpool
 
 
@@ -309,7 +309,7 @@ def se_scale_weights(w, gate):
     cout, cexp = w.shape[0], w.shape[1]
     n = gate.shape[0]
     out = torch.empty((n, cout, cexp), dtype=torch.bfloat16, device=w.device)
-    check(lib().mclip_se_scale_weights(ptr(w), ptr(gate), ptr(out), n, cout, cexp, stream_ptr()), "mclip_se_scale_weights")
+    call("mclip_se_scale_weights", ptr(w), ptr(gate), ptr(out), n, cout, cexp)
     return out
 
 
@@ -331,15 +331,15 @@ def ew_backward(mode, y, bn, act, du=None, dvec=None, gate=None, dpool=None, row
     if mode != 0:
         out = torch.empty_like(y)
         a.out = out.data_ptr()
-    check(lib().mclip_ew_backward(C.byref(a), stream_ptr()), "mclip_ew_backward")
+    call("mclip_ew_backward", C.byref(a), nbytes=2 * y.numel() * (1 + int(du is not None) + int(mode != 0)))
     return part if mode == 0 else out if mode == 1 else (out, part)
 
 
 def bn_bwd_finalize(partials, count, training, dgamma, dbeta):
     slots, _, c = partials.shape
     cc = torch.empty((2, c), dtype=torch.float32, device=partials.device)
-    check(lib().mclip_bn_bwd_finalize(ptr(partials), slots, c, C.c_longlong(count), int(training), ptr(dgamma), ptr(dbeta), 0,
-                                      ptr(cc[0]), ptr(cc[1]), stream_ptr()), "mclip_bn_bwd_finalize")
+    call("mclip_bn_bwd_finalize", ptr(partials), slots, c, C.c_longlong(count), int(training), ptr(dgamma), ptr(dbeta), 0,
+                                      ptr(cc[0]), ptr(cc[1]))
     return cc[0], cc[1]
 
 
@@ -355,12 +355,12 @@ def weight_prep(entries, device):
 
 
 def weight_prep_run(table, n_entries):
-    check(lib().mclip_weight_prep(ptr(table), n_entries, stream_ptr()), "mclip_weight_prep")
+    call("mclip_weight_prep", ptr(table), n_entries)
 
 
 def cast_bf16(x):
     out = torch.empty(x.shape, dtype=torch.bfloat16, device=x.device)
-    check(lib().mclip_cast_bf16(ptr(x), ptr(out), C.c_longlong(x.numel()), stream_ptr()), "mclip_cast_bf16")
+    call("mclip_cast_bf16", ptr(x), ptr(out), C.c_longlong(x.numel()))
     return out
 
 
@@ -368,27 +368,26 @@ def l2norm_forward(x):
     rows, d = x.shape
     e = torch.empty((rows, d), dtype=torch.float32, device=x.device)
     nrm = torch.empty((rows,), dtype=torch.float32, device=x.device)
-    check(lib().mclip_l2norm_forward(ptr(x), ptr(e), ptr(nrm), rows, d, stream_ptr()), "mclip_l2norm_forward")
+    call("mclip_l2norm_forward", ptr(x), ptr(e), ptr(nrm), rows, d)
     return e, nrm
 
 
 def l2norm_backward(e, de, nrm):
     rows, d = e.shape
     dx = torch.empty((rows, d), dtype=torch.bfloat16, device=e.device)
-    check(lib().mclip_l2norm_backward(ptr(e), ptr(de), ptr(nrm), ptr(dx), rows, d, stream_ptr()), "mclip_l2norm_backward")
+    call("mclip_l2norm_backward", ptr(e), ptr(de), ptr(nrm), ptr(dx), rows, d)
     return dx
 
 
 def colsum(x, out):
     rows, cols = x.shape
-    check(lib().mclip_colsum(ptr(x), ptr(out), rows, cols, C.c_longlong(x.stride(0)), 0, stream_ptr()), "mclip_colsum")
+    call("mclip_colsum", ptr(x), ptr(out), rows, cols, C.c_longlong(x.stride(0)), 0)
     return out
 
 
 def adamw_step(param, grad, exp_avg, exp_avg_sq, lr, beta1, beta2, eps, weight_decay, step, grad_scale=1.0):
-    check(lib().mclip_adamw_step(ptr(param), ptr(grad), ptr(exp_avg), ptr(exp_avg_sq), C.c_longlong(param.numel()), C.c_float(lr), C.c_float(beta1),
-                                 C.c_float(beta2), C.c_float(eps), C.c_float(weight_decay), C.c_longlong(step), C.c_float(grad_scale), stream_ptr()),
-          "mclip_adamw_step")
+    call("mclip_adamw_step", ptr(param), ptr(grad), ptr(exp_avg), ptr(exp_avg_sq), C.c_longlong(param.numel()), C.c_float(lr), C.c_float(beta1),
+                                 C.c_float(beta2), C.c_float(eps), C.c_float(weight_decay), C.c_longlong(step), C.c_float(grad_scale))
 
 
 # ------------------------------------------------------------------------------------------------ BERT pieces
@@ -404,19 +403,18 @@ def bert_embed_ln(ids, tts, word, pos, typ, gamma, beta, eps, dropmask=None, dro
     a.input_ids, a.token_type_ids = ids.data_ptr(), _p(tts)
     a.word, a.pos, a.type, a.gamma, a.beta, a.eps = word.data_ptr(), pos.data_ptr(), typ.data_ptr(), gamma.data_ptr(), beta.data_ptr(), eps
     a.dropmask, a.drop_scale, a.out = _p(dropmask), drop_scale, out.data_ptr()
-    check(lib().mclip_bert_embed_ln(C.byref(a), stream_ptr()), "mclip_bert_embed_ln")
+    call("mclip_bert_embed_ln", C.byref(a))
     return out
 
 
 def layernorm(x, gamma, beta, eps):
     rows, h = x.shape
     out = torch.empty_like(x)
-    check(lib().mclip_layernorm(ptr(x), ptr(gamma), ptr(beta), C.c_float(eps), ptr(out), rows, h, stream_ptr()), "mclip_layernorm")
+    call("mclip_layernorm", ptr(x), ptr(gamma), ptr(beta), C.c_float(eps), ptr(out), rows, h)
     return out
 
 
 def bert_attention(qkv, attention_mask, batch, seq_len, heads, head_dim, dropmask=None, drop_scale=1.0):
     out = torch.empty((batch * seq_len, heads * head_dim), dtype=torch.bfloat16, device=qkv.device)
-    check(lib().mclip_bert_attention(ptr(qkv), ptr(attention_mask), ptr(dropmask), C.c_float(drop_scale), ptr(out), batch, seq_len, heads, head_dim,
-                                     stream_ptr()), "mclip_bert_attention")
+    call("mclip_bert_attention", ptr(qkv), ptr(attention_mask), ptr(dropmask), C.c_float(drop_scale), ptr(out), batch, seq_len, heads, head_dim)
     return out

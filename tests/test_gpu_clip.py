@@ -1,0 +1,131 @@
+"""Whole contrastive step through the reference-shaped public API (build_model / build_loss) vs the oracle and the
+reference-generated c1 goldens (EN-B2 + 2-layer BERT, B=4, 224x224, L=32)."""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import rel_err
+
+pytestmark = pytest.mark.gpu
+
+
+class _Tok:
+    vocab_size = 28996
+
+
+def _cfgs(layers, mvs, dropout=0.0):
+    from transformers import BertConfig
+    from mammoclip_b200.model.modules.text_encoder import BERT_BASE_CASED
+    bcfg = BertConfig(**dict(BERT_BASE_CASED, num_hidden_layers=layers, hidden_dropout_prob=dropout, attention_probs_dropout_prob=dropout))
+    cfg = {"name": "clip_custom",
+           "image_encoder": {"source": "cnn", "name": "tf_efficientnetv2-detect", "pretrained": True, "model_type": "cnn"},
+           "text_encoder": {"source": "huggingface", "name": "offline", "pretrained": False, "gradient_checkpointing": False, "pooling": "eos",
+                            "cache_dir": "/tmp/none", "trust_remote_code": False, "config": bcfg},
+           "projection_head": {"name": "linear", "proj_dim": 512, "dropout": 0.1}, "temperature": 0.07}
+    key = "breast_clip" if mvs else "breast_clip_contrastive"
+    return cfg, {key: {"label_smoothing": 0.1, "i2i_weight": 1.0, "t2t_weight": 0.5, "loss_ratio": 1.0}}
+
+
+def _batch(B, h, w, L, mvs):
+    from oracle import port
+    from transformers import BatchEncoding
+    b = {"images": port.synth_images(B, h, w, seed=1234, device="cuda"), "text_tokens": BatchEncoding(port.synth_tokens(B, L, seed=4321, device="cuda"))}
+    if mvs:
+        b["image_views"] = port.synth_images(B, h, w, seed=1235, device="cuda")
+        b["text_tokens2"] = BatchEncoding(port.synth_tokens(B, L, seed=4322, device="cuda"))
+    return b
+
+
+@pytest.mark.parametrize("mvs", [False, True])
+def test_clip_step_eval_vs_oracle(mvs):
+    """eval-mode BatchNorm (running statistics): tight parity of embeddings, loss and every gradient."""
+    from mammoclip_b200.loss import build_loss
+    from mammoclip_b200.model import build_model
+    from oracle import port
+    cfg, lcfg = _cfgs(2, mvs)
+    ours = build_model(cfg, lcfg, _Tok())
+    ref = port.OracleBreastClip("efficientnet-b2", num_hidden_layers=2, hidden_dropout_prob=0.0, attention_probs_dropout_prob=0.0)
+    port.fill_deterministic(ref, 0)
+    ours.load_state_dict(ref.state_dict())
+    ours.cuda().eval(), ref.cuda().eval()
+    batch = _batch(4, 96, 64, 32, mvs)
+    out = ours(batch, "cuda")
+    loss = build_loss(lcfg)(**out, is_train=True)["total"]
+    loss.backward()
+    o_ref = ref(batch)
+    fn = port.mvs_loss if mvs else port.contrastive_loss
+    l_ref = fn(**o_ref, is_train=True, label_smoothing=0.1, i2i_weight=1.0, t2t_weight=0.5)
+    l_ref.backward()
+    for k in o_ref:
+        if k.endswith("embeddings") or k.endswith("embeddings2"):
+            assert rel_err(out[k], o_ref[k]) < 2e-2, k
+    assert abs(loss.item() - l_ref.item()) < 2e-2 * abs(l_ref.item())
+    gr = dict(ref.named_parameters())
+    gmax = max(p.grad.abs().max().item() for p in gr.values() if p.grad is not None)
+    for k, p in ours.named_parameters():
+        if gr[k].grad is None:
+            assert p.grad is None or p.grad.abs().max().item() == 0, k      # BERT pooler: unused in both
+            continue
+        assert p.grad is not None, k
+        d = (p.grad.double() - gr[k].grad.double()).abs().max().item()
+        assert d < 6e-2 * max(gr[k].grad.abs().max().item(), 2e-2 * gmax), (k, d)
+
+
+@pytest.mark.parametrize("tag,mvs", [("clip_c1_contrastive", False), ("clip_c1_mvs", True)])
+def test_clip_c1_reference_golden(golden_dir, tag, mvs):
+    """BASELINE config 1 fixture produced by the reference's own build_model/build_loss in TRAIN mode (fp32, CPU).
+    Batch-statistics BN on 4 images in bf16: checked at the level PyTorch's own bf16 autocast reaches (see
+    test_gpu_encoder._compare), plus structural facts (unused pooler, finite grads, loss within 10%)."""
+    from mammoclip_b200.loss import build_loss
+    from mammoclip_b200.model import build_model
+    from oracle import port
+    z = np.load(os.path.join(golden_dir, tag + ".npz"))
+    meta = json.loads(str(z["meta"]))
+    cfg, lcfg = _cfgs(meta["bert_layers"], mvs)
+    ours = build_model(cfg, lcfg, _Tok())
+    ref = port.OracleBreastClip("efficientnet-b2", num_hidden_layers=meta["bert_layers"], hidden_dropout_prob=0.0, attention_probs_dropout_prob=0.0)
+    port.fill_deterministic(ref, 0)
+    ours.load_state_dict(ref.state_dict())
+    ours.cuda().train()
+    ours.image_encoder.stochastic = False
+    batch = _batch(meta["batch"], meta["h"], meta["w"], meta["L"], mvs)
+    out = ours(batch, "cuda")
+    loss = build_loss(lcfg)(**out, is_train=True)["total"]
+    loss.backward()
+    # text tower has no BatchNorm: tight
+    assert rel_err(out["text_embeddings"], torch.from_numpy(z["text_embeddings"])) < 2e-2
+    # image tower: bf16 + batch statistics on 4 images
+    ref.cuda().train()
+    ref.image_encoder.stochastic = False
+    with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16):
+        e_amp = rel_err(ref._embed_img(batch["images"]).float(), torch.from_numpy(z["image_embeddings"]))
+    e_ours = rel_err(out["image_embeddings"], torch.from_numpy(z["image_embeddings"]))
+    assert e_ours < max(2e-2, 1.5 * e_amp), (e_ours, e_amp)
+    assert abs(loss.item() - float(z["loss"])) < 0.1 * abs(float(z["loss"]))
+    unused = set(z["unused"].tolist())
+    for k, p in ours.named_parameters():
+        if k in unused:
+            assert p.grad is None or p.grad.abs().max().item() == 0, k
+        else:
+            assert p.grad is not None and torch.isfinite(p.grad).all(), k
+
+
+def test_stochastic_train_step_runs_and_is_finite():
+    """drop-connect + dropout + BERT dropout on (the throughput configuration): finite loss/grads, stats updated."""
+    from mammoclip_b200.loss import build_loss
+    from mammoclip_b200.model import build_model
+    cfg, lcfg = _cfgs(2, False, dropout=0.1)
+    torch.manual_seed(0)
+    ours = build_model(cfg, lcfg, _Tok()).cuda().train()
+    batch = _batch(8, 64, 96, 32, False)
+    out = ours(batch, "cuda")
+    loss = build_loss(lcfg)(**out, is_train=True)["total"]
+    loss.backward()
+    assert torch.isfinite(loss)
+    for k, p in ours.named_parameters():
+        if "pooler" not in k:
+            assert p.grad is not None and torch.isfinite(p.grad).all(), k
+    assert ours.image_encoder._bn0.num_batches_tracked.item() == 1
