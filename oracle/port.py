@@ -444,6 +444,8 @@ def fill_deterministic(module: nn.Module, seed: int = 0) -> nn.Module:
         leaf = name.rsplit(".", 1)[-1]
         if leaf == "num_batches_tracked":
             t.zero_()
+        elif leaf == "logit_scale":
+            t.fill_(math.log(1 / 0.07))                # clip.py:39-41
         elif leaf == "running_var":
             t.copy_(torch.rand(t.shape, generator=g) * 0.8 + 0.6)
         elif leaf == "running_mean":
