@@ -13,16 +13,18 @@ class FlatAdamW:
     def __init__(self, params, lr=5e-5, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-4):
         self.params = [p for p in params if p.requires_grad]
         dev = self.params[0].device
-        n = sum(p.numel() for p in self.params)
-        self.flat = torch.empty(n, dtype=torch.float32, device=dev)
-        self.grad = torch.zeros(n, dtype=torch.float32, device=dev)
-        off = 0
+        align = 32                                   # floats: every parameter starts on a 128-byte boundary (vector loads, TMA)
+        offs, n = [], 0
         for p in self.params:
+            offs.append(n)
+            n += (p.numel() + align - 1) // align * align
+        self.flat = torch.zeros(n, dtype=torch.float32, device=dev)
+        self.grad = torch.zeros(n, dtype=torch.float32, device=dev)
+        for p, off in zip(self.params, offs):
             k = p.numel()
             self.flat[off:off + k].copy_(p.data.reshape(-1))
             p.data = self.flat[off:off + k].view(p.shape)
             p.grad = self.grad[off:off + k].view(p.shape)
-            off += k
         self.exp_avg = torch.zeros_like(self.flat)
         self.exp_avg_sq = torch.zeros_like(self.flat)
         self.lr, self.betas, self.eps, self.weight_decay = lr, betas, eps, weight_decay
