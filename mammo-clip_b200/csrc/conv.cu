@@ -15,9 +15,9 @@
 #include <algorithm>
 using std::max;
 
-#define DW_THREADS 256
-#define DW_WARPS 8
-#define DW_CCH 64          // channels per CTA tile: one warp lane = 2 channels
+#define DW_THREADS 128
+#define DW_WARPS 4
+#define DW_CCH 64          // channels per CTA tile: one warp lane = 2 channels (one packed f32x2)
 
 struct DwDev {
   int N, H, W, C, Ho, Wo;
@@ -39,38 +39,108 @@ struct DwDev {
   const float* invstd;
 };
 
+// ---- packed fp32x2 helpers (FFMA2 on sm_100: one issue slot per two FMAs) ---------------------------------------------------
+typedef unsigned long long u64;
+__device__ __forceinline__ float2 bf2_to_f2(uint32_t u) { return make_float2(__uint_as_float(u << 16), __uint_as_float(u & 0xffff0000u)); }
+__device__ __forceinline__ void ffma2(float2& d, const float2& a, const float2& b) {
+  u64& dd = reinterpret_cast<u64&>(d);
+  asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(dd) : "l"(reinterpret_cast<const u64&>(a)), "l"(reinterpret_cast<const u64&>(b)));
+}
+__device__ __forceinline__ float2 ffma2r(const float2& a, const float2& b, const float2& c) {
+  float2 d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(reinterpret_cast<u64&>(d)) : "l"(reinterpret_cast<const u64&>(a)), "l"(reinterpret_cast<const u64&>(b)),
+      "l"(reinterpret_cast<const u64&>(c)));
+  return d;
+}
+
 // ---- tile loader: global NHWC bf16 -> smem [rows][cols][64ch] bf16 with optional affine+swish, zero padded -------------
+// swish(t) = t*sigma(t) = h + h*tanh(h) with h = t/2 : the 1/2 is folded into the affine, one MUFU per element.
+// `pix` is a per-kernel table (ry << 8 | rx) of the tile's pixels so that no division runs per tile.
+__device__ __forceinline__ void dw_make_pixtab(uint16_t* pix, int rows, int cols) {
+  for (int p = threadIdx.x; p < rows * cols; p += DW_THREADS) pix[p] = (uint16_t)(((p / cols) << 8) | (p % cols));
+}
+
 template <bool kTransform>
-__device__ __forceinline__ void dw_load_tile(bf16* __restrict__ tile, const bf16* __restrict__ src, int n, int y0, int x0, int rows,
-                                             int cols, int H, int W, int C, int c0, const float* sc, const float* sh, int act) {
+__device__ __forceinline__ void dw_load_tile(bf16* __restrict__ tile, const uint16_t* __restrict__ pix, const bf16* __restrict__ img, int y0, int x0,
+                                             int npix, int H, int W, int C, int c0, const float* sc, const float* sh, int act) {
+  // img: base of image n.  Offsets inside one image fit in 32 bits.
   const int v = threadIdx.x & 7;                 // 8-channel vector inside the 64-channel chunk (fixed per thread)
   const int c = c0 + v * 8;
   const bool cvalid = c < C;
-  float a[8], b[8];
+  float2 a[4], b[4];
   if (kTransform && cvalid) {
+    const float f = act ? 0.5f : 1.0f;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) { a[i] = sc[c + i]; b[i] = sh[c + i]; }
+    for (int i = 0; i < 4; ++i) {
+      a[i] = make_float2(f * sc[c + 2 * i], f * sc[c + 2 * i + 1]);
+      b[i] = make_float2(f * sh[c + 2 * i], f * sh[c + 2 * i + 1]);
+    }
   }
-  const int npix = rows * cols;
-  for (int p = threadIdx.x >> 3; p < npix; p += DW_THREADS / 8) {
-    const int ry = p / cols, rx = p - ry * cols;
-    const int y = y0 + ry, x = x0 + rx;
-    bf16x8 val;
-    val.w[0] = val.w[1] = val.w[2] = val.w[3] = 0u;
-    if (cvalid && y >= 0 && y < H && x >= 0 && x < W) {
-      val = ldg_bf16x8(src + (((size_t)n * H + y) * W + x) * C + c);
-      if (kTransform) {
-        float f[8];
-        unpack8(val, f);
+  constexpr int PSTEP = DW_THREADS / 8, UNR = 4;
+  const bf16* src = img + c;
+  bf16* dst = tile + v * 8;
+  for (int p0 = threadIdx.x >> 3; p0 < npix; p0 += PSTEP * UNR) {
+    bf16x8 val[UNR];
+    bool inb[UNR];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          float t = fmaf(f[i], a[i], b[i]);
-          f[i] = act ? swish_f(t) : t;
-        }
-        val = pack8(f);
+    for (int u = 0; u < UNR; ++u) {
+      const int p = p0 + u * PSTEP;
+      val[u].w[0] = val[u].w[1] = val[u].w[2] = val[u].w[3] = 0u;
+      inb[u] = false;
+      if (p < npix) {
+        const uint32_t pr = pix[p];
+        const int y = y0 + (int)(pr >> 8), x = x0 + (int)(pr & 255u);
+        inb[u] = cvalid && (unsigned)y < (unsigned)H && (unsigned)x < (unsigned)W;
+        if (inb[u]) val[u] = ldg_bf16x8(src + (unsigned)((y * W + x) * C));
       }
     }
-    *reinterpret_cast<bf16x8*>(tile + ((size_t)p * DW_CCH + v * 8)) = val;
+#pragma unroll
+    for (int u = 0; u < UNR; ++u) {
+      const int p = p0 + u * PSTEP;
+      if (p >= npix) break;
+      bf16x8 o = val[u];
+      if (kTransform && inb[u]) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          float2 h = ffma2r(bf2_to_f2(o.w[i]), a[i], b[i]);
+          if (act) {
+            const float2 th = make_float2(fast_tanh(h.x), fast_tanh(h.y));
+            h = ffma2r(h, th, h);
+          }
+          o.w[i] = pack_bf16(h.x, h.y);
+        }
+      }
+      *reinterpret_cast<bf16x8*>(dst + p * DW_CCH) = o;
+    }
+  }
+}
+
+// One warp computes a PRO x 4 patch of outputs for its 64 channels from a staged tile (row stride IW pixels):
+// acc[oy][ox] += sum_{ky,kx} tile[(py+oy)*S+ky][(px+ox)*S+kx] * w[ky*K+kx]
+template <int K, int S, int PRO>
+__device__ __forceinline__ void dw_patch(const bf16* __restrict__ tile, int IW, int ty, int tx, int lane, const float2* __restrict__ w,
+                                         float2 (&acc)[PRO][4]) {
+  constexpr int PR = (PRO - 1) * S + K, PC = 3 * S + K;
+#pragma unroll
+  for (int i = 0; i < PRO; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = make_float2(0.f, 0.f);
+  const uint32_t* base = reinterpret_cast<const uint32_t*>(tile) + (ty * IW + tx) * (DW_CCH / 2) + lane;
+#pragma unroll
+  for (int iy = 0; iy < PR; ++iy) {
+    float2 r[PC];
+    const uint32_t* rowp = base + iy * IW * (DW_CCH / 2);
+#pragma unroll
+    for (int ix = 0; ix < PC; ++ix) r[ix] = bf2_to_f2(rowp[ix * (DW_CCH / 2)]);
+#pragma unroll
+    for (int oy = 0; oy < PRO; ++oy) {
+      const int ky = iy - oy * S;
+      if (ky < 0 || ky >= K) continue;
+#pragma unroll
+      for (int kx = 0; kx < K; ++kx)
+#pragma unroll
+        for (int ox = 0; ox < 4; ++ox) ffma2(acc[oy][ox], r[ox * S + kx], w[ky * K + kx]);
+    }
   }
 }
 
@@ -78,84 +148,77 @@ __device__ __forceinline__ void dw_load_tile(bf16* __restrict__ tile, const bf16
 // forward
 // =====================================================================================================
 template <int K, int S, int TH, int TW>
-__global__ void __launch_bounds__(DW_THREADS) mclip_dwconv_fwd_kernel(const DwDev p) {
+__global__ void __launch_bounds__(DW_THREADS, 4) mclip_dwconv_fwd_kernel(const DwDev p) {
   constexpr int IH = (TH - 1) * S + K, IW = (TW - 1) * S + K;
-  constexpr int PR = (2 - 1) * S + K, PC = (4 - 1) * S + K;     // input window of a 2x4 output patch
+  constexpr int PRO = (S == 1 && K == 3) ? 4 : 2;                 // output rows per warp patch
   extern __shared__ __align__(16) uint8_t smem_dw[];
   bf16* tile = reinterpret_cast<bf16*>(smem_dw);
+  uint16_t* pix = reinterpret_cast<uint16_t*>(tile + (size_t)IH * IW * DW_CCH);
   __shared__ float red[DW_WARPS][4][32];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int chunk = blockIdx.x % p.n_chunks, slot = blockIdx.x / p.n_chunks;
   const int c0 = chunk * DW_CCH, c = c0 + lane * 2;
   const bool cvalid = c < p.C;
-  float w0[K * K], w1[K * K];
+  dw_make_pixtab(pix, IH, IW);
+  float2 w[K * K];
 #pragma unroll
-  for (int t = 0; t < K * K; ++t) {
-    w0[t] = cvalid ? p.w[(size_t)c * K * K + t] : 0.f;
-    w1[t] = cvalid ? p.w[(size_t)(c + 1) * K * K + t] : 0.f;
-  }
-  float s_sum0 = 0.f, s_sum1 = 0.f, s_sq0 = 0.f, s_sq1 = 0.f;
+  for (int t = 0; t < K * K; ++t) w[t] = cvalid ? make_float2(p.w[(size_t)c * K * K + t], p.w[(size_t)(c + 1) * K * K + t]) : make_float2(0.f, 0.f);
+  float2 s_sum = make_float2(0.f, 0.f), s_sq = make_float2(0.f, 0.f);
+  const float2 one = make_float2(1.f, 1.f);
   const int tiles_per_img = p.tiles_x * p.tiles_y;
   const int total_tiles = p.N * tiles_per_img;
+  const int cw = p.C >> 1;                                         // channel pairs per pixel (row stride in 32-bit words)
   for (int t = slot; t < total_tiles; t += p.slots) {
     const int n = t / tiles_per_img, tr = t % tiles_per_img;
     const int oy0 = (tr / p.tiles_x) * TH, ox0 = (tr % p.tiles_x) * TW;
+    const bf16* img = p.in + (size_t)n * p.H * p.W * p.C;
+    uint32_t* outw = reinterpret_cast<uint32_t*>(p.out + (size_t)n * p.Ho * p.Wo * p.C) + (c >> 1);
     __syncthreads();
-    if (p.scale) dw_load_tile<true>(tile, p.in, n, oy0 * S - p.pt, ox0 * S - p.pl, IH, IW, p.H, p.W, p.C, c0, p.scale, p.shift, p.act);
-    else dw_load_tile<false>(tile, p.in, n, oy0 * S - p.pt, ox0 * S - p.pl, IH, IW, p.H, p.W, p.C, c0, nullptr, nullptr, 0);
+    if (p.scale) dw_load_tile<true>(tile, pix, img, oy0 * S - p.pt, ox0 * S - p.pl, IH * IW, p.H, p.W, p.C, c0, p.scale, p.shift, p.act);
+    else dw_load_tile<false>(tile, pix, img, oy0 * S - p.pt, ox0 * S - p.pl, IH * IW, p.H, p.W, p.C, c0, nullptr, nullptr, 0);
     __syncthreads();
-    for (int pa = warp; pa < (TH / 2) * (TW / 4); pa += DW_WARPS) {
-      const int py = (pa / (TW / 4)) * 2, px = (pa % (TW / 4)) * 4;
-      if (oy0 + py >= p.Ho || ox0 + px >= p.Wo) continue;        // warp-uniform
-      float acc[2][4][2];
+    for (int pa = warp; pa < (TH / PRO) * (TW / 4); pa += DW_WARPS) {
+      const int py = (pa / (TW / 4)) * PRO, px = (pa % (TW / 4)) * 4;
+      const int y0 = oy0 + py, x0 = ox0 + px;
+      if (y0 >= p.Ho || x0 >= p.Wo) continue;                      // warp-uniform
+      float2 acc[PRO][4];
+      dw_patch<K, S, PRO>(tile, IW, py * S, px * S, lane, w, acc);
+      if (!cvalid) continue;
+      uint32_t* op = outw + (y0 * p.Wo + x0) * cw;
+      if (y0 + PRO <= p.Ho && x0 + 4 <= p.Wo) {                    // interior patch: no per-pixel checks
 #pragma unroll
-      for (int i = 0; i < 2; ++i)
+        for (int oy = 0; oy < PRO; ++oy)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.f;
-#pragma unroll
-      for (int iy = 0; iy < PR; ++iy) {
-        float r0[PC], r1[PC];
-        const uint32_t* rowp = reinterpret_cast<const uint32_t*>(tile + ((size_t)((py * S + iy) * IW + px * S) * DW_CCH)) + lane;
-#pragma unroll
-        for (int ix = 0; ix < PC; ++ix) {
-          uint32_t u = rowp[ix * (DW_CCH / 2)];
-          r0[ix] = bf16_lo(u);
-          r1[ix] = bf16_hi(u);
-        }
-#pragma unroll
-        for (int oy = 0; oy < 2; ++oy) {
-          const int ky = iy - oy * S;
-          if (ky < 0 || ky >= K) continue;
-#pragma unroll
-          for (int kx = 0; kx < K; ++kx)
-#pragma unroll
-            for (int ox = 0; ox < 4; ++ox) {
-              acc[oy][ox][0] = fmaf(r0[ox * S + kx], w0[ky * K + kx], acc[oy][ox][0]);
-              acc[oy][ox][1] = fmaf(r1[ox * S + kx], w1[ky * K + kx], acc[oy][ox][1]);
-            }
-        }
-      }
-#pragma unroll
-      for (int oy = 0; oy < 2; ++oy)
-#pragma unroll
-        for (int ox = 0; ox < 4; ++ox) {
-          const int y = oy0 + py + oy, x = ox0 + px + ox;
-          if (y < p.Ho && x < p.Wo && cvalid) {
-            uint32_t pk = pack_bf16(acc[oy][ox][0], acc[oy][ox][1]);
-            *reinterpret_cast<uint32_t*>(p.out + (((size_t)n * p.Ho + y) * p.Wo + x) * p.C + c) = pk;
-            float a0 = bf16_lo(pk), a1 = bf16_hi(pk);
-            s_sum0 += a0; s_sum1 += a1; s_sq0 = fmaf(a0, a0, s_sq0); s_sq1 = fmaf(a1, a1, s_sq1);
+          for (int ox = 0; ox < 4; ++ox) {
+            const uint32_t pk = pack_bf16(acc[oy][ox].x, acc[oy][ox].y);
+            op[(oy * p.Wo + ox) * cw] = pk;
+            const float2 a = bf2_to_f2(pk);
+            ffma2(s_sum, a, one);
+            ffma2(s_sq, a, a);
           }
-        }
+      } else {
+#pragma unroll
+        for (int oy = 0; oy < PRO; ++oy)
+#pragma unroll
+          for (int ox = 0; ox < 4; ++ox) {
+            if (y0 + oy < p.Ho && x0 + ox < p.Wo) {
+              const uint32_t pk = pack_bf16(acc[oy][ox].x, acc[oy][ox].y);
+              op[(oy * p.Wo + ox) * cw] = pk;
+              const float2 a = bf2_to_f2(pk);
+              ffma2(s_sum, a, one);
+              ffma2(s_sq, a, a);
+            }
+          }
+      }
     }
   }
   if (p.stats) {
-    red[warp][0][lane] = s_sum0; red[warp][1][lane] = s_sum1; red[warp][2][lane] = s_sq0; red[warp][3][lane] = s_sq1;
+    red[warp][0][lane] = s_sum.x; red[warp][1][lane] = s_sum.y; red[warp][2][lane] = s_sq.x; red[warp][3][lane] = s_sq.y;
     __syncthreads();
     if (warp == 0 && cvalid) {
       float a = 0.f, b = 0.f, cc = 0.f, d = 0.f;
 #pragma unroll
-      for (int w = 0; w < DW_WARPS; ++w) { a += red[w][0][lane]; b += red[w][1][lane]; cc += red[w][2][lane]; d += red[w][3][lane]; }
+      for (int w2 = 0; w2 < DW_WARPS; ++w2) { a += red[w2][0][lane]; b += red[w2][1][lane]; cc += red[w2][2][lane]; d += red[w2][3][lane]; }
       float* st = p.stats + (size_t)slot * 2 * p.C;
       st[c] = a; st[c + 1] = b; st[p.C + c] = cc; st[p.C + c + 1] = d;
     }
@@ -163,72 +226,106 @@ __global__ void __launch_bounds__(DW_THREADS) mclip_dwconv_fwd_kernel(const DwDe
 }
 
 // =====================================================================================================
-// backward: data gradient (+ swish' of the input activation, + input-BN reduction terms) and weight gradient
+// backward: weight gradient, data gradient (+ swish' of the input activation), input-BN reduction terms
 // =====================================================================================================
-// Tile = TH x TW OUTPUT pixels and the S*TH x S*TW INPUT pixels they own.
+// Tile = TH x TW OUTPUT pixels and the S*TH x S*TW INPUT pixels they own.  Two staged windows:
+//   atile : activated input window feeding the owned outputs          (weight gradient)
+//   gtile : dY window feeding the owned inputs; it contains the owned outputs' dY as a sub-window
+// Per 2x4 patch a warp accumulates dW (registers, for the whole kernel) and computes the data gradient as a
+// register-window correlation of gtile with the flipped kernel (stride 1) or per parity class (stride 2).
 template <int K, int S, int TH, int TW>
-__global__ void __launch_bounds__(DW_THREADS) mclip_dwconv_bwd_kernel(const DwDev p) {
-  constexpr int IH = (TH - 1) * S + K, IW = (TW - 1) * S + K;     // activation window feeding the owned outputs (wgrad)
-  constexpr int GH = (S == 1) ? TH + K - 1 : TH + (K + 1) / 2;    // dY window feeding the owned inputs (dgrad)
+__global__ void __launch_bounds__(DW_THREADS, (K == 3) ? 4 : 3) mclip_dwconv_bwd_kernel(const DwDev p) {
+  constexpr int IH = (TH - 1) * S + K, IW = (TW - 1) * S + K;     // activation window (wgrad)
+  constexpr int GH = (S == 1) ? TH + K - 1 : TH + (K + 1) / 2;    // dY window (dgrad)
   constexpr int GW = (S == 1) ? TW + K - 1 : TW + (K + 1) / 2;
   extern __shared__ __align__(16) uint8_t smem_dw[];
-  bf16* atile = reinterpret_cast<bf16*>(smem_dw);                 // [IH][IW][64] activated input
-  bf16* gtile = atile + (size_t)IH * IW * DW_CCH;                 // [GH][GW][64] dY
-  float* wsm = reinterpret_cast<float*>(gtile + (size_t)GH * GW * DW_CCH);   // [K*K][64] weights
+  bf16* atile = reinterpret_cast<bf16*>(smem_dw);                                  // [IH*IW][64]
+  bf16* gtile = atile + (size_t)IH * IW * DW_CCH;                                  // [GH*GW][64]
+  float* wsm = reinterpret_cast<float*>(gtile + (size_t)GH * GW * DW_CCH);         // [K*K][64] weights
+  uint16_t* apix = reinterpret_cast<uint16_t*>(wsm + K * K * DW_CCH);
+  uint16_t* gpix = apix + IH * IW;
   __shared__ float red[DW_WARPS][4][32];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int chunk = blockIdx.x % p.n_chunks, slot = blockIdx.x / p.n_chunks;
   const int c0 = chunk * DW_CCH, c = c0 + lane * 2;
   const bool cvalid = c < p.C;
   for (int i = threadIdx.x; i < K * K * DW_CCH; i += DW_THREADS) {
-    int t = i / DW_CCH, ch = i % DW_CCH;
+    const int t = i / DW_CCH, ch = i % DW_CCH;
     wsm[i] = (c0 + ch < p.C) ? p.w[(size_t)(c0 + ch) * K * K + t] : 0.f;
   }
-  float dw0[K * K], dw1[K * K];
+  dw_make_pixtab(apix, IH, IW);
+  dw_make_pixtab(gpix, GH, GW);
+  float2 ab = make_float2(1.f, 1.f), bb = make_float2(0.f, 0.f), mu = make_float2(0.f, 0.f), is = make_float2(1.f, 1.f);
+  if (p.scale && cvalid) { ab = make_float2(p.scale[c], p.scale[c + 1]); bb = make_float2(p.shift[c], p.shift[c + 1]); }
+  if (p.bn_part && cvalid) { mu = make_float2(p.mean[c], p.mean[c + 1]); is = make_float2(p.invstd[c], p.invstd[c + 1]); }
+  float2 bs = make_float2(0.f, 0.f), bq = make_float2(0.f, 0.f);
+  float2 dw[K * K];
 #pragma unroll
-  for (int t = 0; t < K * K; ++t) dw0[t] = dw1[t] = 0.f;
-  float a0 = 1.f, b0 = 0.f, a1 = 1.f, b1 = 0.f, m0 = 0.f, m1 = 0.f, is0 = 1.f, is1 = 1.f;
-  if (p.scale && cvalid) { a0 = p.scale[c]; a1 = p.scale[c + 1]; b0 = p.shift[c]; b1 = p.shift[c + 1]; }
-  if (p.bn_part && cvalid) { m0 = p.mean[c]; m1 = p.mean[c + 1]; is0 = p.invstd[c]; is1 = p.invstd[c + 1]; }
-  float bs0 = 0.f, bs1 = 0.f, bq0 = 0.f, bq1 = 0.f;
-  // first dY row/col needed by the owned inputs:  oy >= ceil((y + pt - (K-1)) / S)
+  for (int q = 0; q < K * K; ++q) dw[q] = make_float2(0.f, 0.f);
+  __syncthreads();
+  float2 wf[(S == 1) ? K * K : 1];                                 // flipped kernel (stride-1 data gradient)
+  if constexpr (S == 1) {
+#pragma unroll
+    for (int q = 0; q < K * K; ++q) wf[q] = *reinterpret_cast<const float2*>(wsm + (K * K - 1 - q) * DW_CCH + lane * 2);
+  }
+  const int cw = p.C >> 1;
   const int tiles_per_img = p.tiles_x * p.tiles_y;
   const int total_tiles = p.N * tiles_per_img;
   for (int t = slot; t < total_tiles; t += p.slots) {
     const int n = t / tiles_per_img, tr = t % tiles_per_img;
     const int oy0 = (tr / p.tiles_x) * TH, ox0 = (tr % p.tiles_x) * TW;
     const int iy0 = oy0 * S, ix0 = ox0 * S;                        // first owned input pixel
-    // floor division for possibly negative numerators
     const int gnum_y = iy0 + p.pt - (K - 1), gnum_x = ix0 + p.pl - (K - 1);
-    const int gy0 = (S == 1) ? gnum_y : (gnum_y >= 0 ? (gnum_y + 1) / 2 : -((-gnum_y) / 2));
+    const int gy0 = (S == 1) ? gnum_y : (gnum_y >= 0 ? (gnum_y + 1) / 2 : -((-gnum_y) / 2));   // ceil(gnum / S)
     const int gx0 = (S == 1) ? gnum_x : (gnum_x >= 0 ? (gnum_x + 1) / 2 : -((-gnum_x) / 2));
+    const bf16* img = p.in + (size_t)n * p.H * p.W * p.C;
+    const uint32_t* inw = reinterpret_cast<const uint32_t*>(img) + (c >> 1);
+    uint32_t* dxw = reinterpret_cast<uint32_t*>(p.dx + (size_t)n * p.H * p.W * p.C) + (c >> 1);
     __syncthreads();
-    if (p.scale) dw_load_tile<true>(atile, p.in, n, iy0 - p.pt, ix0 - p.pl, IH, IW, p.H, p.W, p.C, c0, p.scale, p.shift, p.act);
-    else dw_load_tile<false>(atile, p.in, n, iy0 - p.pt, ix0 - p.pl, IH, IW, p.H, p.W, p.C, c0, nullptr, nullptr, 0);
-    dw_load_tile<false>(gtile, p.dy, n, gy0, gx0, GH, GW, p.Ho, p.Wo, p.C, c0, nullptr, nullptr, 0);
+    if (p.scale) dw_load_tile<true>(atile, apix, img, iy0 - p.pt, ix0 - p.pl, IH * IW, p.H, p.W, p.C, c0, p.scale, p.shift, p.act);
+    else dw_load_tile<false>(atile, apix, img, iy0 - p.pt, ix0 - p.pl, IH * IW, p.H, p.W, p.C, c0, nullptr, nullptr, 0);
+    dw_load_tile<false>(gtile, gpix, p.dy + (size_t)n * p.Ho * p.Wo * p.C, gy0, gx0, GH * GW, p.Ho, p.Wo, p.C, c0, nullptr, nullptr, 0);
     __syncthreads();
+
+    // dv = dA*swish'(a*y+b) (y = pre-BN input), BN-backward partials, store
+    auto finish = [&](uint32_t yu, int off, float2 d) {
+      if (p.scale) {
+        const float2 yv = bf2_to_f2(yu);
+        if (p.act) {
+          const float2 tv = ffma2r(yv, ab, bb);
+          d.x *= swish_grad_f(tv.x); d.y *= swish_grad_f(tv.y);
+        }
+        const uint32_t pk = pack_bf16(d.x, d.y);
+        dxw[off] = pk;
+        d = bf2_to_f2(pk);
+        bs.x += d.x; bs.y += d.y;
+        const float2 yh = make_float2((yv.x - mu.x) * is.x, (yv.y - mu.y) * is.y);
+        ffma2(bq, d, yh);
+      } else {
+        dxw[off] = pack_bf16(d.x, d.y);
+      }
+    };
 
     // ---- weight gradient over the owned outputs: dW[ky,kx] += dY[oy,ox] * A[oy*S+ky, ox*S+kx] ----
     for (int pa = warp; pa < (TH / 2) * (TW / 4); pa += DW_WARPS) {
       const int py = (pa / (TW / 4)) * 2, px = (pa % (TW / 4)) * 4;
       if (oy0 + py >= p.Ho || ox0 + px >= p.Wo) continue;
-      constexpr int PR = (2 - 1) * S + K, PC = (4 - 1) * S + K;
-      float g0[2][4], g1[2][4];
+      constexpr int PR = S + K, PC = 3 * S + K;
+      float2 g[2][4];
+      {
+        // owned outputs sit in gtile at (oy - gy0, ox - gx0); outputs past Ho/Wo were zero-filled by the loader
+        const uint32_t* gp = reinterpret_cast<const uint32_t*>(gtile) + ((oy0 + py - gy0) * GW + (ox0 + px - gx0)) * (DW_CCH / 2) + lane;
 #pragma unroll
-      for (int oy = 0; oy < 2; ++oy)
+        for (int oy = 0; oy < 2; ++oy)
 #pragma unroll
-        for (int ox = 0; ox < 4; ++ox) {
-          // dY of the owned outputs sits in gtile at (oy - gy0, ox - gx0); outputs past Ho/Wo were zero-filled
-          const int gy = oy0 + py + oy - gy0, gx = ox0 + px + ox - gx0;
-          uint32_t u = reinterpret_cast<const uint32_t*>(gtile + ((size_t)(gy * GW + gx) * DW_CCH))[lane];
-          g0[oy][ox] = bf16_lo(u); g1[oy][ox] = bf16_hi(u);
-        }
+          for (int ox = 0; ox < 4; ++ox) g[oy][ox] = bf2_to_f2(gp[(oy * GW + ox) * (DW_CCH / 2)]);
+      }
+      const uint32_t* abase = reinterpret_cast<const uint32_t*>(atile) + (py * S * IW + px * S) * (DW_CCH / 2) + lane;
 #pragma unroll
       for (int iy = 0; iy < PR; ++iy) {
-        float r0[PC], r1[PC];
-        const uint32_t* rowp = reinterpret_cast<const uint32_t*>(atile + ((size_t)((py * S + iy) * IW + px * S) * DW_CCH)) + lane;
+        float2 r[PC];
 #pragma unroll
-        for (int ix = 0; ix < PC; ++ix) { uint32_t u = rowp[ix * (DW_CCH / 2)]; r0[ix] = bf16_lo(u); r1[ix] = bf16_hi(u); }
+        for (int ix = 0; ix < PC; ++ix) r[ix] = bf2_to_f2(abase[(iy * IW + ix) * (DW_CCH / 2)]);
 #pragma unroll
         for (int oy = 0; oy < 2; ++oy) {
           const int ky = iy - oy * S;
@@ -236,88 +333,100 @@ __global__ void __launch_bounds__(DW_THREADS) mclip_dwconv_bwd_kernel(const DwDe
 #pragma unroll
           for (int kx = 0; kx < K; ++kx)
 #pragma unroll
-            for (int ox = 0; ox < 4; ++ox) {
-              dw0[ky * K + kx] = fmaf(g0[oy][ox], r0[ox * S + kx], dw0[ky * K + kx]);
-              dw1[ky * K + kx] = fmaf(g1[oy][ox], r1[ox * S + kx], dw1[ky * K + kx]);
-            }
+            for (int ox = 0; ox < 4; ++ox) ffma2(dw[ky * K + kx], g[oy][ox], r[ox * S + kx]);
         }
       }
     }
 
-    // ---- data gradient over the owned inputs: dA[y,x] = sum_{ky,kx : (y+pt-ky)%S==0} dY[(y+pt-ky)/S, (x+pl-kx)/S] * w[ky,kx] ----
-    constexpr int OWN_H = TH * S, OWN_W = TW * S;
-    for (int pa = warp; pa < OWN_H * (OWN_W / 4); pa += DW_WARPS) {
-      const int ly = pa / (OWN_W / 4), lx = (pa % (OWN_W / 4)) * 4;
-      const int y = iy0 + ly;
-      if (y >= p.H || ix0 + lx >= p.W) continue;
-      float d0[4] = {0.f, 0.f, 0.f, 0.f}, d1[4] = {0.f, 0.f, 0.f, 0.f};
+    // ---- data gradient over the owned inputs ----
+    if constexpr (S == 1) {
+      for (int pa = warp; pa < (TH / 2) * (TW / 4); pa += DW_WARPS) {
+        const int ly = (pa / (TW / 4)) * 2, lx = (pa % (TW / 4)) * 4;
+        const int y0 = iy0 + ly, x0 = ix0 + lx;
+        if (y0 >= p.H || x0 >= p.W || !cvalid) continue;
+        const int off0 = (y0 * p.W + x0) * cw;
+        uint32_t yu[2][4];
 #pragma unroll
-      for (int ky = 0; ky < K; ++ky) {
-        const int ny = y + p.pt - ky;
-        if (S == 2 && (ny & 1)) continue;                          // warp-uniform
-        const int gy = (S == 1 ? ny : ny >> 1) - gy0;              // ny >= gnum_y*... inside the window by construction
-        if (gy < 0 || gy >= GH) continue;
+        for (int oy = 0; oy < 2; ++oy)
 #pragma unroll
-        for (int kx = 0; kx < K; ++kx) {
-          const float2 wv = *reinterpret_cast<const float2*>(wsm + (ky * K + kx) * DW_CCH + lane * 2);
+          for (int ox = 0; ox < 4; ++ox)
+            yu[oy][ox] = (p.scale && y0 + oy < p.H && x0 + ox < p.W) ? __ldg(inw + off0 + (oy * p.W + ox) * cw) : 0u;
+        float2 acc[2][4];
+        dw_patch<K, 1, 2>(gtile, GW, ly, lx, lane, wf, acc);
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const int nx = ix0 + lx + j + p.pl - kx;
-            if (S == 2 && (nx & 1)) continue;
-            const int gx = (S == 1 ? nx : nx >> 1) - gx0;
-            if (gx < 0 || gx >= GW) continue;
-            uint32_t u = reinterpret_cast<const uint32_t*>(gtile + ((size_t)(gy * GW + gx) * DW_CCH))[lane];
-            d0[j] = fmaf(bf16_lo(u), wv.x, d0[j]);
-            d1[j] = fmaf(bf16_hi(u), wv.y, d1[j]);
-          }
-        }
+        for (int oy = 0; oy < 2; ++oy)
+#pragma unroll
+          for (int ox = 0; ox < 4; ++ox)
+            if (y0 + oy < p.H && x0 + ox < p.W) finish(yu[oy][ox], off0 + (oy * p.W + ox) * cw, acc[oy][ox]);
       }
+    } else {
+      // stride 2: input pixel (y,x) receives taps ky = cy + 2m, kx = cx + 2n with cy = (y+pt)&1, cx = (x+pl)&1.
+      // work item = one input row, one x parity, 4 same-parity pixels (consecutive dY columns).
+      constexpr int NT = (K + 1) / 2;                                // taps per axis per parity class (max)
+      constexpr int OWN_H = TH * 2, OWN_W = TW * 2;
+      for (int it = warp; it < OWN_H * 2 * (OWN_W / 8); it += DW_WARPS) {
+        const int ly = it / (2 * (OWN_W / 8)), rem = it % (2 * (OWN_W / 8));
+        const int par = rem / (OWN_W / 8), strip = rem % (OWN_W / 8);
+        const int y = iy0 + ly, xb = ix0 + strip * 8 + par;          // pixels xb, xb+2, xb+4, xb+6
+        if (y >= p.H || xb >= p.W || !cvalid) continue;
+        const int off0 = (y * p.W + xb) * cw;
+        uint32_t yu[4];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const int x = ix0 + lx + j;
-        if (x < p.W && cvalid) {
-          const size_t off = (((size_t)n * p.H + y) * p.W + x) * p.C + c;
-          float v0 = d0[j], v1 = d1[j];
-          if (p.scale) {
-            // dv = dA * swish'(a*y+b); yhat = (y-mean)*invstd
-            uint32_t yu = *reinterpret_cast<const uint32_t*>(p.in + off);
-            float y0 = bf16_lo(yu), y1 = bf16_hi(yu);
-            if (p.act) { v0 *= swish_grad_f(fmaf(y0, a0, b0)); v1 *= swish_grad_f(fmaf(y1, a1, b1)); }
-            uint32_t pk = pack_bf16(v0, v1);
-            *reinterpret_cast<uint32_t*>(p.dx + off) = pk;
-            v0 = bf16_lo(pk); v1 = bf16_hi(pk);
-            bs0 += v0; bs1 += v1;
-            bq0 = fmaf(v0, (y0 - m0) * is0, bq0); bq1 = fmaf(v1, (y1 - m1) * is1, bq1);
-          } else {
-            *reinterpret_cast<uint32_t*>(p.dx + off) = pack_bf16(v0, v1);
+        for (int j = 0; j < 4; ++j) yu[j] = (p.scale && xb + 2 * j < p.W) ? __ldg(inw + off0 + 2 * j * cw) : 0u;
+        const int cy = (y + p.pt) & 1, cx = (xb + p.pl) & 1;
+        const int obx = ((xb + p.pl - cx) >> 1) - gx0;               // dY column (tile coords) of pixel j=0 for n=0
+        float2 acc[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[j] = make_float2(0.f, 0.f);
+#pragma unroll
+        for (int m = 0; m < NT; ++m) {
+          const int ky = cy + 2 * m;
+          if (ky >= K) continue;
+          const int gy = ((y + p.pt - ky) >> 1) - gy0;               // numerator is even by construction
+          if (gy < 0 || gy >= GH) continue;
+          float2 r[NT + 3];
+#pragma unroll
+          for (int q = 0; q < NT + 3; ++q) {
+            const int gx = obx - (NT - 1) + q;
+            uint32_t u = 0u;
+            if (gx >= 0 && gx < GW) u = reinterpret_cast<const uint32_t*>(gtile)[(gy * GW + gx) * (DW_CCH / 2) + lane];
+            r[q] = bf2_to_f2(u);
+          }
+#pragma unroll
+          for (int nn = 0; nn < NT; ++nn) {
+            const int kx = cx + 2 * nn;
+            if (kx >= K) continue;
+            const float2 wv = *reinterpret_cast<const float2*>(wsm + (ky * K + kx) * DW_CCH + lane * 2);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) ffma2(acc[j], r[j - nn + NT - 1], wv);
           }
         }
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          if (xb + 2 * j < p.W) finish(yu[j], off0 + 2 * j * cw, acc[j]);
       }
     }
   }
   // ---- flush partials ----
   __syncthreads();
-  float* wred = reinterpret_cast<float*>(atile);                   // reuse: [warps][K*K][64]
+  float* wred = reinterpret_cast<float*>(smem_dw);                 // reuse the tiles: [warps][K*K][64]
 #pragma unroll
-  for (int t = 0; t < K * K; ++t) {
-    wred[((size_t)warp * K * K + t) * DW_CCH + lane * 2] = dw0[t];
-    wred[((size_t)warp * K * K + t) * DW_CCH + lane * 2 + 1] = dw1[t];
-  }
-  red[warp][0][lane] = bs0; red[warp][1][lane] = bs1; red[warp][2][lane] = bq0; red[warp][3][lane] = bq1;
+  for (int q = 0; q < K * K; ++q) *reinterpret_cast<float2*>(wred + ((size_t)warp * K * K + q) * DW_CCH + lane * 2) = dw[q];
+  red[warp][0][lane] = bs.x; red[warp][1][lane] = bs.y; red[warp][2][lane] = bq.x; red[warp][3][lane] = bq.y;
   __syncthreads();
   for (int i = threadIdx.x; i < K * K * DW_CCH; i += DW_THREADS) {
     const int t = i / DW_CCH, ch = i % DW_CCH;
     if (c0 + ch < p.C) {
-      float s = 0.f;
+      float s2 = 0.f;
 #pragma unroll
-      for (int w = 0; w < DW_WARPS; ++w) s += wred[((size_t)w * K * K + t) * DW_CCH + ch];
-      p.dw_part[((size_t)slot * K * K + t) * p.C + c0 + ch] = s;
+      for (int w2 = 0; w2 < DW_WARPS; ++w2) s2 += wred[((size_t)w2 * K * K + t) * DW_CCH + ch];
+      p.dw_part[((size_t)slot * K * K + t) * p.C + c0 + ch] = s2;
     }
   }
   if (p.bn_part && warp == 0 && cvalid) {
     float a = 0.f, b = 0.f, cc = 0.f, d = 0.f;
 #pragma unroll
-    for (int w = 0; w < DW_WARPS; ++w) { a += red[w][0][lane]; b += red[w][1][lane]; cc += red[w][2][lane]; d += red[w][3][lane]; }
+    for (int w2 = 0; w2 < DW_WARPS; ++w2) { a += red[w2][0][lane]; b += red[w2][1][lane]; cc += red[w2][2][lane]; d += red[w2][3][lane]; }
     float* st = p.bn_part + (size_t)slot * 2 * p.C;
     st[c] = a; st[c + 1] = b; st[p.C + c] = cc; st[p.C + c + 1] = d;
   }
@@ -339,8 +448,9 @@ __global__ void mclip_dw_wgrad_reduce_kernel(const float* __restrict__ part, flo
 // ------------------------------------------------------------------------------------------------
 template <int K, int S>
 struct DwCfg {
-  static constexpr int TH = (S == 1) ? 16 : 8;
+  static constexpr int TH = (S == 1) ? 16 : 8;      // forward tile (outputs)
   static constexpr int TW = 16;
+  static constexpr int BTH = (S == 1) ? 8 : 4;   // backward tile height
 };
 
 static int dw_slots(int n_chunks, int total_tiles, int per_sm) {
@@ -354,7 +464,7 @@ template <int K, int S>
 static int dw_launch_fwd(DwDev& p, cudaStream_t stream, int slots_given) {
   constexpr int TH = DwCfg<K, S>::TH, TW = DwCfg<K, S>::TW;
   constexpr int IH = (TH - 1) * S + K, IW = (TW - 1) * S + K;
-  const int smem = IH * IW * DW_CCH * 2;
+  const int smem = IH * IW * DW_CCH * 2 + IH * IW * 2 + 16;
   p.tiles_x = ceil_div(p.Wo, TW); p.tiles_y = ceil_div(p.Ho, TH);
   p.n_chunks = ceil_div(p.C, DW_CCH);
   p.slots = slots_given;
@@ -368,11 +478,11 @@ static int dw_launch_fwd(DwDev& p, cudaStream_t stream, int slots_given) {
 
 template <int K, int S>
 static int dw_launch_bwd(DwDev& p, cudaStream_t stream, int slots_given) {
-  constexpr int TH = DwCfg<K, S>::TH / 2 * 1, TW = DwCfg<K, S>::TW;   // half-height tiles: two staged tensors
+  constexpr int TH = DwCfg<K, S>::BTH, TW = DwCfg<K, S>::TW;
   constexpr int IH = (TH - 1) * S + K, IW = (TW - 1) * S + K;
   constexpr int GH = (S == 1) ? TH + K - 1 : TH + (K + 1) / 2, GW = (S == 1) ? TW + K - 1 : TW + (K + 1) / 2;
-  int smem = (IH * IW + GH * GW) * DW_CCH * 2 + K * K * DW_CCH * 4;
-  const int red_bytes = DW_WARPS * K * K * DW_CCH * 4;                // flush reuses the front of the buffer
+  int smem = (IH * IW + GH * GW) * DW_CCH * 2 + K * K * DW_CCH * 4 + (IH * IW + GH * GW) * 2 + 16;
+  const int red_bytes = DW_WARPS * K * K * DW_CCH * 4;                // the final dW reduction reuses the tiles
   if (smem < red_bytes) smem = red_bytes;
   // the tile grid must cover every OUTPUT pixel (weight gradient) and every INPUT pixel (data gradient): with the
   // reference's static pads, S*Ho can be smaller than H (e.g. H=33, k3 s2 pads (0,1) -> Ho=16 but input row 32 is read)
@@ -390,14 +500,14 @@ static int dw_launch_bwd(DwDev& p, cudaStream_t stream, int slots_given) {
 static int dw_tiles(const mclip_dwconv_args* a, bool bwd) {
   int TH = a->stride == 1 ? 16 : 8, TW = 16;
   if (!bwd) return a->n * ceil_div(a->ho, TH) * ceil_div(a->wo, TW);
-  TH /= 2;
+  TH = a->stride == 1 ? 8 : 4;
   const int hy = max(a->ho, ceil_div(a->h, a->stride)), wx = max(a->wo, ceil_div(a->w, a->stride));
   return a->n * ceil_div(hy, TH) * ceil_div(wx, TW);
 }
 
 extern "C" int mclip_dwconv_slots(const mclip_dwconv_args* a, int backward) {
   if (!a || a->c <= 0) return -1;
-  return dw_slots(ceil_div(a->c, DW_CCH), dw_tiles(a, backward != 0), backward ? 2 : 3);
+  return dw_slots(ceil_div(a->c, DW_CCH), dw_tiles(a, backward != 0), backward ? 3 : 4);
 }
 
 static int dw_fill(const mclip_dwconv_args* a, DwDev& p) {
