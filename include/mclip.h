@@ -183,7 +183,8 @@ typedef struct mclip_se_args {
   const float* w1; const float* b1;     /* _se_reduce: [cse,c], [cse] */
   const float* w2; const float* b2;     /* _se_expand: [c,cse], [c] */
   float* pooled; float* z1; float* gate;          /* fp32 [n,c], [n,cse], [n,c] (saved for backward) */
-  const float* dgate_partials;          /* fp32 [n][chunks][c] (backward) */
+  const float* dgate_partials;          /* fp32 [n][chunks][stride] (backward): d gate sums; stride = dgate_chunk_stride or c */
+  int dgate_chunk_stride;
   float* dz2; float* dz1; float* dpool;           /* fp32 [n,c], [n,cse], [n,c] */
   float* dw1; float* db1; float* dw2; float* db2;
 } mclip_se_args;
@@ -193,7 +194,9 @@ int mclip_se_scale_weights(const float* w, const float* gate, void* out_bf16, in
 
 /* Backward streaming passes (autograd of BatchNorm2d + MemoryEfficientSwish (efficient_net_custom_utils.py:64-80) +
  * SE gating + drop-connect).  mode 0: BN-backward reduction partials [n*chunks][2][c] (sum dv, sum dv*yhat);
- * mode 1: dY = scale*(dv - c1 - yhat*c2) (bf16); mode 2: A2 = gate*swish(scale*y+shift) (bf16) + dgate partials. */
+ * mode 1: dY = scale*(dv - c1 - yhat*c2) (bf16); mode 2: A2 = gate*swish(scale*y+shift) (bf16) + partials
+ * [n][chunks][5][c] = (sum dU*u, sum dU*s', sum s', sum dU*s'*yhat, sum s'*yhat): the d-gate sums AND everything the
+ * following BatchNorm backward needs (mclip_se_bn_combine), so no separate reduction pass runs over the tensor. */
 typedef struct mclip_ew_bwd_args {
   int n, hw, c, act, mode, dv_given, chunks;
   const void* y; const float* scale; const float* shift;
@@ -202,6 +205,8 @@ typedef struct mclip_ew_bwd_args {
   float* partials; void* out;
 } mclip_ew_bwd_args;
 int mclip_ew_backward(const mclip_ew_bwd_args* args, void* stream);
+int mclip_se_bn_combine(const float* partials, int n, int chunks, int c, const float* gate, const float* dpool, float* out_n_2_c,
+                        void* stream);
 int mclip_bn_bwd_finalize(const float* partials, int slots, int c, long long count, int training, float* dgamma, float* dbeta,
                           int accumulate, float* c1, float* c2, void* stream);
 

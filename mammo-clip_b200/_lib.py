@@ -195,7 +195,7 @@ class SeArgs(C.Structure):
         ("n", C.c_int), ("hw", C.c_int), ("c", C.c_int), ("cse", C.c_int), ("chunks", C.c_int), ("accumulate", C.c_int),
         ("pool_partials", C.c_void_p), ("w1", C.c_void_p), ("b1", C.c_void_p), ("w2", C.c_void_p), ("b2", C.c_void_p),
         ("pooled", C.c_void_p), ("z1", C.c_void_p), ("gate", C.c_void_p),
-        ("dgate_partials", C.c_void_p), ("dz2", C.c_void_p), ("dz1", C.c_void_p), ("dpool", C.c_void_p),
+        ("dgate_partials", C.c_void_p), ("dgate_chunk_stride", C.c_int), ("dz2", C.c_void_p), ("dz1", C.c_void_p), ("dpool", C.c_void_p),
         ("dw1", C.c_void_p), ("db1", C.c_void_p), ("dw2", C.c_void_p), ("db2", C.c_void_p),
     ]
 

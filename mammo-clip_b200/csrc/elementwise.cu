@@ -14,20 +14,53 @@
 #include "common.cuh"
 #include "mclip_internal.h"
 
-#define EW_MAX_THREADS 384
+#define EW_MAX_THREADS 256
+#define EW_CPT 4            // channels per thread (8-byte vectors; a warp still covers 256 contiguous bytes)
+#define EW_UNR 4            // pixels in flight per thread
+
+typedef unsigned long long u64;
+__device__ __forceinline__ float2 bf2_to_f2(uint32_t u) { return make_float2(__uint_as_float(u << 16), __uint_as_float(u & 0xffff0000u)); }
+__device__ __forceinline__ float2 ffma2r(const float2& a, const float2& b, const float2& c) {
+  float2 d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(reinterpret_cast<u64&>(d)) : "l"(reinterpret_cast<const u64&>(a)), "l"(reinterpret_cast<const u64&>(b)),
+      "l"(reinterpret_cast<const u64&>(c)));
+  return d;
+}
+__device__ __forceinline__ void ffma2(float2& d, const float2& a, const float2& b) { d = ffma2r(a, b, d); }
+__device__ __forceinline__ float2 fmul2(const float2& a, const float2& b) {
+  float2 d;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(reinterpret_cast<u64&>(d)) : "l"(reinterpret_cast<const u64&>(a)), "l"(reinterpret_cast<const u64&>(b)));
+  return d;
+}
+__device__ __forceinline__ uint2 ldg_b64(const bf16* p) {
+  uint2 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v2.u32 {%0,%1}, [%2];" : "=r"(r.x), "=r"(r.y) : "l"(p));
+  return r;
+}
+__device__ __forceinline__ void stg_b64(bf16* p, uint2 v) {
+  asm volatile("st.global.L1::no_allocate.v2.u32 [%0], {%1,%2};" ::"l"(p), "r"(v.x), "r"(v.y) : "memory");
+}
+// sigma(t) via one MUFU; returns (sigma(t.x), sigma(t.y))
+__device__ __forceinline__ float2 sigmoid2(const float2& t) {
+  const float2 h = make_float2(fast_tanh(0.5f * t.x), fast_tanh(0.5f * t.y));
+  return ffma2r(h, make_float2(0.5f, 0.5f), make_float2(0.5f, 0.5f));
+}
 
 struct EwGeom {
-  int N, HW, C, CV, PL, chunks, pix_per_chunk;
+  int N, HW, C, G, CG, TPP, PL, chunks, pix_per_chunk;
 };
 
+// Channel groups of <= 1024 channels (256 threads x 4); a thread keeps its 4 channels for the whole kernel.
 static int ew_geom(int n, int hw, int c, EwGeom* g, int* threads) {
-  if (c % 8 != 0 || c / 8 > EW_MAX_THREADS) { mclip_set_error("elementwise: C=%d must be a multiple of 8 and <= %d", c, 8 * EW_MAX_THREADS); return MCLIP_ERR_INVALID; }
-  g->N = n; g->HW = hw; g->C = c; g->CV = c / 8;
-  g->PL = 256 / g->CV; if (g->PL < 1) g->PL = 1;
-  *threads = g->CV * g->PL;
-  long long want = (long long)mclip_num_sms() * 8;
-  int chunks = (int)((want + n - 1) / n);
-  int max_chunks = (hw + g->PL * 4 - 1) / (g->PL * 4);
+  if (c % 8 != 0) { mclip_set_error("elementwise: C=%d must be a multiple of 8", c); return MCLIP_ERR_INVALID; }
+  int G = (c + EW_MAX_THREADS * EW_CPT - 1) / (EW_MAX_THREADS * EW_CPT);
+  while (c % (G * EW_CPT) != 0) ++G;
+  g->N = n; g->HW = hw; g->C = c; g->G = G; g->CG = c / G; g->TPP = g->CG / EW_CPT;
+  g->PL = EW_MAX_THREADS / g->TPP; if (g->PL < 1) g->PL = 1;
+  *threads = g->TPP * g->PL;
+  long long want = (long long)mclip_num_sms() * 16;
+  int chunks = (int)((want + (long long)n * G - 1) / ((long long)n * G));
+  int max_chunks = (hw + g->PL * EW_UNR - 1) / (g->PL * EW_UNR);
   if (chunks > max_chunks) chunks = max_chunks;
   if (chunks < 1) chunks = 1;
   g->pix_per_chunk = (hw + chunks - 1) / chunks;
@@ -41,17 +74,15 @@ extern "C" int mclip_ew_chunks(int n, int hw, int c) {
   return g.chunks;
 }
 
-// block reduction over the PL pixel lanes of 8-channel vectors: out[cv*8+i] = sum over lanes
-__device__ __forceinline__ void ew_block_reduce8(float* smem, const float* v, int cv, int pl, int CV, int PL, float* dst, bool add_to = false) {
-  // smem: [PL][CV*8]
+// block reduction over the PL pixel lanes: dst[cv*4+i] = sum over lanes of v[i]   (smem: [PL][CG])
+__device__ __forceinline__ void ew_block_reduce4(float* smem, const float2* v, int cv, int pl, int CG, int PL, float* dst) {
   __syncthreads();
-#pragma unroll
-  for (int i = 0; i < 8; ++i) smem[(size_t)pl * CV * 8 + cv * 8 + i] = v[i];
+  *reinterpret_cast<float4*>(smem + (size_t)pl * CG + cv * 4) = make_float4(v[0].x, v[0].y, v[1].x, v[1].y);
   __syncthreads();
-  for (int i = threadIdx.x; i < CV * 8; i += blockDim.x) {
+  for (int i = threadIdx.x; i < CG; i += blockDim.x) {
     float s = 0.f;
-    for (int l = 0; l < PL; ++l) s += smem[(size_t)l * CV * 8 + i];
-    dst[i] = add_to ? dst[i] + s : s;
+    for (int l = 0; l < PL; ++l) s += smem[(size_t)l * CG + i];
+    dst[i] = s;
   }
 }
 
@@ -111,42 +142,55 @@ struct EwFwdDev {
   bf16* out; float* pool_part;     // pool_part: [N][chunks][C]
 };
 
-__global__ void __launch_bounds__(EW_MAX_THREADS) mclip_ew_fwd_kernel(const EwFwdDev p) {
+__global__ void __launch_bounds__(EW_MAX_THREADS, 4) mclip_ew_fwd_kernel(const EwFwdDev p) {
   extern __shared__ float ew_smem[];
   const EwGeom& g = p.g;
-  const int cv = threadIdx.x % g.CV, pl = threadIdx.x / g.CV;
-  const int n = blockIdx.x / g.chunks, chunk = blockIdx.x % g.chunks;
+  const int cv = threadIdx.x % g.TPP, pl = threadIdx.x / g.TPP;
+  const int grp = blockIdx.x % g.G, bc = blockIdx.x / g.G;
+  const int n = bc / g.chunks, chunk = bc % g.chunks;
   const int p0 = chunk * g.pix_per_chunk, p1 = min(g.HW, p0 + g.pix_per_chunk);
-  float a[8], b[8], acc[8];
+  const int c = grp * g.CG + cv * EW_CPT;
+  const float f = p.act ? 0.5f : 1.0f;                    // swish(t) = h + h*tanh(h), h = t/2
+  float2 a[2], b[2], acc[2];
 #pragma unroll
-  for (int i = 0; i < 8; ++i) { a[i] = p.scale ? p.scale[cv * 8 + i] : 1.f; b[i] = p.shift ? p.shift[cv * 8 + i] : 0.f; acc[i] = 0.f; }
-  const float rs = p.rowscale ? p.rowscale[n] : 1.f;
-  const size_t base = (size_t)n * g.HW * g.C + (size_t)cv * 8;
-  for (int px = p0 + pl; px < p1; px += g.PL) {
-    const size_t off = base + (size_t)px * g.C;
-    float f[8];
-    unpack8(ldg_bf16x8(p.y + off), f);
+  for (int i = 0; i < 2; ++i) {
+    a[i] = p.scale ? make_float2(f * p.scale[c + 2 * i], f * p.scale[c + 2 * i + 1]) : make_float2(f, f);
+    b[i] = p.shift ? make_float2(f * p.shift[c + 2 * i], f * p.shift[c + 2 * i + 1]) : make_float2(0.f, 0.f);
+    acc[i] = make_float2(0.f, 0.f);
+  }
+  const float rsv = p.rowscale ? p.rowscale[n] : 1.f;
+  const float2 rs = make_float2(rsv, rsv), one = make_float2(1.f, 1.f);
+  const size_t base = (size_t)n * g.HW * g.C + c;
+  for (int px0 = p0 + pl; px0 < p1; px0 += g.PL * EW_UNR) {
+    uint2 yv[EW_UNR], rv[EW_UNR];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      float v = fmaf(f[i], a[i], b[i]);
-      f[i] = (p.act ? swish_f(v) : v) * rs;
+    for (int u = 0; u < EW_UNR; ++u) {
+      const int px = px0 + u * g.PL;
+      if (px < p1) {
+        const size_t off = base + (size_t)px * g.C;
+        yv[u] = ldg_b64(p.y + off);
+        if (p.residual) rv[u] = ldg_b64(p.residual + off);
+      }
     }
-    if (p.residual) {
-      float r[8];
-      unpack8(ldg_bf16x8(p.residual + off), r);
 #pragma unroll
-      for (int i = 0; i < 8; ++i) f[i] += r[i];
-    }
-    bf16x8 pk = pack8(f);
-    if (p.out) stg_bf16x8(p.out + off, pk);
-    if (p.pool_part) {
-      float r[8];
-      unpack8(pk, r);        // pool what the consumer will read (bf16-rounded), like the reference's autocast tensors
+    for (int u = 0; u < EW_UNR; ++u) {
+      const int px = px0 + u * g.PL;
+      if (px >= p1) break;
+      const uint32_t yw[2] = {yv[u].x, yv[u].y}, rw[2] = {rv[u].x, rv[u].y};
+      uint32_t ow[2];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) acc[i] += r[i];
+      for (int i = 0; i < 2; ++i) {
+        float2 h = ffma2r(bf2_to_f2(yw[i]), a[i], b[i]);
+        if (p.act) h = ffma2r(h, make_float2(fast_tanh(h.x), fast_tanh(h.y)), h);
+        if (p.rowscale) h = fmul2(h, rs);
+        if (p.residual) h = ffma2r(bf2_to_f2(rw[i]), one, h);
+        ow[i] = pack_bf16(h.x, h.y);
+        if (p.pool_part) ffma2(acc[i], bf2_to_f2(ow[i]), one);     // pool what the consumer reads (bf16-rounded)
+      }
+      if (p.out) stg_b64(p.out + base + (size_t)px * g.C, make_uint2(ow[0], ow[1]));
     }
   }
-  if (p.pool_part) ew_block_reduce8(ew_smem, acc, cv, pl, g.CV, g.PL, p.pool_part + ((size_t)n * g.chunks + chunk) * g.C);
+  if (p.pool_part) ew_block_reduce4(ew_smem, acc, cv, pl, g.CG, g.PL, p.pool_part + ((size_t)n * g.chunks + chunk) * g.C + grp * g.CG);
 }
 
 extern "C" int mclip_ew_forward(const mclip_ew_args* a, void* stream) {
@@ -157,8 +201,8 @@ extern "C" int mclip_ew_forward(const mclip_ew_args* a, void* stream) {
   if (a->pool_partials) MCLIP_REQUIRE(a->chunks == p.g.chunks, "mclip_ew_forward: chunks=%d, expected %d", a->chunks, p.g.chunks);
   p.y = (const bf16*)a->y; p.scale = a->scale; p.shift = a->shift; p.act = a->act; p.rowscale = a->rowscale;
   p.residual = (const bf16*)a->residual; p.out = (bf16*)a->out; p.pool_part = a->pool_partials;
-  const int smem = p.g.PL * p.g.C * 4;
-  mclip_ew_fwd_kernel<<<a->n * p.g.chunks, threads, smem, (cudaStream_t)stream>>>(p);
+  const int smem = p.g.PL * p.g.CG * 4;
+  mclip_ew_fwd_kernel<<<a->n * p.g.chunks * p.g.G, threads, smem, (cudaStream_t)stream>>>(p);
   MCLIP_CHECK_LAUNCH();
   return MCLIP_OK;
 }
@@ -276,68 +320,123 @@ struct EwBwdDev {
 };
 
 template <int MODE>   // 0 reduce, 1 apply, 2 se pass 1
-__global__ void __launch_bounds__(EW_MAX_THREADS) mclip_ew_bwd_kernel(const EwBwdDev p) {
+__global__ void __launch_bounds__(EW_MAX_THREADS, 3) mclip_ew_bwd_kernel(const EwBwdDev p) {
   extern __shared__ float ew_smem[];
   const EwGeom& g = p.g;
-  const int cv = threadIdx.x % g.CV, pl = threadIdx.x / g.CV;
-  const int n = blockIdx.x / g.chunks, chunk = blockIdx.x % g.chunks;
+  const int cv = threadIdx.x % g.TPP, pl = threadIdx.x / g.TPP;
+  const int grp = blockIdx.x % g.G, bc = blockIdx.x / g.G;
+  const int n = bc / g.chunks, chunk = bc % g.chunks;
   const int p0 = chunk * g.pix_per_chunk, p1 = min(g.HW, p0 + g.pix_per_chunk);
-  float a[8], b[8], mu[8], is[8], gt[8], dp[8], dvv[8], k1[8], k2[8], acc0[8], acc1[8];
+  const int c = grp * g.CG + cv * EW_CPT;
+  constexpr int NACC = (MODE == 2) ? 5 : 2;
+  float2 a[2], b[2], mu[2], is[2], gt[2], dp[2], dvv[2], k1[2], k2[2], acc[NACC][2];
+  const float rsv = p.rowscale ? p.rowscale[n] : 1.f;
 #pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    const int c = cv * 8 + i;
-    a[i] = p.scale ? p.scale[c] : 1.f; b[i] = p.shift ? p.shift[c] : 0.f;
-    mu[i] = p.mean ? p.mean[c] : 0.f; is[i] = p.invstd ? p.invstd[c] : 1.f;
-    gt[i] = p.gate ? p.gate[(size_t)n * g.C + c] : 1.f;
-    dp[i] = p.dpool ? p.dpool[(size_t)n * g.C + c] : 0.f;
-    dvv[i] = p.dvec ? p.dvec[(size_t)n * g.C + c] : 0.f;
-    k1[i] = (MODE == 1 && p.c1) ? p.c1[c] : 0.f; k2[i] = (MODE == 1 && p.c2) ? p.c2[c] : 0.f;
-    acc0[i] = acc1[i] = 0.f;
+  for (int i = 0; i < 2; ++i) {
+    const int ci = c + 2 * i;
+    auto ld2 = [&](const float* q, float dflt) { return q ? make_float2(q[ci], q[ci + 1]) : make_float2(dflt, dflt); };
+    auto ld2n = [&](const float* q, float dflt) { return q ? make_float2(q[(size_t)n * g.C + ci], q[(size_t)n * g.C + ci + 1]) : make_float2(dflt, dflt); };
+    a[i] = ld2(p.scale, 1.f); b[i] = ld2(p.shift, 0.f); mu[i] = ld2(p.mean, 0.f); is[i] = ld2(p.invstd, 1.f);
+    gt[i] = ld2n(p.gate, 1.f); dp[i] = ld2n(p.dpool, 0.f); dvv[i] = ld2n(p.dvec, 0.f);
+    if (MODE != 2) { gt[i].x *= rsv; gt[i].y *= rsv; dp[i].x *= rsv; dp[i].y *= rsv; }    // drop-connect row scale folded in
+    k1[i] = (MODE == 1) ? ld2(p.c1, 0.f) : make_float2(0.f, 0.f);
+    k2[i] = (MODE == 1) ? ld2(p.c2, 0.f) : make_float2(0.f, 0.f);
+#pragma unroll
+    for (int q = 0; q < NACC; ++q) acc[q][i] = make_float2(0.f, 0.f);
   }
-  const float rs = p.rowscale ? p.rowscale[n] : 1.f;
-  const size_t base = (size_t)n * g.HW * g.C + (size_t)cv * 8;
-  for (int px = p0 + pl; px < p1; px += g.PL) {
-    const size_t off = base + (size_t)px * g.C;
-    float y[8], du[8];
-    unpack8(ldg_bf16x8(p.y + off), y);
-    if (p.dU) unpack8(ldg_bf16x8(p.dU + off), du);
-    else {
+  const float2 one = make_float2(1.f, 1.f);
+  const size_t base = (size_t)n * g.HW * g.C + c;
+  for (int px0 = p0 + pl; px0 < p1; px0 += g.PL * EW_UNR) {
+    uint2 yv[EW_UNR], dv_[EW_UNR];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) du[i] = dvv[i];
+    for (int u = 0; u < EW_UNR; ++u) {
+      const int px = px0 + u * g.PL;
+      if (px < p1) {
+        const size_t off = base + (size_t)px * g.C;
+        yv[u] = ldg_b64(p.y + off);
+        if (p.dU) dv_[u] = ldg_b64(p.dU + off);
+      }
     }
-    if (MODE == 2) {
-      float o[8];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        float u = swish_f(fmaf(y[i], a[i], b[i]));
-        acc0[i] = fmaf(du[i], u, acc0[i]);
-        o[i] = u * gt[i];
-      }
-      stg_bf16x8(p.out + off, pack8(o));
-    } else {
-      float o[8];
+    for (int u = 0; u < EW_UNR; ++u) {
+      const int px = px0 + u * g.PL;
+      if (px >= p1) break;
+      const uint32_t yw[2] = {yv[u].x, yv[u].y}, dw_[2] = {dv_[u].x, dv_[u].y};
+      uint32_t ow[2];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        float dv;
-        if (p.dv_given) dv = du[i];
-        else {
-          float t = fmaf(du[i], gt[i], dp[i]) * rs;
-          dv = p.act ? t * swish_grad_f(fmaf(y[i], a[i], b[i])) : t;
+      for (int i = 0; i < 2; ++i) {
+        const float2 y = bf2_to_f2(yw[i]);
+        const float2 du = p.dU ? bf2_to_f2(dw_[i]) : dvv[i];
+        const float2 yh = fmul2(make_float2(y.x - mu[i].x, y.y - mu[i].y), is[i]);
+        if (MODE == 2) {
+          const float2 v = ffma2r(y, a[i], b[i]);
+          const float2 sg = sigmoid2(v);
+          const float2 u_ = fmul2(v, sg);                                             // swish(v)
+          const float2 sp = fmul2(sg, ffma2r(v, make_float2(1.f - sg.x, 1.f - sg.y), one));   // swish'(v)
+          const float2 dsp = fmul2(du, sp);
+          ffma2(acc[0][i], du, u_);          // d gate
+          ffma2(acc[1][i], dsp, one);        // sum dU s'
+          ffma2(acc[2][i], sp, one);         // sum s'
+          ffma2(acc[3][i], dsp, yh);         // sum dU s' yhat
+          ffma2(acc[4][i], sp, yh);          // sum s' yhat
+          const float2 o = fmul2(u_, gt[i]);
+          ow[i] = pack_bf16(o.x, o.y);
+        } else {
+          float2 dv;
+          if (p.dv_given) dv = du;
+          else {
+            dv = ffma2r(du, gt[i], dp[i]);
+            if (p.act) {
+              const float2 v = ffma2r(y, a[i], b[i]);
+              const float2 sg = sigmoid2(v);
+              dv = fmul2(dv, fmul2(sg, ffma2r(v, make_float2(1.f - sg.x, 1.f - sg.y), one)));
+            }
+          }
+          if (MODE == 0) { ffma2(acc[0][i], dv, one); ffma2(acc[1][i], dv, yh); }
+          else {
+            const float2 t = ffma2r(yh, make_float2(-k2[i].x, -k2[i].y), make_float2(dv.x - k1[i].x, dv.y - k1[i].y));
+            const float2 o = fmul2(a[i], t);
+            ow[i] = pack_bf16(o.x, o.y);
+          }
         }
-        const float yh = (y[i] - mu[i]) * is[i];
-        if (MODE == 0) { acc0[i] += dv; acc1[i] = fmaf(dv, yh, acc1[i]); }
-        else o[i] = a[i] * (dv - k1[i] - yh * k2[i]);
       }
-      if (MODE == 1) stg_bf16x8(p.out + off, pack8(o));
+      if (MODE != 0) stg_b64(p.out + base + (size_t)px * g.C, make_uint2(ow[0], ow[1]));
     }
   }
   if (MODE == 0) {
-    float* dst = p.part + (size_t)blockIdx.x * 2 * g.C;
-    ew_block_reduce8(ew_smem, acc0, cv, pl, g.CV, g.PL, dst);
-    ew_block_reduce8(ew_smem, acc1, cv, pl, g.CV, g.PL, dst + g.C);
+    float* dst = p.part + (size_t)bc * 2 * g.C + grp * g.CG;
+    ew_block_reduce4(ew_smem, acc[0], cv, pl, g.CG, g.PL, dst);
+    ew_block_reduce4(ew_smem, acc[1], cv, pl, g.CG, g.PL, dst + g.C);
   } else if (MODE == 2) {
-    ew_block_reduce8(ew_smem, acc0, cv, pl, g.CV, g.PL, p.part + ((size_t)n * g.chunks + chunk) * g.C);
+    float* dst = p.part + (size_t)bc * 5 * g.C + grp * g.CG;
+#pragma unroll
+    for (int q = 0; q < 5; ++q) ew_block_reduce4(ew_smem, acc[q], cv, pl, g.CG, g.PL, dst + (size_t)q * g.C);
   }
+}
+
+// BN1-backward sums from the SE pass-1 partials: with dv = (dU*gate + dpool) * s'(v),
+//   sum dv      = gate * sum(dU s')      + dpool * sum(s')
+//   sum dv*yhat = gate * sum(dU s' yhat) + dpool * sum(s' yhat)        per (sample, channel)  ->  out [N][2][C]
+__global__ void mclip_se_bn_combine_kernel(const float* __restrict__ part, int chunks, int C, const float* __restrict__ gate,
+                                           const float* __restrict__ dpool, float* __restrict__ out, int N) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N * C) return;
+  const int n = i / C, c = i % C;
+  float s1 = 0.f, s2 = 0.f, s3 = 0.f, s4 = 0.f;
+  for (int k = 0; k < chunks; ++k) {
+    const float* q = part + ((size_t)n * chunks + k) * 5 * C + c;
+    s1 += q[C]; s2 += q[2 * C]; s3 += q[3 * C]; s4 += q[4 * C];
+  }
+  const float g = gate[i], d = dpool[i];
+  out[((size_t)n * 2 + 0) * C + c] = g * s1 + d * s2;
+  out[((size_t)n * 2 + 1) * C + c] = g * s3 + d * s4;
+}
+
+extern "C" int mclip_se_bn_combine(const float* partials, int n, int chunks, int c, const float* gate, const float* dpool, float* out, void* stream) {
+  MCLIP_REQUIRE(partials && gate && dpool && out && n > 0 && c > 0, "mclip_se_bn_combine: bad arguments");
+  mclip_se_bn_combine_kernel<<<ceil_div((long long)n * c, 256), 256, 0, (cudaStream_t)stream>>>(partials, chunks, c, gate, dpool, out, n);
+  MCLIP_CHECK_LAUNCH();
+  return MCLIP_OK;
 }
 
 extern "C" int mclip_ew_backward(const mclip_ew_bwd_args* a, void* stream) {
@@ -351,8 +450,8 @@ extern "C" int mclip_ew_backward(const mclip_ew_bwd_args* a, void* stream) {
   p.y = (const bf16*)a->y; p.scale = a->scale; p.shift = a->shift; p.act = a->act; p.dv_given = a->dv_given;
   p.dU = (const bf16*)a->du; p.dvec = a->dvec; p.gate = a->gate; p.dpool = a->dpool; p.rowscale = a->rowscale;
   p.mean = a->mean; p.invstd = a->invstd; p.c1 = a->c1; p.c2 = a->c2; p.part = a->partials; p.out = (bf16*)a->out;
-  const int smem = p.g.PL * p.g.C * 4;
-  const int grid = a->n * p.g.chunks;
+  const int smem = p.g.PL * p.g.CG * 4;
+  const int grid = a->n * p.g.chunks * p.g.G;
   if (a->mode == 0) mclip_ew_bwd_kernel<0><<<grid, threads, smem, (cudaStream_t)stream>>>(p);
   else if (a->mode == 1) mclip_ew_bwd_kernel<1><<<grid, threads, smem, (cudaStream_t)stream>>>(p);
   else mclip_ew_bwd_kernel<2><<<grid, threads, smem, (cudaStream_t)stream>>>(p);
@@ -386,7 +485,7 @@ extern "C" int mclip_bn_bwd_finalize(const float* partials, int slots, int c, lo
 //   k1 (per sample): dz2 = dg*g*(1-g) ; dh = W2^T dz2 ; dz1 = dh*swish'(z1) ; ds = W1^T dz1 ; dpool = ds/HW
 //   k2 (per output element): dW2 = sum_n dz2 h^T ; db2 = sum_n dz2 ; dW1 = sum_n dz1 s^T ; db1 = sum_n dz1
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) mclip_se_bwd1_kernel(const float* __restrict__ dg_part, int chunks, int C, int Cse, float inv_hw,
+__global__ void __launch_bounds__(256) mclip_se_bwd1_kernel(const float* __restrict__ dg_part, int chunks, int cstride, int C, int Cse, float inv_hw,
                                                             const float* __restrict__ W1, const float* __restrict__ W2, const float* __restrict__ z1,
                                                             const float* __restrict__ gate, float* __restrict__ dz2_out, float* __restrict__ dz1_out,
                                                             float* __restrict__ dpool) {
@@ -396,7 +495,7 @@ __global__ void __launch_bounds__(256) mclip_se_bwd1_kernel(const float* __restr
   const int n = blockIdx.x;
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
     float dg = 0.f;
-    for (int k = 0; k < chunks; ++k) dg += dg_part[((size_t)n * chunks + k) * C + c];
+    for (int k = 0; k < chunks; ++k) dg += dg_part[((size_t)n * chunks + k) * cstride + c];
     const float g = gate[(size_t)n * C + c];
     const float v = dg * g * (1.f - g);
     dz2[c] = v;
@@ -455,7 +554,7 @@ extern "C" int mclip_se_fc_backward(const mclip_se_args* a, void* stream) {
   MCLIP_REQUIRE(a && a->dgate_partials && a->w1 && a->w2 && a->z1 && a->gate && a->pooled && a->dz2 && a->dz1 && a->dpool && a->dw1 && a->db1 && a->dw2 && a->db2,
                 "mclip_se_fc_backward: null operand");
   const int smem = (a->c + a->cse) * 4;
-  mclip_se_bwd1_kernel<<<a->n, 256, smem, (cudaStream_t)stream>>>(a->dgate_partials, a->chunks, a->c, a->cse, 1.0f / (float)a->hw, a->w1, a->w2, a->z1, a->gate,
+  mclip_se_bwd1_kernel<<<a->n, 256, smem, (cudaStream_t)stream>>>(a->dgate_partials, a->chunks, a->dgate_chunk_stride > 0 ? a->dgate_chunk_stride : a->c, a->c, a->cse, 1.0f / (float)a->hw, a->w1, a->w2, a->z1, a->gate,
                                                                    a->dz2, a->dz1, a->dpool);
   MCLIP_CHECK_LAUNCH();
   const int total = 2 * a->c * a->cse + a->c + a->cse;

@@ -258,7 +258,12 @@ def _backward(net, S, dfeat):
         dpool = ops.se_fc_backward(dgp, ho * wo, w1, w2, B["pooled"], B["z1"], B["gate"], dw1, db1, dw2, db2)
         grads[pre + "_se_reduce.weight"], grads[pre + "_se_reduce.bias"] = dw1, db1
         grads[pre + "_se_expand.weight"], grads[pre + "_se_expand.bias"] = dw2, db2
-        dy1 = _bn_backward(y1, B["bn1"], training, blk._bn1, grads, pre + "_bn1", 1, du=da2, gate=B["gate"], dpool=dpool)
+        # BN1 backward sums come out of the SE pass-1 partials (no separate reduction pass over dA2 / Y1)
+        bnp1 = ops.se_bn_combine(dgp, B["gate"], dpool)
+        dg1, db1_ = torch.empty_like(blk._bn1.weight), torch.empty_like(blk._bn1.bias)
+        c1, c2 = ops.bn_bwd_finalize(bnp1, B["bn1"].count, training, dg1, db1_)
+        grads[pre + "_bn1.weight"], grads[pre + "_bn1.bias"] = dg1, db1_
+        dy1 = ops.ew_backward(1, y1, B["bn1"], 1, du=da2, gate=B["gate"], dpool=dpool, c1=c1, c2=c2)
         del da2
         dy1 = dy1.view(n, ho, wo, g.cexp)
         ddw = torch.empty_like(blk._depthwise_conv.weight)

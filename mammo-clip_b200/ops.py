@@ -289,7 +289,8 @@ def se_fc(part, hw, w1, b1, w2, b2):
 
 
 def se_fc_backward(dg_part, hw, w1, w2, pooled, z1, gate, dw1, db1, dw2, db2):
-    n, chunks, c = dg_part.shape
+    """dg_part: [N,chunks,C] or the SE pass-1 partials [N,chunks,5,C] (component 0 = d gate sums)."""
+    n, chunks, c = dg_part.shape[0], dg_part.shape[1], dg_part.shape[-1]
     cse = w1.shape[0]
     dev = dg_part.device
     dz2 = torch.empty((n, c), dtype=torch.float32, device=dev)
@@ -299,6 +300,7 @@ def se_fc_backward(dg_part, hw, w1, w2, pooled, z1, gate, dw1, db1, dw2, db2):
     a.n, a.hw, a.c, a.cse, a.chunks, a.accumulate = n, hw, c, cse, chunks, 0
     a.w1, a.w2, a.pooled, a.z1, a.gate = w1.data_ptr(), w2.data_ptr(), pooled.data_ptr(), z1.data_ptr(), gate.data_ptr()
     a.dgate_partials, a.dz2, a.dz1, a.dpool = dg_part.data_ptr(), dz2.data_ptr(), dz1.data_ptr(), dpool.data_ptr()
+    a.dgate_chunk_stride = dg_part.stride(1)
     a.dw1, a.db1, a.dw2, a.db2 = dw1.data_ptr(), db1.data_ptr(), dw2.data_ptr(), db2.data_ptr()
     call("mclip_se_fc_backward", C.byref(a))
     return dpool
@@ -325,7 +327,7 @@ def ew_backward(mode, y, bn, act, du=None, dvec=None, gate=None, dpool=None, row
     part = out = None
     if mode != 1:
         a.chunks = ew_chunks(n, hw, c)
-        shape = (n * a.chunks, 2, c) if mode == 0 else (n, a.chunks, c)
+        shape = (n * a.chunks, 2, c) if mode == 0 else (n, a.chunks, 5, c)
         part = torch.empty(shape, dtype=torch.float32, device=y.device)
         a.partials = part.data_ptr()
     if mode != 0:
@@ -333,6 +335,14 @@ def ew_backward(mode, y, bn, act, du=None, dvec=None, gate=None, dpool=None, row
         a.out = out.data_ptr()
     call("mclip_ew_backward", C.byref(a), nbytes=2 * y.numel() * (1 + int(du is not None) + int(mode != 0)))
     return part if mode == 0 else out if mode == 1 else (out, part)
+
+
+def se_bn_combine(se_part, gate, dpool):
+    """SE pass-1 partials [N,chunks,5,C] + gate/dpool [N,C] -> BN-backward partials [N,2,C]."""
+    n, chunks, _, c = se_part.shape
+    out = torch.empty((n, 2, c), dtype=torch.float32, device=se_part.device)
+    call("mclip_se_bn_combine", ptr(se_part), n, chunks, c, ptr(gate), ptr(dpool), ptr(out))
+    return out
 
 
 def bn_bwd_finalize(partials, count, training, dgamma, dbeta):

@@ -134,9 +134,13 @@ def test_bn_and_elementwise(n, hw, c):
     assert rel_err(dg, g2.grad) < 5e-3 and rel_err(db, b2.grad) < 5e-3
     dy = ops.ew_backward(1, y, st, 1, du=du, gate=gate, dpool=dpool, c1=c1, c2=c2)
     assert rel_err(dy.float(), yv.grad) < 1e-2
-    a2, dgp = ops.ew_backward(2, y, st, 1, du=du, gate=gate)
+    a2, sep = ops.ew_backward(2, y, st, 1, du=du, gate=gate)
     assert rel_err(a2.float(), (u * gate.view(n, 1, c)).detach()) < 8e-3
-    assert rel_err(dgp.sum(1), (du.float() * u.detach()).sum(1)) < 5e-3
+    assert sep.shape[2] == 5
+    assert rel_err(sep[:, :, 0].sum(1), (du.float() * u.detach()).sum(1)) < 5e-3
+    # the four extra sums reproduce the BN-backward reduction without a pass of their own
+    bnp = ops.se_bn_combine(sep, gate, dpool)
+    assert rel_err(bnp.sum(0), part.sum(0)) < 5e-3
 
 
 @pytest.mark.parametrize("n,c,cse,hw", [(4, 144, 6, 100), (2, 3072, 128, 50), (3, 48, 12, 64)])
