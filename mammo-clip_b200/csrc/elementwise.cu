@@ -89,16 +89,36 @@ __device__ __forceinline__ void ew_block_reduce4(float* smem, const float2* v, i
 // ------------------------------------------------------------------------------------------------
 // BatchNorm statistics -> affine (a = gamma*invstd, b = beta - mean*a), running-stat update
 // ------------------------------------------------------------------------------------------------
-__global__ void mclip_bn_finalize_kernel(const float* __restrict__ partials, int slots, int C, double count, const float* __restrict__ gamma,
-                                         const float* __restrict__ beta, float* running_mean, float* running_var, long long* num_batches,
-                                         float momentum, float eps, int training, float* scale, float* shift, float* mean_out, float* invstd_out) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c == 0 && training && num_batches) *num_batches += 1;
-  if (c >= C) return;
+// 256 threads = 32 channels x 8 slot lanes: each lane strides over the partial slots, fp64 tree-combine in smem
+#define BNF_CH 32
+#define BNF_LANES 8
+__device__ __forceinline__ void bn_reduce_slots(const float* __restrict__ partials, int slots, int C, int c, int lane, double& s, double& q,
+                                                double (*sm)[BNF_LANES][BNF_CH]) {
+  s = 0.0; q = 0.0;
+  if (c < C)
+    for (int k = lane; k < slots; k += BNF_LANES) { s += (double)partials[((size_t)k * 2 + 0) * C + c]; q += (double)partials[((size_t)k * 2 + 1) * C + c]; }
+  const int cl = threadIdx.x % BNF_CH;
+  sm[0][lane][cl] = s; sm[1][lane][cl] = q;
+  __syncthreads();
+  if (lane == 0) {
+    s = 0.0; q = 0.0;
+#pragma unroll
+    for (int l = 0; l < BNF_LANES; ++l) { s += sm[0][l][cl]; q += sm[1][l][cl]; }      // fixed order => deterministic
+  }
+}
+
+__global__ void __launch_bounds__(BNF_CH * BNF_LANES) mclip_bn_finalize_kernel(
+    const float* __restrict__ partials, int slots, int C, double count, const float* __restrict__ gamma, const float* __restrict__ beta,
+    float* running_mean, float* running_var, long long* num_batches, float momentum, float eps, int training, float* scale, float* shift,
+    float* mean_out, float* invstd_out) {
+  __shared__ double sm[2][BNF_LANES][BNF_CH];
+  const int c = blockIdx.x * BNF_CH + threadIdx.x % BNF_CH, lane = threadIdx.x / BNF_CH;
+  if (blockIdx.x == 0 && threadIdx.x == 0 && training && num_batches) *num_batches += 1;
   float mean, invstd;
   if (training) {
-    double s = 0.0, q = 0.0;
-    for (int k = 0; k < slots; ++k) { s += (double)partials[((size_t)k * 2 + 0) * C + c]; q += (double)partials[((size_t)k * 2 + 1) * C + c]; }
+    double s, q;
+    bn_reduce_slots(partials, slots, C, c, lane, s, q, sm);
+    if (lane != 0 || c >= C) return;
     double m = s / count;
     double var = q / count - m * m;
     if (var < 0.0) var = 0.0;
@@ -110,6 +130,7 @@ __global__ void mclip_bn_finalize_kernel(const float* __restrict__ partials, int
       running_var[c] = (1.f - momentum) * running_var[c] + momentum * (float)unbiased;
     }
   } else {
+    if (lane != 0 || c >= C) return;
     mean = running_mean[c];
     invstd = rsqrtf(running_var[c] + eps);
   }
@@ -124,7 +145,7 @@ extern "C" int mclip_bn_finalize(const mclip_bn_args* a, void* stream) {
   MCLIP_REQUIRE(a && a->gamma && a->beta && a->scale && a->shift && a->mean && a->invstd, "mclip_bn_finalize: null operand");
   MCLIP_REQUIRE(a->training ? (a->partials != nullptr && a->slots > 0 && a->count > 0) : (a->running_mean && a->running_var),
                 "mclip_bn_finalize: %s", a->training ? "training needs partials and a positive count" : "eval needs running statistics");
-  mclip_bn_finalize_kernel<<<ceil_div(a->c, 128), 128, 0, (cudaStream_t)stream>>>(a->partials, a->slots, a->c, (double)a->count, a->gamma, a->beta,
+  mclip_bn_finalize_kernel<<<ceil_div(a->c, BNF_CH), BNF_CH * BNF_LANES, 0, (cudaStream_t)stream>>>(a->partials, a->slots, a->c, (double)a->count, a->gamma, a->beta,
                                                                                a->running_mean, a->running_var, a->num_batches_tracked,
                                                                                a->momentum, a->eps, a->training, a->scale, a->shift, a->mean, a->invstd);
   MCLIP_CHECK_LAUNCH();
@@ -460,12 +481,14 @@ extern "C" int mclip_ew_backward(const mclip_ew_bwd_args* a, void* stream) {
 }
 
 // BatchNorm backward, second half: dgamma, dbeta, and the two means used by the apply pass
-__global__ void mclip_bn_bwd_finalize_kernel(const float* __restrict__ partials, int slots, int C, double count, int training, float* dgamma, float* dbeta,
-                                             int accumulate, float* c1, float* c2) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= C) return;
-  double s = 0.0, q = 0.0;
-  for (int k = 0; k < slots; ++k) { s += (double)partials[((size_t)k * 2 + 0) * C + c]; q += (double)partials[((size_t)k * 2 + 1) * C + c]; }
+__global__ void __launch_bounds__(BNF_CH * BNF_LANES) mclip_bn_bwd_finalize_kernel(const float* __restrict__ partials, int slots, int C, double count,
+                                                                                   int training, float* dgamma, float* dbeta, int accumulate, float* c1,
+                                                                                   float* c2) {
+  __shared__ double sm[2][BNF_LANES][BNF_CH];
+  const int c = blockIdx.x * BNF_CH + threadIdx.x % BNF_CH, lane = threadIdx.x / BNF_CH;
+  double s, q;
+  bn_reduce_slots(partials, slots, C, c, lane, s, q, sm);
+  if (lane != 0 || c >= C) return;
   if (dgamma) dgamma[c] = accumulate ? dgamma[c] + (float)q : (float)q;
   if (dbeta) dbeta[c] = accumulate ? dbeta[c] + (float)s : (float)s;
   c1[c] = training ? (float)(s / count) : 0.f;
@@ -475,7 +498,7 @@ __global__ void mclip_bn_bwd_finalize_kernel(const float* __restrict__ partials,
 extern "C" int mclip_bn_bwd_finalize(const float* partials, int slots, int c, long long count, int training, float* dgamma, float* dbeta, int accumulate,
                                      float* c1, float* c2, void* stream) {
   MCLIP_REQUIRE(partials && c1 && c2 && slots > 0 && count > 0, "mclip_bn_bwd_finalize: bad arguments");
-  mclip_bn_bwd_finalize_kernel<<<ceil_div(c, 128), 128, 0, (cudaStream_t)stream>>>(partials, slots, c, (double)count, training, dgamma, dbeta, accumulate, c1, c2);
+  mclip_bn_bwd_finalize_kernel<<<ceil_div(c, BNF_CH), BNF_CH * BNF_LANES, 0, (cudaStream_t)stream>>>(partials, slots, c, (double)count, training, dgamma, dbeta, accumulate, c1, c2);
   MCLIP_CHECK_LAUNCH();
   return MCLIP_OK;
 }

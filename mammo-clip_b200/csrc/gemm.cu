@@ -169,15 +169,15 @@ mclip_gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         uint8_t* sb = my_buf + (size_t)buf * GEMM_SLAB_BYTES;
         if (lane == 0) tma_store_wait_read1();     // the store issued two slabs ago (same buffer) has drained
         __syncwarp();
+        uint32_t r[64];
+        tmem_ld64(tmem_base + (uint32_t)as * 256u + (uint32_t)(s * 64) + ((uint32_t)(q * 32) << 16), r);
+        tmem_ld_wait();
 #pragma unroll
         for (int ch = 0; ch < 4; ++ch) {
-          if (s * 64 + ch * 16 >= p.block_n) break;          // warp-uniform
-          uint32_t r[16];
-          tmem_ld16(tmem_base + (uint32_t)as * 256u + (uint32_t)(s * 64 + ch * 16) + ((uint32_t)(q * 32) << 16), r);
-          tmem_ld_wait();
+          if (s * 64 + ch * 16 >= p.block_n) break;          // warp-uniform: columns past block_n hold no result
           float v[16];
 #pragma unroll
-          for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+          for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[ch * 16 + i]);
           const int cc = c0 + ch * 16;
           if (p.bias) {
 #pragma unroll
@@ -220,10 +220,21 @@ mclip_gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         if (p.stats) {
           // column sums over this warp's valid rows, read back from the swizzled slab (conflict-free)
           float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
-          for (int r2 = 0; r2 < nvalid; ++r2) {
-            uint32_t w = *reinterpret_cast<const uint32_t*>(sb + r2 * 128 + (((lane >> 2) ^ (r2 & 7)) << 4) + (lane & 3) * 4);
-            float a0 = bf16_lo(w), a1 = bf16_hi(w);
-            s0 += a0; s1 += a1; q0 = fmaf(a0, a0, q0); q1 = fmaf(a1, a1, q1);
+          const uint8_t* colp = sb + (lane & 3) * 4;
+          const int cq = lane >> 2;
+          if (nvalid == 32) {
+#pragma unroll
+            for (int r2 = 0; r2 < 32; ++r2) {
+              uint32_t w = *reinterpret_cast<const uint32_t*>(colp + r2 * 128 + ((cq ^ (r2 & 7)) << 4));
+              float a0 = bf16_lo(w), a1 = bf16_hi(w);
+              s0 += a0; s1 += a1; q0 = fmaf(a0, a0, q0); q1 = fmaf(a1, a1, q1);
+            }
+          } else {
+            for (int r2 = 0; r2 < nvalid; ++r2) {
+              uint32_t w = *reinterpret_cast<const uint32_t*>(colp + r2 * 128 + ((cq ^ (r2 & 7)) << 4));
+              float a0 = bf16_lo(w), a1 = bf16_hi(w);
+              s0 += a0; s1 += a1; q0 = fmaf(a0, a0, q0); q1 = fmaf(a1, a1, q1);
+            }
           }
           st_sum[si][0] += s0; st_sum[si][1] += s1; st_sq[si][0] += q0; st_sq[si][1] += q1;
         }
