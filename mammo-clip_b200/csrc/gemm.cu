@@ -15,6 +15,7 @@
 #include "common.cuh"
 #include "mclip_internal.h"
 #include <cudaTypedefs.h>
+#include <stdlib.h>
 
 #define GEMM_EPI_WARPS 8
 #define GEMM_THREADS (64 + 32 * GEMM_EPI_WARPS)
@@ -33,6 +34,9 @@ struct GemmDev {
   int act;
   float* stats;     // [(gridDim.x / n_blocks) * 4][2][N]
   const uint8_t* dropmask; float drop_scale;
+  int small_k;      // K <= 64 and shared B: B panel resident in smem, A tiles staged with cp.async by warp 0
+  const bf16* a_ptr; long long lda, a_bs;
+  int debug;        // MCLIP_GEMM_DEBUG bitmask (experiments only): 1 no stats, 2 no TMA store, 4 no TMEM load/convert
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -81,20 +85,25 @@ mclip_gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
                      const __grid_constant__ CUtensorMap tmD, const GemmDev p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  const uint32_t a_bytes = GEMM_BM * GEMM_BK * 2, b_bytes = (uint32_t)p.block_n * GEMM_BK * 2, stage_bytes = a_bytes + b_bytes;
-  uint8_t* dstage = smem + (size_t)p.stages * stage_bytes;
+  const uint32_t a_bytes = GEMM_BM * GEMM_BK * 2, b_bytes = (uint32_t)p.block_n * GEMM_BK * 2;
+  // normal mode: every stage holds an A and a B tile; small-K mode: stages hold A only, one resident B panel follows them
+  const uint32_t stage_bytes = p.small_k ? a_bytes : a_bytes + b_bytes;
+  uint8_t* bpanel = smem + (size_t)p.stages * stage_bytes;
+  uint8_t* dstage = bpanel + (p.small_k ? b_bytes : 0);
   uint64_t* bars = reinterpret_cast<uint64_t*>(dstage + GEMM_EPI_WARPS * 2 * GEMM_SLAB_BYTES);
   uint64_t* full = bars;
   uint64_t* empty = bars + p.stages;
   uint64_t* tfull = bars + 2 * p.stages;
   uint64_t* tempty = tfull + 2;
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tempty + 2);
+  uint64_t* bfull = tempty + 2;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bfull + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA); tma_prefetch_desc(&tmB); tma_prefetch_desc(&tmD);
     for (int s = 0; s < p.stages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
     for (int a = 0; a < 2; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], GEMM_EPI_WARPS); }
+    mbar_init(bfull, 1);
     fence_mbar_init();
   }
   if (warp == 1) { tmem_alloc(tmem_ptr, 512); tmem_relinquish(); }
@@ -108,7 +117,60 @@ mclip_gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
   const int mt0 = blockIdx.x / p.n_blocks, mt_step = gridDim.x / p.n_blocks;
   const int n0 = n_blk * p.block_n;
 
-  if (warp == 0) {
+  if (warp == 0 && p.small_k) {
+    // ---- small-K producer (whole warp): B panel once by TMA; A tiles by 16-byte cp.async into the 128B-swizzled K-major
+    //      layout (TMA would issue one 48..128-byte request per row, which costs more than the data itself) ----
+    if (lane == 0) {
+      mbar_expect_tx(bfull, b_bytes);
+      tma_load_3d(bpanel, &tmB, bfull, 0, n0, 0);
+    }
+    const int kch = (p.K * 2) >> 4;                       // valid 16-byte chunks per row (K % 8 == 0)
+    const int rch = ((p.K + 15) >> 4) * 2;                // chunks the MMAs read (K rounded up to 16)
+    for (int st = 0; st < p.stages; ++st)                 // zero the K padding once; cp.async never touches it again
+      for (int idx = lane; idx < GEMM_BM * (rch - kch); idx += 32) {
+        const int r = idx / (rch - kch), c = kch + idx % (rch - kch);
+        *reinterpret_cast<uint4*>(smem + (size_t)st * stage_bytes + r * 128 + ((c ^ (r & 7)) << 4)) = make_uint4(0u, 0u, 0u, 0u);
+      }
+    fence_proxy_async_smem();
+    __syncwarp();
+    constexpr int LOOK = 4;                               // tiles in flight behind the one being issued (stages >= LOOK + 2)
+    int it = 0;
+    for (int mt = mt0; mt < p.m_tiles_total; mt += mt_step, ++it) {
+      const int st = it % p.stages;
+      const uint32_t ph = (uint32_t)(it / p.stages) & 1u;
+      mbar_wait(&empty[st], ph ^ 1);
+      const int b = mt / p.m_blocks, m0 = (mt % p.m_blocks) * GEMM_BM;
+      const bf16* abase = p.a_ptr + (size_t)b * p.a_bs + (size_t)m0 * p.lda;
+      const uint32_t sdst = smem_u32(smem + (size_t)st * stage_bytes);
+      const int rows = min(GEMM_BM, p.M - m0);
+#pragma unroll
+      for (int rr = 0; rr < GEMM_BM / 32; ++rr) {          // lane owns rows lane, lane+32, ...: no index arithmetic per chunk
+        const int r = lane + rr * 32;
+        const uint32_t nbytes = r < rows ? 16u : 0u;      // rows past M are zero-filled
+        const bf16* src = abase + (size_t)(r < rows ? r : 0) * p.lda;
+        const uint32_t drow = sdst + r * 128;
+        for (int c = 0; c < kch; ++c)
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(drow + ((c ^ (r & 7)) << 4)), "l"(src + c * 8), "r"(nbytes) : "memory");
+      }
+      asm volatile("cp.async.commit_group;" ::: "memory");
+      if (it >= LOOK) {
+        asm volatile("cp.async.wait_group %0;" ::"n"(LOOK) : "memory");
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&full[(it - LOOK) % p.stages]);
+      }
+    }
+    // drain
+    for (int d = (it < LOOK ? it : LOOK); d > 0; --d) {
+      if (d == 4) asm volatile("cp.async.wait_group 3;" ::: "memory");
+      else if (d == 3) asm volatile("cp.async.wait_group 2;" ::: "memory");
+      else if (d == 2) asm volatile("cp.async.wait_group 1;" ::: "memory");
+      else asm volatile("cp.async.wait_group 0;" ::: "memory");
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&full[(it - d) % p.stages]);
+    }
+  } else if (warp == 0) {
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0;
       for (int mt = mt0; mt < p.m_tiles_total; mt += mt_step) {
@@ -126,6 +188,7 @@ mclip_gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
   } else if (warp == 1) {
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0; int as = 0; uint32_t aphase = 0;
+      if (p.small_k) mbar_wait(bfull, 0);
       for (int mt = mt0; mt < p.m_tiles_total; mt += mt_step) {
         mbar_wait(&tempty[as], aphase ^ 1);
         tc_fence_after();
@@ -133,7 +196,7 @@ mclip_gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         for (int kb = 0; kb < p.k_blocks; ++kb) {
           mbar_wait(&full[stage], phase);
           tc_fence_after();
-          const uint32_t sa = smem_u32(smem + (size_t)stage * stage_bytes), sb = sa + a_bytes;
+          const uint32_t sa = smem_u32(smem + (size_t)stage * stage_bytes), sb = p.small_k ? smem_u32(bpanel) : sa + a_bytes;
           const int krem = p.K - kb * GEMM_BK;
           const int nk = krem >= GEMM_BK ? 4 : (krem + 15) >> 4;
           for (int kk = 0; kk < nk; ++kk)
@@ -170,7 +233,7 @@ mclip_gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         if (lane == 0) tma_store_wait_read1();     // the store issued two slabs ago (same buffer) has drained
         __syncwarp();
         uint32_t r[64];
-        tmem_ld64(tmem_base + (uint32_t)as * 256u + (uint32_t)(s * 64) + ((uint32_t)(q * 32) << 16), r);
+        if (!(p.debug & 4)) tmem_ld64(tmem_base + (uint32_t)as * 256u + (uint32_t)(s * 64) + ((uint32_t)(q * 32) << 16), r);
         tmem_ld_wait();
 #pragma unroll
         for (int ch = 0; ch < 4; ++ch) {
@@ -216,7 +279,7 @@ mclip_gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         }
         fence_proxy_async_smem();
         __syncwarp();
-        if (lane == 0) { tma_store_3d(&tmD, sb, c0, m0 + q * 32, b); tma_store_commit(); }
+        if (lane == 0 && !(p.debug & 2)) { tma_store_3d(&tmD, sb, c0, m0 + q * 32, b); tma_store_commit(); }
         if (p.stats) {
           // column sums over this warp's valid rows, read back from the swizzled slab (conflict-free)
           float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
@@ -306,12 +369,17 @@ extern "C" int mclip_gemm_tn(const mclip_gemm_args* g, void* stream_) {
   p.idesc = umma_idesc_bf16(GEMM_BM, p.block_n, 0, 0);
   p.bias = g->bias; p.residual = (const bf16*)g->residual; p.res_ld = g->ldr; p.res_bs = g->r_batch_stride; p.act = g->act;
   p.stats = g->stats;
+  { const char* e = getenv("MCLIP_GEMM_DEBUG"); p.debug = e ? atoi(e) : 0; if (p.debug & 1) p.stats = nullptr; }
   p.dropmask = (const uint8_t*)g->dropmask; p.drop_scale = g->drop_scale;
   if (g->dropmask) MCLIP_REQUIRE(g->n % 16 == 0, "mclip_gemm_tn: dropout mask needs N %% 16 == 0");
-  const int stage_bytes = GEMM_BM * GEMM_BK * 2 + p.block_n * GEMM_BK * 2;
-  const int fixed = GEMM_EPI_WARPS * 2 * GEMM_SLAB_BYTES + 256 + 1024;
+  p.small_k = (p.k_blocks == 1 && !p.b_batched && g->lda % 8 == 0 && ((uintptr_t)g->a & 15) == 0) ? 1 : 0;
+  if (getenv("MCLIP_GEMM_NO_SMALLK")) p.small_k = 0;
+  p.a_ptr = (const bf16*)g->a; p.lda = g->lda; p.a_bs = g->a_batch_stride;
+  const int stage_bytes = p.small_k ? GEMM_BM * GEMM_BK * 2 : GEMM_BM * GEMM_BK * 2 + p.block_n * GEMM_BK * 2;
+  const int fixed = GEMM_EPI_WARPS * 2 * GEMM_SLAB_BYTES + 256 + 1024 + (p.small_k ? p.block_n * GEMM_BK * 2 : 0);
   p.stages = (GEMM_SMEM_LIMIT - fixed) / stage_bytes;
   if (p.stages > 8) p.stages = 8;
+  if (p.small_k) MCLIP_REQUIRE(p.stages >= 6, "mclip_gemm_tn: small-K mode needs 6 stages");   // always true for block_n <= 256
   MCLIP_REQUIRE(p.stages >= 2, "mclip_gemm_tn: tile does not fit in shared memory");
   const int smem = p.stages * stage_bytes + fixed;
   CUtensorMap tmA, tmB, tmD;
