@@ -40,6 +40,10 @@ void mclip_set_error(const char* fmt, ...);
 #define MCLIP_CHECK_LAUNCH() MCLIP_CHECK_CUDA(cudaGetLastError())
 
 int mclip_num_sms();   // cached SM count of the current device
+// cuTensorMapEncodeTiled through the runtime's driver entry point (no libcuda link dependency); bf16 tensors, dims[0] innermost,
+// strides in BYTES for dims 1..rank-1, zero fill out of bounds.  swizzle128 != 0 selects CU_TENSOR_MAP_SWIZZLE_128B.
+int mclip_tmap_encode_bf16(CUtensorMap* m, const void* ptr, int rank, const unsigned long long* dims, const unsigned long long* strides_bytes,
+                           const unsigned* box, int swizzle128);
 
 static inline int ceil_div(long long a, long long b) { return (int)((a + b - 1) / b); }
 
@@ -162,6 +166,14 @@ __device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* m
       "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
       : "memory");
 }
+__device__ __forceinline__ void tma_load_4d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(
+          smem_u32(smem_dst)),
+      "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
 __device__ __forceinline__ void tma_store_3d(const CUtensorMap* map, const void* smem_src, int c0, int c1, int c2) {
   asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(map),
                "r"(smem_u32(smem_src)), "r"(c0), "r"(c1), "r"(c2)

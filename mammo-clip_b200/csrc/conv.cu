@@ -60,58 +60,37 @@ __device__ __forceinline__ void dw_make_pixtab(uint16_t* pix, int rows, int cols
   for (int p = threadIdx.x; p < rows * cols; p += DW_THREADS) pix[p] = (uint16_t)(((p / cols) << 8) | (p % cols));
 }
 
-template <bool kTransform>
-__device__ __forceinline__ void dw_load_tile(bf16* __restrict__ tile, const uint16_t* __restrict__ pix, const bf16* __restrict__ img, int y0, int x0,
-                                             int npix, int H, int W, int C, int c0, const float* sc, const float* sh, int act) {
-  // img: base of image n.  Offsets inside one image fit in 32 bits.
-  const int v = threadIdx.x & 7;                 // 8-channel vector inside the 64-channel chunk (fixed per thread)
+// In-place BN-affine + swish of a TMA-staged tile [npix][64ch] (bf16) by the DW_THREADS compute threads.
+// Pixels outside the image were zero-filled by TMA and must STAY zero (ZeroPad2d acts on the activated tensor).
+__device__ __forceinline__ void dw_transform_tile(bf16* __restrict__ tile, const uint16_t* __restrict__ pix, int y0, int x0, int rows, int cols,
+                                                  int H, int W, int C, int c0, const float* sc, const float* sh, int act) {
+  const int v = threadIdx.x & 7;
   const int c = c0 + v * 8;
-  const bool cvalid = c < C;
+  if (c >= C) return;                                    // channels past C: zero-filled, never stored
+  const float f = act ? 0.5f : 1.0f;
   float2 a[4], b[4];
-  if (kTransform && cvalid) {
-    const float f = act ? 0.5f : 1.0f;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    a[i] = make_float2(f * sc[c + 2 * i], f * sc[c + 2 * i + 1]);
+    b[i] = make_float2(f * sh[c + 2 * i], f * sh[c + 2 * i + 1]);
+  }
+  const int npix = rows * cols;
+  const bool interior = y0 >= 0 && x0 >= 0 && y0 + rows <= H && x0 + cols <= W;
+  bf16* base = tile + v * 8;
+  for (int p = threadIdx.x >> 3; p < npix; p += DW_THREADS / 8) {
+    if (!interior) {
+      const uint32_t pr = pix[p];
+      const int y = y0 + (int)(pr >> 8), x = x0 + (int)(pr & 255u);
+      if ((unsigned)y >= (unsigned)H || (unsigned)x >= (unsigned)W) continue;
+    }
+    bf16x8 o = *reinterpret_cast<const bf16x8*>(base + p * DW_CCH);
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-      a[i] = make_float2(f * sc[c + 2 * i], f * sc[c + 2 * i + 1]);
-      b[i] = make_float2(f * sh[c + 2 * i], f * sh[c + 2 * i + 1]);
+      float2 h = ffma2r(bf2_to_f2(o.w[i]), a[i], b[i]);
+      if (act) h = ffma2r(h, make_float2(fast_tanh(h.x), fast_tanh(h.y)), h);
+      o.w[i] = pack_bf16(h.x, h.y);
     }
-  }
-  constexpr int PSTEP = DW_THREADS / 8, UNR = 4;
-  const bf16* src = img + c;
-  bf16* dst = tile + v * 8;
-  for (int p0 = threadIdx.x >> 3; p0 < npix; p0 += PSTEP * UNR) {
-    bf16x8 val[UNR];
-    bool inb[UNR];
-#pragma unroll
-    for (int u = 0; u < UNR; ++u) {
-      const int p = p0 + u * PSTEP;
-      val[u].w[0] = val[u].w[1] = val[u].w[2] = val[u].w[3] = 0u;
-      inb[u] = false;
-      if (p < npix) {
-        const uint32_t pr = pix[p];
-        const int y = y0 + (int)(pr >> 8), x = x0 + (int)(pr & 255u);
-        inb[u] = cvalid && (unsigned)y < (unsigned)H && (unsigned)x < (unsigned)W;
-        if (inb[u]) val[u] = ldg_bf16x8(src + (unsigned)((y * W + x) * C));
-      }
-    }
-#pragma unroll
-    for (int u = 0; u < UNR; ++u) {
-      const int p = p0 + u * PSTEP;
-      if (p >= npix) break;
-      bf16x8 o = val[u];
-      if (kTransform && inb[u]) {
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          float2 h = ffma2r(bf2_to_f2(o.w[i]), a[i], b[i]);
-          if (act) {
-            const float2 th = make_float2(fast_tanh(h.x), fast_tanh(h.y));
-            h = ffma2r(h, th, h);
-          }
-          o.w[i] = pack_bf16(h.x, h.y);
-        }
-      }
-      *reinterpret_cast<bf16x8*>(dst + p * DW_CCH) = o;
-    }
+    *reinterpret_cast<bf16x8*>(base + p * DW_CCH) = o;
   }
 }
 
@@ -147,36 +126,67 @@ __device__ __forceinline__ void dw_patch(const bf16* __restrict__ tile, int IW, 
 // =====================================================================================================
 // forward
 // =====================================================================================================
-template <int K, int S, int TH, int TW>
-__global__ void __launch_bounds__(DW_THREADS, 4) mclip_dwconv_fwd_kernel(const DwDev p) {
+// The halo tile of the NEXT work item is fetched by TMA (issued by one thread as soon as every warp has released the other
+// stage) while the current one is transformed (BN+swish in place) and convolved.  TMA zero-fills the static padding and
+// the channel tail, so the kernel has no load address arithmetic at all.
+template <int K, int S, int TH, int TW, int DW_STAGES>
+__global__ void __launch_bounds__(DW_THREADS, 4) mclip_dwconv_fwd_kernel(const __grid_constant__ CUtensorMap tmIn, const DwDev p) {
   constexpr int IH = (TH - 1) * S + K, IW = (TW - 1) * S + K;
   constexpr int PRO = (S == 1 && K == 3) ? 4 : 2;                 // output rows per warp patch
-  extern __shared__ __align__(16) uint8_t smem_dw[];
-  bf16* tile = reinterpret_cast<bf16*>(smem_dw);
-  uint16_t* pix = reinterpret_cast<uint16_t*>(tile + (size_t)IH * IW * DW_CCH);
+  constexpr uint32_t TILE_BYTES = IH * IW * DW_CCH * 2;
+  extern __shared__ __align__(128) uint8_t smem_dw[];
+  uint8_t* sbase = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_dw) + 127) & ~uintptr_t(127));
+  uint16_t* pix = reinterpret_cast<uint16_t*>(sbase + DW_STAGES * TILE_BYTES);
   __shared__ float red[DW_WARPS][4][32];
+  __shared__ __align__(8) uint64_t full[DW_STAGES], empty[DW_STAGES];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int chunk = blockIdx.x % p.n_chunks, slot = blockIdx.x / p.n_chunks;
-  const int c0 = chunk * DW_CCH, c = c0 + lane * 2;
-  const bool cvalid = c < p.C;
+  const int c0 = chunk * DW_CCH;
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tmIn);
+    for (int s = 0; s < DW_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], DW_WARPS); }
+    fence_mbar_init();
+  }
   dw_make_pixtab(pix, IH, IW);
+  __syncthreads();
+  const int tiles_per_img = p.tiles_x * p.tiles_y;
+  const int total_tiles = p.N * tiles_per_img;
+  const int my_tiles = total_tiles > slot ? (total_tiles - slot + p.slots - 1) / p.slots : 0;
+  auto issue = [&](int it) {      // thread 0 only: fetch work item `it` into its stage once all warps released it
+    const int st = it % DW_STAGES;
+    const uint32_t ph = (uint32_t)(it / DW_STAGES) & 1u;
+    const int t = slot + it * p.slots;
+    const int n = t / tiles_per_img, tr = t % tiles_per_img;
+    const int oy0 = (tr / p.tiles_x) * TH, ox0 = (tr % p.tiles_x) * TW;
+    mbar_wait(&empty[st], ph ^ 1);
+    mbar_expect_tx(&full[st], TILE_BYTES);
+    tma_load_4d(sbase + (size_t)st * TILE_BYTES, &tmIn, &full[st], c0, ox0 * S - p.pl, oy0 * S - p.pt, n);
+  };
+  if (threadIdx.x == 0)
+    for (int i = 0; i < DW_STAGES - 1 && i < my_tiles; ++i) issue(i);
+  const int c = c0 + lane * 2;
+  const bool cvalid = c < p.C;
   float2 w[K * K];
 #pragma unroll
   for (int t = 0; t < K * K; ++t) w[t] = cvalid ? make_float2(p.w[(size_t)c * K * K + t], p.w[(size_t)(c + 1) * K * K + t]) : make_float2(0.f, 0.f);
   float2 s_sum = make_float2(0.f, 0.f), s_sq = make_float2(0.f, 0.f);
   const float2 one = make_float2(1.f, 1.f);
-  const int tiles_per_img = p.tiles_x * p.tiles_y;
-  const int total_tiles = p.N * tiles_per_img;
   const int cw = p.C >> 1;                                         // channel pairs per pixel (row stride in 32-bit words)
-  for (int t = slot; t < total_tiles; t += p.slots) {
+  int it = 0;
+  for (int t = slot; t < total_tiles; t += p.slots, ++it) {
+    const int st = it % DW_STAGES;
+    const uint32_t ph = (uint32_t)(it / DW_STAGES) & 1u;
     const int n = t / tiles_per_img, tr = t % tiles_per_img;
     const int oy0 = (tr / p.tiles_x) * TH, ox0 = (tr % p.tiles_x) * TW;
-    const bf16* img = p.in + (size_t)n * p.H * p.W * p.C;
+    bf16* tile = reinterpret_cast<bf16*>(sbase + (size_t)st * TILE_BYTES);
     uint32_t* outw = reinterpret_cast<uint32_t*>(p.out + (size_t)n * p.Ho * p.Wo * p.C) + (c >> 1);
-    __syncthreads();
-    if (p.scale) dw_load_tile<true>(tile, pix, img, oy0 * S - p.pt, ox0 * S - p.pl, IH * IW, p.H, p.W, p.C, c0, p.scale, p.shift, p.act);
-    else dw_load_tile<false>(tile, pix, img, oy0 * S - p.pt, ox0 * S - p.pl, IH * IW, p.H, p.W, p.C, c0, nullptr, nullptr, 0);
-    __syncthreads();
+    if (threadIdx.x == 0 && it + DW_STAGES - 1 < my_tiles) issue(it + DW_STAGES - 1);
+    __syncwarp();
+    mbar_wait(&full[st], ph);
+    if (p.scale) {
+      dw_transform_tile(tile, pix, oy0 * S - p.pt, ox0 * S - p.pl, IH, IW, p.H, p.W, p.C, c0, p.scale, p.shift, p.act);
+      named_bar_sync(1, DW_THREADS);
+    }
     for (int pa = warp; pa < (TH / PRO) * (TW / 4); pa += DW_WARPS) {
       const int py = (pa / (TW / 4)) * PRO, px = (pa % (TW / 4)) * 4;
       const int y0 = oy0 + py, x0 = ox0 + px;
@@ -185,42 +195,34 @@ __global__ void __launch_bounds__(DW_THREADS, 4) mclip_dwconv_fwd_kernel(const D
       dw_patch<K, S, PRO>(tile, IW, py * S, px * S, lane, w, acc);
       if (!cvalid) continue;
       uint32_t* op = outw + (y0 * p.Wo + x0) * cw;
-      if (y0 + PRO <= p.Ho && x0 + 4 <= p.Wo) {                    // interior patch: no per-pixel checks
+      const bool inner = y0 + PRO <= p.Ho && x0 + 4 <= p.Wo;       // interior patch: no per-pixel checks
 #pragma unroll
-        for (int oy = 0; oy < PRO; ++oy)
+      for (int oy = 0; oy < PRO; ++oy)
 #pragma unroll
-          for (int ox = 0; ox < 4; ++ox) {
+        for (int ox = 0; ox < 4; ++ox) {
+          if (inner || (y0 + oy < p.Ho && x0 + ox < p.Wo)) {
             const uint32_t pk = pack_bf16(acc[oy][ox].x, acc[oy][ox].y);
             op[(oy * p.Wo + ox) * cw] = pk;
             const float2 a = bf2_to_f2(pk);
             ffma2(s_sum, a, one);
             ffma2(s_sq, a, a);
           }
-      } else {
-#pragma unroll
-        for (int oy = 0; oy < PRO; ++oy)
-#pragma unroll
-          for (int ox = 0; ox < 4; ++ox) {
-            if (y0 + oy < p.Ho && x0 + ox < p.Wo) {
-              const uint32_t pk = pack_bf16(acc[oy][ox].x, acc[oy][ox].y);
-              op[(oy * p.Wo + ox) * cw] = pk;
-              const float2 a = bf2_to_f2(pk);
-              ffma2(s_sum, a, one);
-              ffma2(s_sq, a, a);
-            }
-          }
-      }
+        }
     }
+    // this warp is done with the stage (generic-proxy writes of the transform must be ordered before the next TMA write)
+    fence_proxy_async_smem();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&empty[st]);
   }
   if (p.stats) {
     red[warp][0][lane] = s_sum.x; red[warp][1][lane] = s_sum.y; red[warp][2][lane] = s_sq.x; red[warp][3][lane] = s_sq.y;
-    __syncthreads();
+    named_bar_sync(1, DW_THREADS);
     if (warp == 0 && cvalid) {
       float a = 0.f, b = 0.f, cc = 0.f, d = 0.f;
 #pragma unroll
       for (int w2 = 0; w2 < DW_WARPS; ++w2) { a += red[w2][0][lane]; b += red[w2][1][lane]; cc += red[w2][2][lane]; d += red[w2][3][lane]; }
-      float* st = p.stats + (size_t)slot * 2 * p.C;
-      st[c] = a; st[c + 1] = b; st[p.C + c] = cc; st[p.C + c + 1] = d;
+      float* stp = p.stats + (size_t)slot * 2 * p.C;
+      stp[c] = a; stp[c + 1] = b; stp[p.C + c] = cc; stp[p.C + c + 1] = d;
     }
   }
 }
@@ -233,28 +235,58 @@ __global__ void __launch_bounds__(DW_THREADS, 4) mclip_dwconv_fwd_kernel(const D
 //   gtile : dY window feeding the owned inputs; it contains the owned outputs' dY as a sub-window
 // Per 2x4 patch a warp accumulates dW (registers, for the whole kernel) and computes the data gradient as a
 // register-window correlation of gtile with the flipped kernel (stride 1) or per parity class (stride 2).
-template <int K, int S, int TH, int TW>
-__global__ void __launch_bounds__(DW_THREADS, (K == 3) ? 4 : 3) mclip_dwconv_bwd_kernel(const DwDev p) {
+template <int K, int S, int TH, int TW, int DW_STAGES>
+__global__ void __launch_bounds__(DW_THREADS, 3)
+mclip_dwconv_bwd_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constant__ CUtensorMap tmDy, const DwDev p) {
   constexpr int IH = (TH - 1) * S + K, IW = (TW - 1) * S + K;     // activation window (wgrad)
   constexpr int GH = (S == 1) ? TH + K - 1 : TH + (K + 1) / 2;    // dY window (dgrad)
   constexpr int GW = (S == 1) ? TW + K - 1 : TW + (K + 1) / 2;
-  extern __shared__ __align__(16) uint8_t smem_dw[];
-  bf16* atile = reinterpret_cast<bf16*>(smem_dw);                                  // [IH*IW][64]
-  bf16* gtile = atile + (size_t)IH * IW * DW_CCH;                                  // [GH*GW][64]
-  float* wsm = reinterpret_cast<float*>(gtile + (size_t)GH * GW * DW_CCH);         // [K*K][64] weights
+  constexpr uint32_t A_BYTES = IH * IW * DW_CCH * 2, G_BYTES = GH * GW * DW_CCH * 2, STAGE_BYTES = A_BYTES + G_BYTES;
+  extern __shared__ __align__(128) uint8_t smem_dw[];
+  uint8_t* sbase = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_dw) + 127) & ~uintptr_t(127));
+  float* wsm = reinterpret_cast<float*>(sbase + DW_STAGES * STAGE_BYTES);          // [K*K][64] weights
   uint16_t* apix = reinterpret_cast<uint16_t*>(wsm + K * K * DW_CCH);
-  uint16_t* gpix = apix + IH * IW;
   __shared__ float red[DW_WARPS][4][32];
+  __shared__ __align__(8) uint64_t full[DW_STAGES], empty[DW_STAGES];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int chunk = blockIdx.x % p.n_chunks, slot = blockIdx.x / p.n_chunks;
   const int c0 = chunk * DW_CCH, c = c0 + lane * 2;
   const bool cvalid = c < p.C;
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tmIn); tma_prefetch_desc(&tmDy);
+    for (int s = 0; s < DW_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], DW_WARPS); }
+    fence_mbar_init();
+  }
   for (int i = threadIdx.x; i < K * K * DW_CCH; i += DW_THREADS) {
     const int t = i / DW_CCH, ch = i % DW_CCH;
     wsm[i] = (c0 + ch < p.C) ? p.w[(size_t)(c0 + ch) * K * K + t] : 0.f;
   }
   dw_make_pixtab(apix, IH, IW);
-  dw_make_pixtab(gpix, GH, GW);
+  __syncthreads();
+  const int tiles_per_img = p.tiles_x * p.tiles_y;
+  const int total_tiles = p.N * tiles_per_img;
+  const int my_tiles = total_tiles > slot ? (total_tiles - slot + p.slots - 1) / p.slots : 0;
+  auto tile_origin = [&](int t, int& n, int& oy0, int& ox0, int& gy0, int& gx0) {
+    n = t / tiles_per_img;
+    const int tr = t % tiles_per_img;
+    oy0 = (tr / p.tiles_x) * TH; ox0 = (tr % p.tiles_x) * TW;
+    const int gnum_y = oy0 * S + p.pt - (K - 1), gnum_x = ox0 * S + p.pl - (K - 1);
+    gy0 = (S == 1) ? gnum_y : (gnum_y >= 0 ? (gnum_y + 1) / 2 : -((-gnum_y) / 2));   // ceil(gnum / S)
+    gx0 = (S == 1) ? gnum_x : (gnum_x >= 0 ? (gnum_x + 1) / 2 : -((-gnum_x) / 2));
+  };
+  auto issue = [&](int it) {      // thread 0 only
+    const int st = it % DW_STAGES;
+    const uint32_t ph = (uint32_t)(it / DW_STAGES) & 1u;
+    int n, oy0, ox0, gy0, gx0;
+    tile_origin(slot + it * p.slots, n, oy0, ox0, gy0, gx0);
+    mbar_wait(&empty[st], ph ^ 1);
+    mbar_expect_tx(&full[st], STAGE_BYTES);
+    uint8_t* dst = sbase + (size_t)st * STAGE_BYTES;
+    tma_load_4d(dst, &tmIn, &full[st], c0, ox0 * S - p.pl, oy0 * S - p.pt, n);
+    tma_load_4d(dst + A_BYTES, &tmDy, &full[st], c0, gx0, gy0, n);
+  };
+  if (threadIdx.x == 0)
+    for (int i = 0; i < (DW_STAGES > 1 ? DW_STAGES - 1 : 1) && i < my_tiles; ++i) issue(i);
   float2 ab = make_float2(1.f, 1.f), bb = make_float2(0.f, 0.f), mu = make_float2(0.f, 0.f), is = make_float2(1.f, 1.f);
   if (p.scale && cvalid) { ab = make_float2(p.scale[c], p.scale[c + 1]); bb = make_float2(p.shift[c], p.shift[c + 1]); }
   if (p.bn_part && cvalid) { mu = make_float2(p.mean[c], p.mean[c + 1]); is = make_float2(p.invstd[c], p.invstd[c + 1]); }
@@ -262,30 +294,30 @@ __global__ void __launch_bounds__(DW_THREADS, (K == 3) ? 4 : 3) mclip_dwconv_bwd
   float2 dw[K * K];
 #pragma unroll
   for (int q = 0; q < K * K; ++q) dw[q] = make_float2(0.f, 0.f);
-  __syncthreads();
   float2 wf[(S == 1) ? K * K : 1];                                 // flipped kernel (stride-1 data gradient)
   if constexpr (S == 1) {
 #pragma unroll
     for (int q = 0; q < K * K; ++q) wf[q] = *reinterpret_cast<const float2*>(wsm + (K * K - 1 - q) * DW_CCH + lane * 2);
   }
   const int cw = p.C >> 1;
-  const int tiles_per_img = p.tiles_x * p.tiles_y;
-  const int total_tiles = p.N * tiles_per_img;
-  for (int t = slot; t < total_tiles; t += p.slots) {
-    const int n = t / tiles_per_img, tr = t % tiles_per_img;
-    const int oy0 = (tr / p.tiles_x) * TH, ox0 = (tr % p.tiles_x) * TW;
+  int it = 0;
+  for (int t = slot; t < total_tiles; t += p.slots, ++it) {
+    const int st = it % DW_STAGES;
+    const uint32_t ph = (uint32_t)(it / DW_STAGES) & 1u;
+    int n, oy0, ox0, gy0, gx0;
+    tile_origin(t, n, oy0, ox0, gy0, gx0);
     const int iy0 = oy0 * S, ix0 = ox0 * S;                        // first owned input pixel
-    const int gnum_y = iy0 + p.pt - (K - 1), gnum_x = ix0 + p.pl - (K - 1);
-    const int gy0 = (S == 1) ? gnum_y : (gnum_y >= 0 ? (gnum_y + 1) / 2 : -((-gnum_y) / 2));   // ceil(gnum / S)
-    const int gx0 = (S == 1) ? gnum_x : (gnum_x >= 0 ? (gnum_x + 1) / 2 : -((-gnum_x) / 2));
-    const bf16* img = p.in + (size_t)n * p.H * p.W * p.C;
-    const uint32_t* inw = reinterpret_cast<const uint32_t*>(img) + (c >> 1);
+    bf16* atile = reinterpret_cast<bf16*>(sbase + (size_t)st * STAGE_BYTES);
+    bf16* gtile = reinterpret_cast<bf16*>(sbase + (size_t)st * STAGE_BYTES + A_BYTES);
+    const uint32_t* inw = reinterpret_cast<const uint32_t*>(p.in + (size_t)n * p.H * p.W * p.C) + (c >> 1);
     uint32_t* dxw = reinterpret_cast<uint32_t*>(p.dx + (size_t)n * p.H * p.W * p.C) + (c >> 1);
-    __syncthreads();
-    if (p.scale) dw_load_tile<true>(atile, apix, img, iy0 - p.pt, ix0 - p.pl, IH * IW, p.H, p.W, p.C, c0, p.scale, p.shift, p.act);
-    else dw_load_tile<false>(atile, apix, img, iy0 - p.pt, ix0 - p.pl, IH * IW, p.H, p.W, p.C, c0, nullptr, nullptr, 0);
-    dw_load_tile<false>(gtile, gpix, p.dy + (size_t)n * p.Ho * p.Wo * p.C, gy0, gx0, GH * GW, p.Ho, p.Wo, p.C, c0, nullptr, nullptr, 0);
-    __syncthreads();
+    if (DW_STAGES > 1 && threadIdx.x == 0 && it + DW_STAGES - 1 < my_tiles) issue(it + DW_STAGES - 1);
+    __syncwarp();
+    mbar_wait(&full[st], ph);
+    if (p.scale) {
+      dw_transform_tile(atile, apix, iy0 - p.pt, ix0 - p.pl, IH, IW, p.H, p.W, p.C, c0, p.scale, p.shift, p.act);
+      named_bar_sync(1, DW_THREADS);
+    }
 
     // dv = dA*swish'(a*y+b) (y = pre-BN input), BN-backward partials, store
     auto finish = [&](uint32_t yu, int off, float2 d) {
@@ -406,14 +438,18 @@ __global__ void __launch_bounds__(DW_THREADS, (K == 3) ? 4 : 3) mclip_dwconv_bwd
           if (xb + 2 * j < p.W) finish(yu[j], off0 + 2 * j * cw, acc[j]);
       }
     }
+    fence_proxy_async_smem();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&empty[st]);
+    if (DW_STAGES == 1 && threadIdx.x == 0 && it + 1 < my_tiles) issue(it + 1);
   }
-  // ---- flush partials ----
-  __syncthreads();
-  float* wred = reinterpret_cast<float*>(smem_dw);                 // reuse the tiles: [warps][K*K][64]
+  // ---- flush partials (all TMA loads have been consumed: the stage buffers are free) ----
+  named_bar_sync(1, DW_THREADS);
+  float* wred = reinterpret_cast<float*>(sbase);                   // reuse the tiles: [warps][K*K][64]
 #pragma unroll
   for (int q = 0; q < K * K; ++q) *reinterpret_cast<float2*>(wred + ((size_t)warp * K * K + q) * DW_CCH + lane * 2) = dw[q];
   red[warp][0][lane] = bs.x; red[warp][1][lane] = bs.y; red[warp][2][lane] = bq.x; red[warp][3][lane] = bq.y;
-  __syncthreads();
+  named_bar_sync(1, DW_THREADS);
   for (int i = threadIdx.x; i < K * K * DW_CCH; i += DW_THREADS) {
     const int t = i / DW_CCH, ch = i % DW_CCH;
     if (c0 + ch < p.C) {
@@ -448,9 +484,11 @@ __global__ void mclip_dw_wgrad_reduce_kernel(const float* __restrict__ part, flo
 // ------------------------------------------------------------------------------------------------
 template <int K, int S>
 struct DwCfg {
-  static constexpr int TH = (S == 1) ? 16 : 8;      // forward tile (outputs)
+  static constexpr int TH = 8;                      // forward tile (outputs)
   static constexpr int TW = 16;
-  static constexpr int BTH = (S == 1) ? 8 : 4;   // backward tile height
+  static constexpr int BTH = (S == 1) ? 8 : 4;      // backward tile height
+  static constexpr int FST = 2;                     // TMA stages, forward
+  static constexpr int BST = (K == 3) ? 2 : 1;      // backward: two staged tensors; k5 keeps one stage for occupancy
 };
 
 static int dw_slots(int n_chunks, int total_tiles, int per_sm) {
@@ -460,18 +498,29 @@ static int dw_slots(int n_chunks, int total_tiles, int per_sm) {
   return s;
 }
 
+// 4-D tensor map over an NHWC bf16 tensor: dims {C, W, H, N}, box {64 channels, box_w, box_h, 1}, no swizzle.
+static int dw_tmap(CUtensorMap* m, const void* ptr, int N, int H, int W, int C, int box_w, int box_h) {
+  const unsigned long long dims[4] = {(unsigned long long)C, (unsigned long long)W, (unsigned long long)H, (unsigned long long)N};
+  const unsigned long long strides[3] = {(unsigned long long)C * 2, (unsigned long long)W * C * 2, (unsigned long long)H * W * C * 2};
+  const unsigned box[4] = {DW_CCH, (unsigned)box_w, (unsigned)box_h, 1};
+  return mclip_tmap_encode_bf16(m, ptr, 4, dims, strides, box, 0);
+}
+
 template <int K, int S>
 static int dw_launch_fwd(DwDev& p, cudaStream_t stream, int slots_given) {
   constexpr int TH = DwCfg<K, S>::TH, TW = DwCfg<K, S>::TW;
   constexpr int IH = (TH - 1) * S + K, IW = (TW - 1) * S + K;
-  const int smem = IH * IW * DW_CCH * 2 + IH * IW * 2 + 16;
+  const int smem = DwCfg<K, S>::FST * IH * IW * DW_CCH * 2 + IH * IW * 2 + 256;
   p.tiles_x = ceil_div(p.Wo, TW); p.tiles_y = ceil_div(p.Ho, TH);
   p.n_chunks = ceil_div(p.C, DW_CCH);
   p.slots = slots_given;
-  auto kern = mclip_dwconv_fwd_kernel<K, S, TH, TW>;
+  CUtensorMap tm;
+  int rc = dw_tmap(&tm, p.in, p.N, p.H, p.W, p.C, IW, IH);
+  if (rc) return rc;
+  auto kern = mclip_dwconv_fwd_kernel<K, S, TH, TW, DwCfg<K, S>::FST>;
   static bool attr = false;
   if (!attr) { MCLIP_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); attr = true; }
-  kern<<<p.n_chunks * p.slots, DW_THREADS, smem, stream>>>(p);
+  kern<<<p.n_chunks * p.slots, DW_THREADS, smem, stream>>>(tm, p);
   MCLIP_CHECK_LAUNCH();
   return MCLIP_OK;
 }
@@ -481,33 +530,67 @@ static int dw_launch_bwd(DwDev& p, cudaStream_t stream, int slots_given) {
   constexpr int TH = DwCfg<K, S>::BTH, TW = DwCfg<K, S>::TW;
   constexpr int IH = (TH - 1) * S + K, IW = (TW - 1) * S + K;
   constexpr int GH = (S == 1) ? TH + K - 1 : TH + (K + 1) / 2, GW = (S == 1) ? TW + K - 1 : TW + (K + 1) / 2;
-  int smem = (IH * IW + GH * GW) * DW_CCH * 2 + K * K * DW_CCH * 4 + (IH * IW + GH * GW) * 2 + 16;
-  const int red_bytes = DW_WARPS * K * K * DW_CCH * 4;                // the final dW reduction reuses the tiles
+  int smem = DwCfg<K, S>::BST * (IH * IW + GH * GW) * DW_CCH * 2 + K * K * DW_CCH * 4 + IH * IW * 2 + 256;
+  const int red_bytes = DW_WARPS * K * K * DW_CCH * 4 + 256;          // the final dW reduction reuses the stage buffers
   if (smem < red_bytes) smem = red_bytes;
   // the tile grid must cover every OUTPUT pixel (weight gradient) and every INPUT pixel (data gradient): with the
   // reference's static pads, S*Ho can be smaller than H (e.g. H=33, k3 s2 pads (0,1) -> Ho=16 but input row 32 is read)
   p.tiles_x = ceil_div(max(p.Wo, ceil_div(p.W, S)), TW); p.tiles_y = ceil_div(max(p.Ho, ceil_div(p.H, S)), TH);
   p.n_chunks = ceil_div(p.C, DW_CCH);
   p.slots = slots_given;
-  auto kern = mclip_dwconv_bwd_kernel<K, S, TH, TW>;
+  CUtensorMap tmIn, tmDy;
+  int rc = dw_tmap(&tmIn, p.in, p.N, p.H, p.W, p.C, IW, IH);
+  if (rc) return rc;
+  if ((rc = dw_tmap(&tmDy, p.dy, p.N, p.Ho, p.Wo, p.C, GW, GH))) return rc;
+  auto kern = mclip_dwconv_bwd_kernel<K, S, TH, TW, DwCfg<K, S>::BST>;
   static bool attr = false;
   if (!attr) { MCLIP_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); attr = true; }
-  kern<<<p.n_chunks * p.slots, DW_THREADS, smem, stream>>>(p);
+  kern<<<p.n_chunks * p.slots, DW_THREADS, smem, stream>>>(tmIn, tmDy, p);
   MCLIP_CHECK_LAUNCH();
   return MCLIP_OK;
 }
 
 static int dw_tiles(const mclip_dwconv_args* a, bool bwd) {
-  int TH = a->stride == 1 ? 16 : 8, TW = 16;
+  int TH = 8, TW = 16;
   if (!bwd) return a->n * ceil_div(a->ho, TH) * ceil_div(a->wo, TW);
   TH = a->stride == 1 ? 8 : 4;
   const int hy = max(a->ho, ceil_div(a->h, a->stride)), wx = max(a->wo, ceil_div(a->w, a->stride));
   return a->n * ceil_div(hy, TH) * ceil_div(wx, TW);
 }
 
+template <int K, int S>
+static int dw_blocks_per_sm(bool bwd) {
+  static int cache[2] = {0, 0};
+  if (cache[bwd]) return cache[bwd];
+  int n = 0, smem;
+  if (!bwd) {
+    constexpr int TH = DwCfg<K, S>::TH, TW = DwCfg<K, S>::TW, IH = (TH - 1) * S + K, IW = (TW - 1) * S + K;
+    smem = DwCfg<K, S>::FST * IH * IW * DW_CCH * 2 + IH * IW * 2 + 256;
+    auto kern = mclip_dwconv_fwd_kernel<K, S, TH, TW, DwCfg<K, S>::FST>;
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kern, DW_THREADS, smem);
+  } else {
+    constexpr int TH = DwCfg<K, S>::BTH, TW = DwCfg<K, S>::TW, IH = (TH - 1) * S + K, IW = (TW - 1) * S + K;
+    constexpr int GH = (S == 1) ? TH + K - 1 : TH + (K + 1) / 2, GW = (S == 1) ? TW + K - 1 : TW + (K + 1) / 2;
+    smem = DwCfg<K, S>::BST * (IH * IW + GH * GW) * DW_CCH * 2 + K * K * DW_CCH * 4 + IH * IW * 2 + 256;
+    auto kern = mclip_dwconv_bwd_kernel<K, S, TH, TW, DwCfg<K, S>::BST>;
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kern, DW_THREADS, smem);
+  }
+  if (n < 1) n = 1;
+  cache[bwd] = n;
+  return n;
+}
+
 extern "C" int mclip_dwconv_slots(const mclip_dwconv_args* a, int backward) {
   if (!a || a->c <= 0) return -1;
-  return dw_slots(ceil_div(a->c, DW_CCH), dw_tiles(a, backward != 0), backward ? 3 : 4);
+  const bool b = backward != 0;
+  int per_sm;
+  if (a->k == 3 && a->stride == 1) per_sm = dw_blocks_per_sm<3, 1>(b);
+  else if (a->k == 3) per_sm = dw_blocks_per_sm<3, 2>(b);
+  else if (a->stride == 1) per_sm = dw_blocks_per_sm<5, 1>(b);
+  else per_sm = dw_blocks_per_sm<5, 2>(b);
+  return dw_slots(ceil_div(a->c, DW_CCH), dw_tiles(a, b), per_sm);
 }
 
 static int dw_fill(const mclip_dwconv_args* a, DwDev& p) {

@@ -38,3 +38,29 @@ extern "C" int mclip_device_check(void) {
   }
   return MCLIP_OK;
 }
+
+#include <cudaTypedefs.h>
+int mclip_tmap_encode_bf16(CUtensorMap* m, const void* ptr, int rank, const unsigned long long* dims, const unsigned long long* strides_bytes,
+                           const unsigned* box, int swizzle128) {
+  static PFN_cuTensorMapEncodeTiled_v12000 enc = nullptr;
+  if (!enc) {
+    void* fp = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fp, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+      enc = (PFN_cuTensorMapEncodeTiled_v12000)fp;
+  }
+  if (!enc) { mclip_set_error("cuTensorMapEncodeTiled not available from the driver"); return MCLIP_ERR_CUDA; }
+  if ((uintptr_t)ptr & 15) { mclip_set_error("TMA operand %p is not 16-byte aligned", ptr); return MCLIP_ERR_INVALID; }
+  cuuint64_t d[5], st[4];
+  cuuint32_t b[5], es[5];
+  for (int i = 0; i < rank; ++i) { d[i] = dims[i]; b[i] = box[i]; es[i] = 1; }
+  for (int i = 0; i + 1 < rank; ++i) {
+    st[i] = strides_bytes[i];
+    if (st[i] % 16) { mclip_set_error("TMA stride %llu is not a multiple of 16 bytes", strides_bytes[i]); return MCLIP_ERR_INVALID; }
+  }
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(ptr), d, st, b, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { mclip_set_error("cuTensorMapEncodeTiled failed (%d), rank %d", (int)r, rank); return MCLIP_ERR_CUDA; }
+  return MCLIP_OK;
+}
