@@ -128,23 +128,17 @@ int mclip_dwconv_slots(const mclip_dwconv_args* args, int backward);
 int mclip_dwconv_forward(const mclip_dwconv_args* args, void* stream);
 int mclip_dwconv_backward(const mclip_dwconv_args* args, void* stream);
 
-/* mclip_stem_*: EfficientNet._conv_stem (efficientnet_custom.py:174-176,273): dense 3x3 stride-2, 3 -> c channels,
- * static pads; input fp32 with arbitrary element strides (the trainer passes NCHW-shaped NHWC memory,
- * trainer_ddp.py:288-291); output bf16 NHWC + BN statistics partials.  No data gradient (images need none). */
+/* mclip_stem_im2col: EfficientNet._conv_stem (efficientnet_custom.py:174-176,273), dense 3x3 stride-2 on 3 channels with
+ * static pads, as im2col + tcgen05 GEMM.  Gathers each output pixel's 27 taps (t = ci*9 + ky*3 + kx, zero padded to 32)
+ * from the fp32 image with arbitrary element strides (the trainer passes NCHW-shaped NHWC memory, trainer_ddp.py:288-291)
+ * into bf16 rows; forward = mclip_gemm_tn(patches, W[c,32]) (+ BN statistics), weight gradient = mclip_gemm_wgrad(dY, patches). */
 typedef struct mclip_stem_args {
-  int n, h, w, ho, wo, c;
+  int n, h, w, ho, wo;
   int pad_left, pad_right, pad_top, pad_bottom;
   const float* in; long long stride_n, stride_c, stride_h, stride_w;
-  const float* weight;            /* fp32 [c,3,3,3] */
-  void* out;                      /* bf16 [n,ho,wo,c] */
-  float* stats; int stat_slots;   /* slots = mclip_stem_slots(n,ho,wo) */
-  const void* dy;                 /* bf16 [n,ho,wo,c] (wgrad) */
-  float* dweight; int accumulate;
-  float* dw_partials;             /* fp32 [stat_slots][27][c] */
+  void* out;                      /* bf16 [n*ho*wo, 32] */
 } mclip_stem_args;
-int mclip_stem_slots(int n, int ho, int wo);
-int mclip_stem_forward(const mclip_stem_args* args, void* stream);
-int mclip_stem_wgrad(const mclip_stem_args* args, void* stream);
+int mclip_stem_im2col(const mclip_stem_args* args, void* stream);
 
 /* ---- BatchNorm / swish / squeeze-excite / pooling passes ---------------------------------------------------------
  * Producer kernels (GEMM, depthwise, stem) emit per-channel (sum, sum sq) partials; mclip_bn_finalize turns them
@@ -230,7 +224,7 @@ int mclip_bert_attention(const void* qkv, const void* attention_mask, const void
                          int batch, int seq_len, int heads, int head_dim, void* stream);
 
 /* fp32 master weights -> bf16 GEMM operands (and their transposes for the data-gradient GEMMs), one launch per tower. */
-typedef struct mclip_prep_entry { const void* src; void* dst; void* dst_t; int rows, cols; } mclip_prep_entry;
+typedef struct mclip_prep_entry { const void* src; void* dst; void* dst_t; int rows, cols, dst_ld, pad_; } mclip_prep_entry;   /* dst_ld: row stride of dst (0: cols) */
 int mclip_weight_prep(const void* table_dev, int n_entries, void* stream);
 
 /* CLIP head helpers: cast, x/||x|| (clip.py:90-91) forward/backward, Linear bias gradient. */

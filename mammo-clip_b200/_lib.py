@@ -89,7 +89,7 @@ def check(rc: int, what: str = ""):
 
 
 # kernels launched per ABI call (for bench.py's `gpu_launches`); default 1
-LAUNCHES = {"mclip_gemm_wgrad": 2, "mclip_dwconv_backward": 2, "mclip_se_fc_backward": 2, "mclip_stem_wgrad": 2}
+LAUNCHES = {"mclip_gemm_wgrad": 2, "mclip_dwconv_backward": 2, "mclip_se_fc_backward": 2}
 
 
 class Profiler:
@@ -163,12 +163,10 @@ class DwconvArgs(C.Structure):
 
 class StemArgs(C.Structure):
     _fields_ = [
-        ("n", C.c_int), ("h", C.c_int), ("w", C.c_int), ("ho", C.c_int), ("wo", C.c_int), ("c", C.c_int),
+        ("n", C.c_int), ("h", C.c_int), ("w", C.c_int), ("ho", C.c_int), ("wo", C.c_int),
         ("pad_left", C.c_int), ("pad_right", C.c_int), ("pad_top", C.c_int), ("pad_bottom", C.c_int),
         ("in_", C.c_void_p), ("stride_n", C.c_longlong), ("stride_c", C.c_longlong), ("stride_h", C.c_longlong), ("stride_w", C.c_longlong),
-        ("weight", C.c_void_p), ("out", C.c_void_p),
-        ("stats", C.c_void_p), ("stat_slots", C.c_int),
-        ("dy", C.c_void_p), ("dweight", C.c_void_p), ("accumulate", C.c_int), ("dw_partials", C.c_void_p),
+        ("out", C.c_void_p),
     ]
 
 
@@ -211,7 +209,7 @@ class EwBwdArgs(C.Structure):
 
 
 class PrepEntry(C.Structure):
-    _fields_ = [("src", C.c_void_p), ("dst", C.c_void_p), ("dst_t", C.c_void_p), ("rows", C.c_int), ("cols", C.c_int)]
+    _fields_ = [("src", C.c_void_p), ("dst", C.c_void_p), ("dst_t", C.c_void_p), ("rows", C.c_int), ("cols", C.c_int), ("dst_ld", C.c_int), ("pad_", C.c_int)]
 
 
 class BertEmbedArgs(C.Structure):

@@ -644,196 +644,51 @@ extern "C" int mclip_dwconv_backward(const mclip_dwconv_args* a, void* stream_) 
 }
 
 // =====================================================================================================
-// stem: dense 3x3 stride-2 convolution, fp32 input with arbitrary strides (the trainer hands NCHW-shaped NHWC memory,
-// trainer_ddp.py:288-291), 3 input channels, Cout <= 64, bf16 NHWC output + BN statistics partials
+// stem: dense 3x3 stride-2 convolution, 3 input channels (EfficientNet._conv_stem, efficientnet_custom.py:174-176,273)
+// as im2col + tcgen05 GEMM: this kernel gathers every output pixel's 27-tap patch (static pads zero-filled) from the fp32
+// image (arbitrary element strides: the trainer hands NCHW-shaped NHWC memory, trainer_ddp.py:288-291) into a bf16 row of
+// 32 (K padded for the MMA), t = ci*9 + ky*3 + kx like the OIHW weight.  Forward = mclip_gemm_tn(patches, W[c,32]) with
+// the BN-statistics epilogue; weight gradient = mclip_gemm_wgrad(dY, patches).  (bf16 patches = what autocast feeds the conv.)
 // =====================================================================================================
-#define STEM_THREADS 256
-#define STEM_MAXC 64
-
-struct StemDev {
-  int N, H, W, Ho, Wo, C, pl, pt, slots;
-  long long sn, sc, sh, sw;     // element strides of the fp32 input
-  const float* in; const float* w;   // w: [C,3,3,3] (OIHW)
-  bf16* out; float* stats;
-  // backward
-  const bf16* dy; float* dw_part;    // [slots][27][C]
-};
-
-__global__ void __launch_bounds__(STEM_THREADS) mclip_stem_fwd_kernel(const StemDev p) {
-  __shared__ float ws[27][STEM_MAXC];
-  __shared__ float red[2][STEM_MAXC];
-  for (int i = threadIdx.x; i < 27 * STEM_MAXC; i += STEM_THREADS) {
-    int t = i / STEM_MAXC, c = i % STEM_MAXC;     // t = ci*9 + ky*3 + kx
-    ws[t][c] = c < p.C ? p.w[(size_t)c * 27 + t] : 0.f;
-  }
-  if (threadIdx.x < 2 * STEM_MAXC) red[threadIdx.x / STEM_MAXC][threadIdx.x % STEM_MAXC] = 0.f;
-  __syncthreads();
-  // thread = (pixel, group of 16 output channels): 4 channel groups cover 64 channels
-  const int cg = threadIdx.x & 3;
-  const int ngroups = (p.C + 15) / 16;
-  float ssum[16], ssq[16];
+__global__ void __launch_bounds__(256) mclip_stem_im2col_kernel(const float* __restrict__ in, long long sn, long long sc, long long sh, long long sw,
+                                                                bf16* __restrict__ out, int N, int H, int W, int Ho, int Wo, int pl, int pt) {
+  const long long npix = (long long)N * Ho * Wo;
+  for (long long px = (long long)blockIdx.x * blockDim.x + threadIdx.x; px < npix; px += (long long)gridDim.x * blockDim.x) {
+    const int ox = (int)(px % Wo);
+    const int oy = (int)((px / Wo) % Ho);
+    const int n = (int)(px / ((long long)Wo * Ho));
+    float v[32];
 #pragma unroll
-  for (int i = 0; i < 16; ++i) ssum[i] = ssq[i] = 0.f;
-  const long long npix = (long long)p.N * p.Ho * p.Wo;
-  for (long long px = (long long)blockIdx.x * (STEM_THREADS / 4) + (threadIdx.x >> 2); px < npix; px += (long long)gridDim.x * (STEM_THREADS / 4)) {
-    if (cg >= ngroups) continue;
-    const int ox = (int)(px % p.Wo);
-    const int oy = (int)((px / p.Wo) % p.Ho);
-    const int n = (int)(px / ((long long)p.Wo * p.Ho));
-    float acc[16];
-#pragma unroll
-    for (int i = 0; i < 16; ++i) acc[i] = 0.f;
+    for (int t = 0; t < 32; ++t) v[t] = 0.f;
+    const float* base = in + n * sn;
 #pragma unroll
     for (int ky = 0; ky < 3; ++ky) {
-      const int y = oy * 2 - p.pt + ky;
-      if (y < 0 || y >= p.H) continue;
+      const int y = oy * 2 - pt + ky;
+      if ((unsigned)y >= (unsigned)H) continue;
 #pragma unroll
       for (int kx = 0; kx < 3; ++kx) {
-        const int x = ox * 2 - p.pl + kx;
-        if (x < 0 || x >= p.W) continue;
-        const float* ip = p.in + n * p.sn + y * p.sh + x * p.sw;
+        const int x = ox * 2 - pl + kx;
+        if ((unsigned)x >= (unsigned)W) continue;
+        const float* ip = base + y * sh + x * sw;
 #pragma unroll
-        for (int ci = 0; ci < 3; ++ci) {
-          const float v = __ldg(ip + ci * p.sc);
-          const float4* wr = reinterpret_cast<const float4*>(&ws[ci * 9 + ky * 3 + kx][cg * 16]);
-#pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            float4 w4 = wr[q];
-            acc[q * 4 + 0] = fmaf(v, w4.x, acc[q * 4 + 0]); acc[q * 4 + 1] = fmaf(v, w4.y, acc[q * 4 + 1]);
-            acc[q * 4 + 2] = fmaf(v, w4.z, acc[q * 4 + 2]); acc[q * 4 + 3] = fmaf(v, w4.w, acc[q * 4 + 3]);
-          }
-        }
+        for (int ci = 0; ci < 3; ++ci) v[ci * 9 + ky * 3 + kx] = __ldg(ip + ci * sc);
       }
     }
-    bf16* op = p.out + (size_t)px * p.C + cg * 16;
+    bf16* op = out + (size_t)px * 32;
 #pragma unroll
-    for (int g = 0; g < 2; ++g) {
-      if (cg * 16 + g * 8 < p.C) {
-        bf16x8 pk = pack8(acc + g * 8);
-        stg_bf16x8(op + g * 8, pk);
-        float f[8];
-        unpack8(pk, f);
-#pragma unroll
-        for (int i = 0; i < 8; ++i) { ssum[g * 8 + i] += f[i]; ssq[g * 8 + i] = fmaf(f[i], f[i], ssq[g * 8 + i]); }
-      }
-    }
-  }
-  if (p.stats) {
-    // threads with equal cg are lanes {cg, cg+4, ...}: reduce over xor 4,8,16 then one shared atomic per warp
-#pragma unroll
-    for (int i = 0; i < 16; ++i) {
-      float a = ssum[i], b = ssq[i];
-#pragma unroll
-      for (int o = 4; o < 32; o <<= 1) { a += __shfl_xor_sync(0xffffffffu, a, o); b += __shfl_xor_sync(0xffffffffu, b, o); }
-      if ((threadIdx.x & 31) < 4) { atomicAdd(&red[0][cg * 16 + i], a); atomicAdd(&red[1][cg * 16 + i], b); }
-    }
-    __syncthreads();
-    if (threadIdx.x < p.C) {
-      p.stats[(size_t)blockIdx.x * 2 * p.C + threadIdx.x] = red[0][threadIdx.x];
-      p.stats[(size_t)blockIdx.x * 2 * p.C + p.C + threadIdx.x] = red[1][threadIdx.x];
-    }
+    for (int g = 0; g < 4; ++g) stg_bf16x8(op + g * 8, pack8(v + g * 8));
   }
 }
 
-// weight gradient of the stem: dW[c, t] = sum_pixels dY[pix, c] * patch[pix, t],  t in 0..26
-// CTA stages 64 pixels of (patch[27], dY[C]) in smem; thread owns (tap t, 4 channels) pairs.
-__global__ void __launch_bounds__(STEM_THREADS) mclip_stem_wgrad_kernel(const StemDev p) {
-  __shared__ float patch[64][28];
-  __shared__ __align__(16) float dys[64][STEM_MAXC + 4];
-  // work item w = t*16 + cq  (27 taps x 16 channel-quads = 432 items, 2 per thread max)
-  float acc[2][4];
-#pragma unroll
-  for (int i = 0; i < 2; ++i) acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.f;
-  const long long npix = (long long)p.N * p.Ho * p.Wo;
-  for (long long base = (long long)blockIdx.x * 64; base < npix; base += (long long)gridDim.x * 64) {
-    __syncthreads();
-    for (int i = threadIdx.x; i < 64 * 27; i += STEM_THREADS) {
-      const int lp = i / 27, t = i % 27;
-      const long long px = base + lp;
-      float v = 0.f;
-      if (px < npix) {
-        const int ox = (int)(px % p.Wo), oy = (int)((px / p.Wo) % p.Ho), n = (int)(px / ((long long)p.Wo * p.Ho));
-        const int ci = t / 9, ky = (t % 9) / 3, kx = t % 3;
-        const int y = oy * 2 - p.pt + ky, x = ox * 2 - p.pl + kx;
-        if (y >= 0 && y < p.H && x >= 0 && x < p.W) v = __ldg(p.in + n * p.sn + ci * p.sc + y * p.sh + x * p.sw);
-      }
-      patch[lp][t] = v;
-    }
-    for (int i = threadIdx.x; i < 64 * STEM_MAXC; i += STEM_THREADS) {
-      const int lp = i / STEM_MAXC, c = i % STEM_MAXC;
-      const long long px = base + lp;
-      dys[lp][c] = (px < npix && c < p.C) ? __bfloat162float(p.dy[(size_t)px * p.C + c]) : 0.f;
-    }
-    __syncthreads();
-#pragma unroll
-    for (int it = 0; it < 2; ++it) {
-      const int wi = threadIdx.x + it * STEM_THREADS;
-      if (wi < 27 * 16) {
-        const int t = wi >> 4, cq = (wi & 15) * 4;
-        for (int lp = 0; lp < 64; ++lp) {
-          const float pv = patch[lp][t];
-          const float4 d4 = *reinterpret_cast<const float4*>(&dys[lp][cq]);
-          acc[it][0] = fmaf(pv, d4.x, acc[it][0]); acc[it][1] = fmaf(pv, d4.y, acc[it][1]);
-          acc[it][2] = fmaf(pv, d4.z, acc[it][2]); acc[it][3] = fmaf(pv, d4.w, acc[it][3]);
-        }
-      }
-    }
-  }
-#pragma unroll
-  for (int it = 0; it < 2; ++it) {
-    const int wi = threadIdx.x + it * STEM_THREADS;
-    if (wi < 27 * 16) {
-      const int t = wi >> 4, cq = (wi & 15) * 4;
-#pragma unroll
-      for (int e = 0; e < 4; ++e)
-        if (cq + e < p.C) p.dw_part[((size_t)blockIdx.x * 27 + t) * p.C + cq + e] = acc[it][e];
-    }
-  }
-}
-
-extern "C" int mclip_stem_slots(int n, int ho, int wo) {
-  long long npix = (long long)n * ho * wo;
-  int g = mclip_num_sms() * 4;
-  long long need = (npix + 63) / 64;
-  return (int)(need < g ? need : g);
-}
-
-static int stem_fill(const mclip_stem_args* a, StemDev& p) {
-  MCLIP_REQUIRE(a && a->in && a->weight, "mclip_stem: null operand");
-  MCLIP_REQUIRE(a->c % 8 == 0 && a->c <= STEM_MAXC, "mclip_stem: Cout=%d must be a multiple of 8 and <= %d", a->c, STEM_MAXC);
+extern "C" int mclip_stem_im2col(const mclip_stem_args* a, void* stream_) {
+  MCLIP_REQUIRE(a && a->in && a->out, "mclip_stem_im2col: null operand");
   MCLIP_REQUIRE(a->ho == (a->h + a->pad_top + a->pad_bottom - 3) / 2 + 1 && a->wo == (a->w + a->pad_left + a->pad_right - 3) / 2 + 1,
-                "mclip_stem: output size inconsistent with the static padding");
-  memset(&p, 0, sizeof(p));
-  p.N = a->n; p.H = a->h; p.W = a->w; p.Ho = a->ho; p.Wo = a->wo; p.C = a->c; p.pl = a->pad_left; p.pt = a->pad_top;
-  p.sn = a->stride_n; p.sc = a->stride_c; p.sh = a->stride_h; p.sw = a->stride_w;
-  p.in = a->in; p.w = a->weight;
-  p.slots = mclip_stem_slots(a->n, a->ho, a->wo);
-  return MCLIP_OK;
-}
-
-extern "C" int mclip_stem_forward(const mclip_stem_args* a, void* stream_) {
-  StemDev p;
-  int rc = stem_fill(a, p);
-  if (rc) return rc;
-  MCLIP_REQUIRE(a->out, "mclip_stem_forward: null output");
-  if (a->stats) MCLIP_REQUIRE(a->stat_slots == p.slots, "mclip_stem_forward: stat_slots=%d, expected %d", a->stat_slots, p.slots);
-  p.out = (bf16*)a->out; p.stats = a->stats;
-  mclip_stem_fwd_kernel<<<p.slots, STEM_THREADS, 0, (cudaStream_t)stream_>>>(p);
-  MCLIP_CHECK_LAUNCH();
-  return MCLIP_OK;
-}
-
-extern "C" int mclip_stem_wgrad(const mclip_stem_args* a, void* stream_) {
-  StemDev p;
-  int rc = stem_fill(a, p);
-  if (rc) return rc;
-  MCLIP_REQUIRE(a->dy && a->dweight && a->dw_partials, "mclip_stem_wgrad: null operand");
-  MCLIP_REQUIRE(a->stat_slots == p.slots, "mclip_stem_wgrad: stat_slots=%d, expected %d", a->stat_slots, p.slots);
-  p.dy = (const bf16*)a->dy; p.dw_part = a->dw_partials;
-  mclip_stem_wgrad_kernel<<<p.slots, STEM_THREADS, 0, (cudaStream_t)stream_>>>(p);
-  MCLIP_CHECK_LAUNCH();
-  // dweight is [C,27] (OIHW flattened) which is exactly the [c][t] layout of the depthwise reducer
-  mclip_dw_wgrad_reduce_kernel<<<ceil_div(27 * a->c, 256), 256, 0, (cudaStream_t)stream_>>>(a->dw_partials, a->dweight, p.slots, 27, a->c, a->accumulate);
+                "mclip_stem_im2col: output size inconsistent with the static padding");
+  const long long npix = (long long)a->n * a->ho * a->wo;
+  long long grid = (npix + 255) / 256;
+  if (grid > (long long)mclip_num_sms() * 16) grid = (long long)mclip_num_sms() * 16;
+  mclip_stem_im2col_kernel<<<(int)grid, 256, 0, (cudaStream_t)stream_>>>(a->in, a->stride_n, a->stride_c, a->stride_h, a->stride_w, (bf16*)a->out, a->n,
+                                                                          a->h, a->w, a->ho, a->wo, a->pad_left, a->pad_top);
   MCLIP_CHECK_LAUNCH();
   return MCLIP_OK;
 }

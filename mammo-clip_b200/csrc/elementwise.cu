@@ -367,10 +367,11 @@ __global__ void __launch_bounds__(EW_MAX_THREADS, 3) mclip_ew_bwd_kernel(const E
   }
   const float2 one = make_float2(1.f, 1.f);
   const size_t base = (size_t)n * g.HW * g.C + c;
-  for (int px0 = p0 + pl; px0 < p1; px0 += g.PL * EW_UNR) {
-    uint2 yv[EW_UNR], dv_[EW_UNR];
+  constexpr int UNR = (MODE == 2) ? 2 : EW_UNR;
+  for (int px0 = p0 + pl; px0 < p1; px0 += g.PL * UNR) {
+    uint2 yv[UNR], dv_[UNR];
 #pragma unroll
-    for (int u = 0; u < EW_UNR; ++u) {
+    for (int u = 0; u < UNR; ++u) {
       const int px = px0 + u * g.PL;
       if (px < p1) {
         const size_t off = base + (size_t)px * g.C;
@@ -379,7 +380,7 @@ __global__ void __launch_bounds__(EW_MAX_THREADS, 3) mclip_ew_bwd_kernel(const E
       }
     }
 #pragma unroll
-    for (int u = 0; u < EW_UNR; ++u) {
+    for (int u = 0; u < UNR; ++u) {
       const int px = px0 + u * g.PL;
       if (px >= p1) break;
       const uint32_t yw[2] = {yv[u].x, yv[u].y}, dw_[2] = {dv_[u].x, dv_[u].y};
@@ -599,7 +600,7 @@ __global__ void mclip_weight_prep_kernel(const mclip_prep_entry* __restrict__ ta
     bf16* dstT = (bf16*)t.dst_t;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
       const bf16 v = __float2bfloat16_rn(src[i]);
-      if (dst) dst[i] = v;
+      if (dst) { if (t.dst_ld > 0) dst[(i / t.cols) * t.dst_ld + i % t.cols] = v; else dst[i] = v; }
       if (dstT) { const long long r = i / t.cols, c = i % t.cols; dstT[c * t.rows + r] = v; }
     }
   }

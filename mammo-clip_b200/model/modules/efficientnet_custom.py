@@ -149,6 +149,9 @@ class _WeightCache:
                 add(("e", i), blk._expand_conv.weight, True, True)
             add(("p", i), blk._project_conv.weight, False, True)
         add(("h",), net._conv_head.weight, True, True)
+        ws = net._conv_stem.weight
+        self.bf16[("s",)] = torch.zeros((ws.shape[0], 32), dtype=torch.bfloat16, device=dev)      # K = 27 taps padded to 32
+        self.entries.append((ws.detach().view(ws.shape[0], 27), self.bf16[("s",)], None, 32))
         self.table = ops.weight_prep(self.entries, dev)
         self.key = self._key(net)
 
@@ -167,7 +170,8 @@ def _forward(net, images, training, drop_rowscales, dropout_mult, want_raw):
     wc = net._weights()
     wc.refresh()
     S = {"images": images, "training": training, "blocks": []}
-    y, st = ops.stem_forward(images, net._conv_stem.weight, geom.stem_pads, want_stats=training)
+    y, st, patches = ops.stem_forward(images, net._conv_stem.weight, geom.stem_pads, want_stats=training, w_bf16=wc.bf16[("s",)], return_patches=True)
+    S["patches"] = patches
     h, w = y.shape[1], y.shape[2]
     bn = _bn_fin(st, n * h * w, net._bn0, training)
     S["stem"] = (y, bn)
@@ -290,7 +294,7 @@ def _backward(net, S, dfeat):
             cs = geom.stem_out
             dys = ops.ew_backward(1, ys.view(n, h * w, cs), bns, 0, du=dvs.view(n, h * w, cs), dv_given=True, c1=c1, c2=c2)
             dws = torch.empty_like(net._conv_stem.weight)
-            ops.stem_wgrad(S["images"], dys.view(n, h, w, cs), geom.stem_pads, dws)
+            ops.stem_wgrad(S["images"], dys.view(n, h, w, cs), geom.stem_pads, dws, patches=S["patches"])
             grads["_conv_stem.weight"] = dws
             dx = None
         else:
@@ -304,7 +308,7 @@ def _backward(net, S, dfeat):
         nn_, hs, ws, cs = ys.shape
         dys = _bn_backward(ys.view(nn_, hs * ws, cs), bns, training, net._bn0, grads, "_bn0", 1, du=dx.view(nn_, hs * ws, cs))
         dws = torch.empty_like(net._conv_stem.weight)
-        ops.stem_wgrad(S["images"], dys.view(nn_, hs, ws, cs), geom.stem_pads, dws)
+        ops.stem_wgrad(S["images"], dys.view(nn_, hs, ws, cs), geom.stem_pads, dws, patches=S["patches"])
         grads["_conv_stem.weight"] = dws
     return grads
 

@@ -154,44 +154,49 @@ def bn_finalize(partials, count, gamma, beta, running_mean, running_var, num_bat
     return st
 
 
-def stem_forward(images, weight, pads, want_stats=True):
-    """images: [N,3,H,W] fp32 (any strides); weight [C,3,3,3] fp32 -> (Y [N,Ho,Wo,C] bf16, stats)."""
-    _require_cuda(images, weight)
+def stem_im2col(images, pads):
+    """images: [N,3,H,W] fp32 (any strides) -> (patches [N*Ho*Wo, 32] bf16, Ho, Wo); taps t = ci*9 + ky*3 + kx, zero padded."""
+    _require_cuda(images)
     n, ci, h, w = images.shape
     assert ci == 3 and images.dtype == torch.float32
     pl, pr, pt, pb = pads
     ho, wo = (h + pt + pb - 3) // 2 + 1, (w + pl + pr - 3) // 2 + 1
+    out = torch.empty((n * ho * wo, 32), dtype=torch.bfloat16, device=images.device)
+    a = StemArgs()
+    a.n, a.h, a.w, a.ho, a.wo = n, h, w, ho, wo
+    a.pad_left, a.pad_right, a.pad_top, a.pad_bottom = pl, pr, pt, pb
+    a.in_ = images.data_ptr()
+    a.stride_n, a.stride_c, a.stride_h, a.stride_w = images.stride()
+    a.out = out.data_ptr()
+    call("mclip_stem_im2col", C.byref(a), nbytes=4 * images.numel() + 2 * out.numel())
+    return out, ho, wo
+
+
+def stem_weight_bf16(weight):
+    """[C,3,3,3] fp32 -> [C,32] bf16 (K padded with zeros)."""
     c = weight.shape[0]
-    out = torch.empty((n, ho, wo, c), dtype=torch.bfloat16, device=images.device)
-    a = StemArgs()
-    a.n, a.h, a.w, a.ho, a.wo, a.c = n, h, w, ho, wo, c
-    a.pad_left, a.pad_right, a.pad_top, a.pad_bottom = pl, pr, pt, pb
-    a.in_ = images.data_ptr()
-    a.stride_n, a.stride_c, a.stride_h, a.stride_w = images.stride()
-    a.weight, a.out = weight.data_ptr(), out.data_ptr()
-    stats = None
-    if want_stats:
-        slots = lib().mclip_stem_slots(n, ho, wo)
-        stats = torch.empty((slots, 2, c), dtype=torch.float32, device=images.device)
-        a.stats, a.stat_slots = stats.data_ptr(), slots
-    call("mclip_stem_forward", C.byref(a), nbytes=4 * images.numel() + 2 * out.numel())
-    return out, stats
+    w = torch.zeros((c, 32), dtype=torch.bfloat16, device=weight.device)
+    table = weight_prep([(weight.detach().view(c, 27), w, None)], weight.device, dst_ld=32)
+    weight_prep_run(table, 1)
+    return w
 
 
-def stem_wgrad(images, dy, pads, dweight):
-    n, _, h, w = images.shape
-    _, ho, wo, c = dy.shape
-    pl, pr, pt, pb = pads
-    a = StemArgs()
-    a.n, a.h, a.w, a.ho, a.wo, a.c = n, h, w, ho, wo, c
-    a.pad_left, a.pad_right, a.pad_top, a.pad_bottom = pl, pr, pt, pb
-    a.in_ = images.data_ptr()
-    a.stride_n, a.stride_c, a.stride_h, a.stride_w = images.stride()
-    a.weight = dweight.data_ptr()        # unused by the wgrad kernel, must be non-null
-    slots = lib().mclip_stem_slots(n, ho, wo)
-    part = torch.empty((slots, 27, c), dtype=torch.float32, device=dy.device)
-    a.stat_slots, a.dy, a.dweight, a.accumulate, a.dw_partials = slots, dy.data_ptr(), dweight.data_ptr(), 0, part.data_ptr()
-    call("mclip_stem_wgrad", C.byref(a), nbytes=4 * images.numel() + 2 * dy.numel())
+def stem_forward(images, weight, pads, want_stats=True, w_bf16=None, return_patches=False):
+    """Stem conv = im2col + tcgen05 GEMM.  -> (Y [N,Ho,Wo,C] bf16, stats) (+ patches for the weight gradient)."""
+    patches, ho, wo = stem_im2col(images, pads)
+    wb = w_bf16 if w_bf16 is not None else stem_weight_bf16(weight)
+    y, stats = gemm_tn(patches, wb, want_stats=bool(want_stats))
+    y = y.view(images.shape[0], ho, wo, weight.shape[0])
+    return (y, stats, patches) if return_patches else (y, stats)
+
+
+def stem_wgrad(images, dy, pads, dweight, patches=None):
+    """dW[c, ci,ky,kx] = sum_pixels dY[pix,c] * patch[pix,t] on the tcgen05 wgrad GEMM."""
+    if patches is None:
+        patches, _, _ = stem_im2col(images, pads)
+    c = dy.shape[-1]
+    tmp = gemm_wgrad(dy.reshape(-1, c), patches)            # [C, 32]
+    dweight.view(c, 27).copy_(tmp[:, :27])
     return dweight
 
 
@@ -353,13 +358,15 @@ def bn_bwd_finalize(partials, count, training, dgamma, dbeta):
     return cc[0], cc[1]
 
 
-def weight_prep(entries, device):
-    """entries: list of (src fp32 2-D, dst bf16 or None, dst_t bf16 or None). Returns the device table (keep it alive)."""
+def weight_prep(entries, device, dst_ld=0):
+    """entries: list of (src fp32 2-D, dst bf16 or None, dst_t bf16 or None[, dst_ld]). Returns the device table (keep it alive)."""
     import numpy as np
     arr = (PrepEntry * len(entries))()
-    for i, (src, dst, dst_t) in enumerate(entries):
+    for i, e in enumerate(entries):
+        src, dst, dst_t = e[0], e[1], e[2]
         arr[i].src, arr[i].dst, arr[i].dst_t = src.data_ptr(), _p(dst), _p(dst_t)
         arr[i].rows, arr[i].cols = src.shape[0], src[0].numel()
+        arr[i].dst_ld = e[3] if len(e) > 3 else dst_ld
     raw = np.frombuffer(bytes(arr), dtype=np.uint8).copy()
     return torch.from_numpy(raw).to(device)
 

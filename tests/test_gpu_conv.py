@@ -85,9 +85,12 @@ def test_stem(n, h, w, c, pads, nhwc):
     img = torch.randn(n, h, w, 3, generator=g, device="cuda").permute(0, 3, 1, 2) if nhwc else torch.randn(n, 3, h, w, generator=g, device="cuda")
     wt = _rand((c, 3, 3, 3), 6, 0.3, torch.float32)
     y, stats = ops.stem_forward(img, wt, pads)
-    wref = wt.clone().requires_grad_(True)
-    yref = F.conv2d(F.pad(img, pads), wref, stride=2)
+    # the stem runs as im2col (bf16 patches, like autocast) + tcgen05 GEMM with bf16 weights
+    wref = wt.to(torch.bfloat16).float().requires_grad_(True)
+    imgq = img.to(torch.bfloat16).float()
+    yref = F.conv2d(F.pad(imgq, pads), wref, stride=2)
     assert rel_err(y.float(), yref.permute(0, 2, 3, 1)) < 6e-3
+    assert rel_err(y.float(), F.conv2d(F.pad(img, pads), wt, stride=2).permute(0, 2, 3, 1)) < 2e-2      # vs the fp32 conv
     st = stats.double().sum(0)
     yd = y.double().reshape(-1, c)
     assert rel_err(st[0], yd.sum(0)) < 1e-4 and rel_err(st[1], (yd * yd).sum(0)) < 1e-4
