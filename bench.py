@@ -189,7 +189,7 @@ def run_ours(args):
     torch.manual_seed(0)
     model = build_model(cfg, loss_cfg, Tok()).to(dev).train()
     loss_fn = build_loss(loss_cfg)
-    opt = FlatAdamW(model.parameters(), lr=5e-5, weight_decay=1e-4)
+    opt = FlatAdamW(model.parameters(), lr=5e-5, weight_decay=1e-4).attach(model)
     img_h, tok_h = _synth_host(batch, h, w, L, rank)
     img_d = img_h.to(dev, non_blocking=True).permute(0, 3, 1, 2)
     tok_d = BatchEncoding({k: v.to(dev, non_blocking=True) for k, v in tok_h.items()})

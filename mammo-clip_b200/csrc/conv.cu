@@ -52,6 +52,11 @@ __device__ __forceinline__ float2 ffma2r(const float2& a, const float2& b, const
       "l"(reinterpret_cast<const u64&>(c)));
   return d;
 }
+__device__ __forceinline__ float2 fmul2(const float2& a, const float2& b) {
+  float2 d;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(reinterpret_cast<u64&>(d)) : "l"(reinterpret_cast<const u64&>(a)), "l"(reinterpret_cast<const u64&>(b)));
+  return d;
+}
 
 // ---- tile loader: global NHWC bf16 -> smem [rows][cols][64ch] bf16 with optional affine+swish, zero padded -------------
 // swish(t) = t*sigma(t) = h + h*tanh(h) with h = t/2 : the 1/2 is folded into the affine, one MUFU per element.
@@ -291,6 +296,9 @@ mclip_dwconv_bwd_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_c
   if (p.scale && cvalid) { ab = make_float2(p.scale[c], p.scale[c + 1]); bb = make_float2(p.shift[c], p.shift[c + 1]); }
   if (p.bn_part && cvalid) { mu = make_float2(p.mean[c], p.mean[c + 1]); is = make_float2(p.invstd[c], p.invstd[c + 1]); }
   float2 bs = make_float2(0.f, 0.f), bq = make_float2(0.f, 0.f);
+  const float2 abh = make_float2(0.5f * ab.x, 0.5f * ab.y), bbh = make_float2(0.5f * bb.x, 0.5f * bb.y);
+  const float2 nmis = make_float2(-mu.x * is.x, -mu.y * is.y);
+  const float2 half2 = make_float2(0.5f, 0.5f), one2 = make_float2(1.f, 1.f), two2 = make_float2(2.f, 2.f), neg1 = make_float2(-1.f, -1.f);
   float2 dw[K * K];
 #pragma unroll
   for (int q = 0; q < K * K; ++q) dw[q] = make_float2(0.f, 0.f);
@@ -324,15 +332,18 @@ mclip_dwconv_bwd_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_c
       if (p.scale) {
         const float2 yv = bf2_to_f2(yu);
         if (p.act) {
-          const float2 tv = ffma2r(yv, ab, bb);
-          d.x *= swish_grad_f(tv.x); d.y *= swish_grad_f(tv.y);
+          // swish'(v) = s (1 + v (1 - s)), s = sigma(v) = 0.5 + 0.5 tanh(v/2); packed math, one MUFU per element
+          const float2 hv = ffma2r(yv, abh, bbh);                                   // v / 2
+          const float2 sg = ffma2r(make_float2(fast_tanh(hv.x), fast_tanh(hv.y)), half2, half2);
+          const float2 om = ffma2r(sg, neg1, one2);                                 // 1 - s
+          const float2 q = ffma2r(fmul2(hv, om), two2, one2);                       // 1 + v (1 - s)
+          d = fmul2(d, fmul2(sg, q));
         }
         const uint32_t pk = pack_bf16(d.x, d.y);
         dxw[off] = pk;
         d = bf2_to_f2(pk);
-        bs.x += d.x; bs.y += d.y;
-        const float2 yh = make_float2((yv.x - mu.x) * is.x, (yv.y - mu.y) * is.y);
-        ffma2(bq, d, yh);
+        ffma2(bs, d, one2);
+        ffma2(bq, d, ffma2r(yv, is, nmis));                                         // yhat = (y - mean) * invstd
       } else {
         dxw[off] = pack_bf16(d.x, d.y);
       }

@@ -222,28 +222,36 @@ def _forward(net, images, training, drop_rowscales, dropout_mult, want_raw):
     return feat, S, raw
 
 
-def _bn_backward(y3, bn, training, bnp: _BNParams, grads, prefix, act, du=None, dvec=None, gate=None, dpool=None, rowscale=None):
+def _bn_backward(y3, bn, training, bnp: _BNParams, grads, prefix, act, du=None, dvec=None, gate=None, dpool=None, rowscale=None, G=torch.empty_like):
     """Two-pass BatchNorm(+swish) backward over y3 [N,HW,C]; returns dY (bf16) and fills grads of gamma/beta."""
     part = ops.ew_backward(0, y3, bn, act, du=du, dvec=dvec, gate=gate, dpool=dpool, rowscale=rowscale)
-    dg, db = torch.empty_like(bnp.weight), torch.empty_like(bnp.bias)
+    dg, db = G(bnp.weight), G(bnp.bias)
     c1, c2 = ops.bn_bwd_finalize(part, bn.count, training, dg, db)
     grads[prefix + ".weight"], grads[prefix + ".bias"] = dg, db
     return ops.ew_backward(1, y3, bn, act, du=du, dvec=dvec, gate=gate, dpool=dpool, rowscale=rowscale, c1=c1, c2=c2)
 
 
-def _backward(net, S, dfeat):
-    """dfeat: [N,Chead] fp32.  Returns {state-dict key: gradient tensor} for every trainable parameter."""
+def _backward(net, S, dfeat, direct=False):
+    """dfeat: [N,Chead] fp32.  Returns {state-dict key: gradient tensor} for every trainable parameter.
+    direct=True: kernels write straight into the (freshly zeroed) `.grad` views of a flat gradient buffer (FlatAdamW),
+    so autograd has nothing to accumulate for this tower."""
     geom, wc, training = net.geom, net._weights(), S["training"]
     grads = {}
+
+    def G(param):
+        return param.grad if direct else torch.empty_like(param)
+
     n, h, w = dfeat.shape[0], S["h"], S["w"]
     dvec = dfeat * (1.0 / (h * w))
     if S["dropout_mult"] is not None:
         dvec = dvec * S["dropout_mult"]
     dvec = dvec.contiguous()
     x_last = S["x_last"]
-    dyh = _bn_backward(S["yh"], S["bnh"], training, net._bn1, grads, "_bn1", 1, dvec=dvec)
+    dyh = _bn_backward(S["yh"], S["bnh"], training, net._bn1, grads, "_bn1", 1, dvec=dvec, G=G)
     dyh2 = dyh.view(n * h * w, geom.head_out)
-    grads["_conv_head.weight"] = ops.gemm_wgrad(dyh2, x_last.view(n * h * w, -1)).view_as(net._conv_head.weight)
+    gh = G(net._conv_head.weight)
+    ops.gemm_wgrad(dyh2, x_last.view(n * h * w, -1), out=gh.view(gh.shape[0], -1))
+    grads["_conv_head.weight"] = gh
     dx = ops.gemm_tn(dyh2, wc.bf16_t[("h",)]).view(x_last.shape)
     del dyh, dyh2
     for i in reversed(range(len(net._blocks))):
@@ -251,49 +259,53 @@ def _backward(net, S, dfeat):
         g, pre = blk.geom, f"_blocks.{i}."
         h, w, ho, wo = B["h"], B["w"], B["ho"], B["wo"]
         dxo = dx.view(n, ho * wo, g.cout)
-        dy2 = _bn_backward(B["y2"], B["bn2"], training, blk._bn2, grads, pre + "_bn2", 0, du=dxo, rowscale=B["rowscale"])
+        dy2 = _bn_backward(B["y2"], B["bn2"], training, blk._bn2, grads, pre + "_bn2", 0, du=dxo, rowscale=B["rowscale"], G=G)
         da2 = ops.gemm_tn(dy2.view(n * ho * wo, g.cout), wc.bf16_t[("p", i)]).view(n, ho * wo, g.cexp)
         y1 = B["y1"].view(n, ho * wo, g.cexp)
         a2, dgp = ops.ew_backward(2, y1, B["bn1"], 1, du=da2, gate=B["gate"])
-        grads[pre + "_project_conv.weight"] = ops.gemm_wgrad(dy2.view(n * ho * wo, g.cout), a2.view(n * ho * wo, g.cexp)).view_as(blk._project_conv.weight)
+        gp = G(blk._project_conv.weight)
+        ops.gemm_wgrad(dy2.view(n * ho * wo, g.cout), a2.view(n * ho * wo, g.cexp), out=gp.view(g.cout, g.cexp))
+        grads[pre + "_project_conv.weight"] = gp
         del a2, dy2
         w1, w2 = blk._se_reduce.weight.view(g.cse, g.cexp), blk._se_expand.weight.view(g.cexp, g.cse)
-        dw1, db1, dw2, db2 = (torch.empty_like(t) for t in (blk._se_reduce.weight, blk._se_reduce.bias, blk._se_expand.weight, blk._se_expand.bias))
+        dw1, db1, dw2, db2 = (G(t) for t in (blk._se_reduce.weight, blk._se_reduce.bias, blk._se_expand.weight, blk._se_expand.bias))
         dpool = ops.se_fc_backward(dgp, ho * wo, w1, w2, B["pooled"], B["z1"], B["gate"], dw1, db1, dw2, db2)
         grads[pre + "_se_reduce.weight"], grads[pre + "_se_reduce.bias"] = dw1, db1
         grads[pre + "_se_expand.weight"], grads[pre + "_se_expand.bias"] = dw2, db2
         # BN1 backward sums come out of the SE pass-1 partials (no separate reduction pass over dA2 / Y1)
         bnp1 = ops.se_bn_combine(dgp, B["gate"], dpool)
-        dg1, db1_ = torch.empty_like(blk._bn1.weight), torch.empty_like(blk._bn1.bias)
+        dg1, db1_ = G(blk._bn1.weight), G(blk._bn1.bias)
         c1, c2 = ops.bn_bwd_finalize(bnp1, B["bn1"].count, training, dg1, db1_)
         grads[pre + "_bn1.weight"], grads[pre + "_bn1.bias"] = dg1, db1_
         dy1 = ops.ew_backward(1, y1, B["bn1"], 1, du=da2, gate=B["gate"], dpool=dpool, c1=c1, c2=c2)
         del da2
         dy1 = dy1.view(n, ho, wo, g.cexp)
-        ddw = torch.empty_like(blk._depthwise_conv.weight)
+        ddw = G(blk._depthwise_conv.weight)
         grads[pre + "_depthwise_conv.weight"] = ddw
         if g.expand:
             y0, bn0 = B["y0"], B["bn0"]
             dv0, bnp = ops.dwconv_backward(y0, blk._depthwise_conv.weight, g.k, g.s, g.pads, dy1, ddw, bn=bn0)
-            dg0, db0 = torch.empty_like(blk._bn0.weight), torch.empty_like(blk._bn0.bias)
+            dg0, db0 = G(blk._bn0.weight), G(blk._bn0.bias)
             c1, c2 = ops.bn_bwd_finalize(bnp, bn0.count, training, dg0, db0)
             grads[pre + "_bn0.weight"], grads[pre + "_bn0.bias"] = dg0, db0
             dy0 = ops.ew_backward(1, y0.view(n, h * w, g.cexp), bn0, 0, du=dv0.view(n, h * w, g.cexp), dv_given=True, c1=c1, c2=c2)
             del dv0
             dy0 = dy0.view(n * h * w, g.cexp)
             x_in = B["x_in"].view(n * h * w, g.cin)
-            grads[pre + "_expand_conv.weight"] = ops.gemm_wgrad(dy0, x_in).view_as(blk._expand_conv.weight)
+            ge = G(blk._expand_conv.weight)
+            ops.gemm_wgrad(dy0, x_in, out=ge.view(g.cexp, g.cin))
+            grads[pre + "_expand_conv.weight"] = ge
             dx = ops.gemm_tn(dy0, wc.bf16_t[("e", i)], residual=dx.view(n * h * w, g.cin) if g.skip else None).view(n, h, w, g.cin)
             del dy0
         elif B.get("from_stem"):
             ys, bns = S["stem"]
             dvs, bnp = ops.dwconv_backward(ys, blk._depthwise_conv.weight, g.k, g.s, g.pads, dy1, ddw, bn=bns)
-            dgs, dbs = torch.empty_like(net._bn0.weight), torch.empty_like(net._bn0.bias)
+            dgs, dbs = G(net._bn0.weight), G(net._bn0.bias)
             c1, c2 = ops.bn_bwd_finalize(bnp, bns.count, training, dgs, dbs)
             grads["_bn0.weight"], grads["_bn0.bias"] = dgs, dbs
             cs = geom.stem_out
             dys = ops.ew_backward(1, ys.view(n, h * w, cs), bns, 0, du=dvs.view(n, h * w, cs), dv_given=True, c1=c1, c2=c2)
-            dws = torch.empty_like(net._conv_stem.weight)
+            dws = G(net._conv_stem.weight)
             ops.stem_wgrad(S["images"], dys.view(n, h, w, cs), geom.stem_pads, dws, patches=S["patches"])
             grads["_conv_stem.weight"] = dws
             dx = None
@@ -306,8 +318,8 @@ def _backward(net, S, dfeat):
     if S.get("stem_materialised"):
         ys, bns = S["stem"]
         nn_, hs, ws, cs = ys.shape
-        dys = _bn_backward(ys.view(nn_, hs * ws, cs), bns, training, net._bn0, grads, "_bn0", 1, du=dx.view(nn_, hs * ws, cs))
-        dws = torch.empty_like(net._conv_stem.weight)
+        dys = _bn_backward(ys.view(nn_, hs * ws, cs), bns, training, net._bn0, grads, "_bn0", 1, du=dx.view(nn_, hs * ws, cs), G=G)
+        dws = G(net._conv_stem.weight)
         ops.stem_wgrad(S["images"], dys.view(nn_, hs, ws, cs), geom.stem_pads, dws, patches=S["patches"])
         grads["_conv_stem.weight"] = dws
     return grads
@@ -326,8 +338,14 @@ class _EncoderFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, dfeat, *unused):
         net = ctx.net
-        grads = _backward(net, ctx.S, dfeat.contiguous().float())
+        # direct mode: a FlatAdamW owns zeroed flat `.grad` views and this is the tower's first backward since zero_grad()
+        opt = getattr(net, "_flat_optimizer", None)
+        direct = opt is not None and opt.zero_count != getattr(net, "_direct_written_at", -1) and all(p.grad is not None for p in net.parameters())
+        grads = _backward(net, ctx.S, dfeat.contiguous().float(), direct=direct)
         ctx.S = None
+        if direct:
+            net._direct_written_at = opt.zero_count
+            return (None,) * (5 + len(list(net.parameters())))
         out = [grads.get(name) for name, _ in net.named_parameters()]
         return (None, None, None, None, None, *out)
 

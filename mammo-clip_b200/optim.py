@@ -29,10 +29,20 @@ class FlatAdamW:
         self.exp_avg_sq = torch.zeros_like(self.flat)
         self.lr, self.betas, self.eps, self.weight_decay = lr, betas, eps, weight_decay
         self.steps = 0
+        self.zero_count = 0
+
+    def attach(self, *modules):
+        """Modules whose backward may write gradients straight into the flat buffer (first backward after each zero_grad)."""
+        for m in modules:
+            for sub in m.modules():
+                if hasattr(sub, "_wcache") and hasattr(sub, "geom"):
+                    object.__setattr__(sub, "_flat_optimizer", self)
+        return self
 
     def zero_grad(self):
         """Gradients live in the flat buffer; autograd accumulates into the views, so clear instead of set_to_none."""
         self.grad.zero_()
+        self.zero_count += 1
 
     def all_reduce_grads(self, world):
         """DDP's gradient averaging (trainer_ddp.py:134) as one NCCL all-reduce over the flat buffer."""
