@@ -138,6 +138,45 @@ def cpu_reference_run(workload, steps, warmup, sample_batch, report_sample=True)
             "sample": f"{len(times)} step(s) of {b} pair(s) of {workload} ({enc_name}, {h}x{w}, L={L}, BERT {layers} layers), fwd+loss+bwd+AdamW, fp32, {sec:.2f} s/step"}, sec
 
 
+def run_oracle_gpu(args):
+    """Informational (not a driver arm): the oracle port — the reference's module wiring on PyTorch/cuDNN/cuBLAS — on
+    cuda:0 under bf16 autocast, channels_last, eager (and torch.compile if --compile), at the largest batch that fits
+    (the reference's eager graph needs ~4.4 GB of saved activations per EN-B5 image, SURVEY finding 2)."""
+    import torch
+    from transformers import BatchEncoding
+    from oracle import port
+    enc_cfg, enc_name, layers, batch, h, w, L = WORKLOADS[args.workload]
+    b = args.batch or min(batch, 16)
+    torch.backends.cudnn.benchmark = True
+    torch.manual_seed(0)
+    model = port.OracleBreastClip(enc_name, num_hidden_layers=layers).cuda().train().to(memory_format=torch.channels_last)
+    fwd = torch.compile(model) if args.compile else model
+    opt = torch.optim.AdamW(model.parameters(), lr=5e-5, weight_decay=1e-4, fused=True)
+    data = {"images": port.synth_images(b, h, w, seed=1234, device="cuda"), "text_tokens": BatchEncoding(port.synth_tokens(b, L, seed=4321, device="cuda"))}
+
+    def step():
+        opt.zero_grad(set_to_none=True)
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            out = fwd(data)
+            loss = port.contrastive_loss(**out, is_train=True, label_smoothing=0.0)
+        loss.backward()
+        opt.step()
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    torch.cuda.synchronize()
+    a, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(args.steps):
+        step()
+    e.record()
+    torch.cuda.synchronize()
+    ms = a.elapsed_time(e) / args.steps
+    print(json.dumps({"impl": "oracle-gpu", "note": "informational: reference wiring on torch %s (cuDNN/cuBLAS), bf16 autocast, channels_last, %s" % (
+        torch.__version__, "torch.compile" if args.compile else "eager"), "value": b / (ms * 1e-3), "unit": "pairs/s", "ms_per_step": ms, "batch": b,
+        "workload": args.workload, "peak_mem_gb": torch.cuda.max_memory_allocated() / 1e9}))
+
+
 def run_reference(args):
     """`--impl reference`: rank 0 times the CPU path; other ranks exit 0 without work."""
     if int(os.environ.get("RANK", "0")) != 0:
@@ -297,13 +336,16 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=8)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference", "oracle-gpu"])
+    ap.add_argument("--compile", action="store_true", help="oracle-gpu only: wrap the model in torch.compile")
     ap.add_argument("--workload", default="c3", choices=list(WORKLOADS))
     ap.add_argument("--batch", type=int, default=0, help="debug only: override the per-GPU batch of the workload")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
+    elif args.impl == "oracle-gpu":
+        run_oracle_gpu(args)
     else:
         run_ours(args)
 
