@@ -243,10 +243,28 @@ def run_ours(args):
         opt.step(grad_scale=scale)
         return loss
 
-    def step_e2e():
-        images = img_h.to(dev, non_blocking=True).permute(0, 3, 1, 2)
-        tokens = BatchEncoding({k: v.to(dev, non_blocking=True) for k, v in tok_h.items()})
-        return step(images, tokens).item()          # device -> host read of the loss
+    # end-to-end: every step's inputs come from pinned HOST memory.  Like any prefetching loader, the copy of step i+1 is
+    # issued on a side stream while step i computes; all K copies and K loss read-backs happen inside the timed region.
+    copy_stream = torch.cuda.Stream(device=dev)
+    pending = {}
+
+    def h2d_async():
+        copy_stream.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(copy_stream):
+            images = img_h.to(dev, non_blocking=True)
+            tokens = {k: v.to(dev, non_blocking=True) for k, v in tok_h.items()}
+        pending["batch"] = (images, tokens)
+
+    def step_e2e(prefetch_next=True):
+        if "batch" not in pending:
+            h2d_async()
+        torch.cuda.current_stream().wait_stream(copy_stream)
+        images, tokens = pending.pop("batch")
+        for t in (images, *tokens.values()):
+            t.record_stream(torch.cuda.current_stream())
+        if prefetch_next:
+            h2d_async()
+        return step(images.permute(0, 3, 1, 2), BatchEncoding(tokens)).item()          # device -> host read of the loss
 
     def barrier():
         if world > 1:
@@ -291,9 +309,15 @@ def run_ours(args):
     _lib.PROF.enable([])
 
     # ---- end-to-end: host buffers, H2D + D2H inside the timed region ----
-    step_e2e()
+    step_e2e(prefetch_next=False)
     e2e_steps = max(2, min(args.steps, 10))
-    ms_e2e = timed(step_e2e, e2e_steps)
+    e2e_count = [0]
+
+    def e2e_iter():
+        e2e_count[0] += 1
+        step_e2e(prefetch_next=e2e_count[0] < e2e_steps)     # exactly e2e_steps copies inside the timed region
+
+    ms_e2e = timed(e2e_iter, e2e_steps)
 
     if rank != 0:
         if world > 1:

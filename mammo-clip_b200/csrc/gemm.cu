@@ -372,7 +372,7 @@ extern "C" int mclip_gemm_tn(const mclip_gemm_args* g, void* stream_) {
   { const char* e = getenv("MCLIP_GEMM_DEBUG"); p.debug = e ? atoi(e) : 0; if (p.debug & 1) p.stats = nullptr; }
   p.dropmask = (const uint8_t*)g->dropmask; p.drop_scale = g->drop_scale;
   if (g->dropmask) MCLIP_REQUIRE(g->n % 16 == 0, "mclip_gemm_tn: dropout mask needs N %% 16 == 0");
-  p.small_k = (p.k_blocks == 1 && !p.b_batched && g->lda % 8 == 0 && ((uintptr_t)g->a & 15) == 0) ? 1 : 0;
+  p.small_k = (p.k_blocks == 1 && !p.b_batched && g->lda % 8 == 0 && g->a_batch_stride % 8 == 0 && ((uintptr_t)g->a & 15) == 0) ? 1 : 0;
   if (getenv("MCLIP_GEMM_NO_SMALLK")) p.small_k = 0;
   p.a_ptr = (const bf16*)g->a; p.lda = g->lda; p.a_bs = g->a_batch_stride;
   const int stage_bytes = p.small_k ? GEMM_BM * GEMM_BK * 2 : GEMM_BM * GEMM_BK * 2 + p.block_n * GEMM_BK * 2;

@@ -151,13 +151,16 @@ def test_flat_adamw_matches_torch_adamw_and_direct_grads():
         opt_b.zero_grad(set_to_none=True)
         loss_fn(**a(batch, "cuda"), is_train=True)["total"].backward()
         loss_fn(**b(batch, "cuda"), is_train=True)["total"].backward()
+        gmax = max(p.grad.abs().max().item() for p in b.parameters() if p.grad is not None)
         for (k, pa), (_, pb) in zip(a.named_parameters(), b.named_parameters()):
             if pb.grad is None:
                 assert pa.grad.abs().max().item() == 0, k
             else:
-                # step 0: identical weights -> identical gradients; later steps: bf16 rounding flips after ~1e-6 weight drift
+                # step 0: identical weights -> identical gradients; later steps: bf16 rounding flips after ~1e-6 weight drift.
+                # structurally-zero gradients (e.g. attention key bias) are pure rounding noise: absolute floor.
                 tol = 1e-5 if step == 0 else 2e-2
-                assert rel_err(pa.grad, pb.grad) < tol or (pa.grad - pb.grad).abs().max().item() < 1e-7, (step, k)
+                d = (pa.grad - pb.grad).abs().max().item()
+                assert d < tol * max(pb.grad.abs().max().item(), 1e-3 * gmax), (step, k, d)
         opt_a.step()
         opt_b.step()
         for (k, pa), (_, pb) in zip(a.named_parameters(), b.named_parameters()):
