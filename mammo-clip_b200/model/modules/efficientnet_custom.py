@@ -396,12 +396,14 @@ class EfficientNet(nn.Module):
         and the dropout multiplier of the pooled features (:312)."""
         if not (self.training and self.stochastic):
             return None, None
-        scales, nb = {}, len(self._blocks)
-        for i, blk in enumerate(self._blocks):
-            rate = DROP_CONNECT_RATE * float(i) / nb
-            if blk.geom.skip and rate > 0:
-                keep = 1.0 - rate
-                scales[i] = torch.floor(keep + torch.rand(n, device=device)) / keep
+        nb = len(self._blocks)
+        idx = [i for i, blk in enumerate(self._blocks) if blk.geom.skip and DROP_CONNECT_RATE * float(i) / nb > 0]
+        keep = getattr(self, "_dc_keep", None)
+        if keep is None or keep.device != device:
+            keep = torch.tensor([1.0 - DROP_CONNECT_RATE * float(i) / nb for i in idx], device=device).view(-1, 1)
+            object.__setattr__(self, "_dc_keep", keep)
+        allscales = torch.floor(keep + torch.rand(len(idx), n, device=device)) / keep      # one launch set for all blocks
+        scales = {i: allscales[j] for j, i in enumerate(idx)}
         p = self.geom.dropout
         mult = (torch.rand(n, self.out_dim, device=device) >= p).float() / (1.0 - p)
         return scales, mult
