@@ -241,7 +241,7 @@ __global__ void __launch_bounds__(DW_THREADS, 4) mclip_dwconv_fwd_kernel(const _
 // Per 2x4 patch a warp accumulates dW (registers, for the whole kernel) and computes the data gradient as a
 // register-window correlation of gtile with the flipped kernel (stride 1) or per parity class (stride 2).
 template <int K, int S, int TH, int TW, int DW_STAGES>
-__global__ void __launch_bounds__(DW_THREADS, 3)
+__global__ void __launch_bounds__(DW_THREADS, (K == 3) ? 4 : 3)
 mclip_dwconv_bwd_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constant__ CUtensorMap tmDy, const DwDev p) {
   constexpr int IH = (TH - 1) * S + K, IW = (TW - 1) * S + K;     // activation window (wgrad)
   constexpr int GH = (S == 1) ? TH + K - 1 : TH + (K + 1) / 2;    // dY window (dgrad)
@@ -498,8 +498,8 @@ struct DwCfg {
   static constexpr int TH = 8;                      // forward tile (outputs)
   static constexpr int TW = 16;
   static constexpr int BTH = (S == 1) ? 8 : 4;      // backward tile height
-  static constexpr int FST = 2;                     // TMA stages, forward
-  static constexpr int BST = (K == 3) ? 2 : 1;      // backward: two staged tensors; k5 keeps one stage for occupancy
+  static constexpr int FST = (K == 3) ? 2 : 1;      // TMA stages, forward (k5: one stage keeps 4 CTAs per SM)
+  static constexpr int BST = 1;                     // backward stages two tensors per tile: one stage, occupancy hides the TMA latency
 };
 
 static int dw_slots(int n_chunks, int total_tiles, int per_sm) {
