@@ -164,5 +164,9 @@ def test_flat_adamw_matches_torch_adamw_and_direct_grads():
         opt_a.step()
         opt_b.step()
         for (k, pa), (_, pb) in zip(a.named_parameters(), b.named_parameters()):
-            if pb.grad is not None:
-                assert (pa - pb).abs().max().item() < (2e-6 if step == 0 else 2e-4) + 1e-5 * pb.abs().max().item(), (step, k)
+            if pb.grad is None:
+                continue
+            if step == 0:      # identical gradients -> the two AdamW implementations must agree
+                assert (pa - pb).abs().max().item() < 2e-6 + 1e-5 * pb.abs().max().item(), (step, k)
+            else:              # Adam normalises by sqrt(v): noise-level gradients may flip sign, |delta| <= 2*lr per step
+                assert (pa - pb).abs().max().item() < 2.5e-3, (step, k)
