@@ -219,12 +219,47 @@ typedef struct mclip_bert_embed_args {
 int mclip_bert_embed_ln(const mclip_bert_embed_args* args, void* stream);
 int mclip_layernorm(const void* x_bf16, const float* gamma, const float* beta, float eps, void* out_bf16, int rows, int hidden, void* stream);
 /* qkv: bf16 [batch*seq_len, 3*heads*head_dim] (Q | K | V); attention_mask int64 [batch, seq_len] (1 = attend);
- * dropmask uint8 [batch, heads, seq_len, seq_len] or NULL; out bf16 [batch*seq_len, heads*head_dim]. */
-int mclip_bert_attention(const void* qkv, const void* attention_mask, const void* dropmask, float drop_scale, void* out,
+ * dropmask uint8 [batch, heads, seq_len, seq_len] or NULL; out bf16 [batch*seq_len, heads*head_dim];
+ * lse fp32 [batch, heads, seq_len] or NULL: log-sum-exp of the scaled masked scores, saved for the backward pass. */
+int mclip_bert_attention(const void* qkv, const void* attention_mask, const void* dropmask, float drop_scale, void* out, float* lse,
                          int batch, int seq_len, int heads, int head_dim, void* stream);
 
+/* ---- BERT text tower, backward (non-GEMM pieces) -----------------------------------------------------------------
+ * The reference trains every BERT parameter (optimizer/__init__.py:23-31 over model.parameters(); trainer_ddp.py:298-300
+ * calls backward through transformers' BertModel).  Linear data/weight gradients run on mclip_gemm_tn / mclip_gemm_wgrad /
+ * mclip_colsum; these entry points are the autograd of LayerNorm, erf-GELU, softmax attention and the embeddings. */
+/* LayerNorm backward over x_bf16 [rows, hidden] (the pre-LN input) and dy_bf16: dx (bf16), optionally also
+ * dx_drop = dx o keep-mask * drop_scale (the gradient entering the dropped sub-layer output, BertSelfOutput/BertOutput),
+ * dgamma/dbeta (+)= column sums via partials fp32 [slots][2][hidden], slots = mclip_layernorm_backward_slots(rows). */
+int mclip_layernorm_backward_slots(int rows);
+int mclip_layernorm_backward(const void* x_bf16, const void* dy_bf16, const float* gamma, float eps, const void* dropmask, float drop_scale,
+                             void* dx_bf16, void* dx_drop_bf16, float* partials, int slots, float* dgamma, float* dbeta, int accumulate,
+                             int rows, int hidden, void* stream);
+/* erf-GELU on bf16 (BertIntermediate): y = gelu(x); dx = dy * gelu'(x).  n = element count, multiple of 8. */
+int mclip_gelu_forward(const void* x_bf16, void* y_bf16, long long n, void* stream);
+int mclip_gelu_backward(const void* dy_bf16, const void* x_bf16, void* dx_bf16, long long n, void* stream);
+/* d qkv (bf16 [batch*seq_len, 3*heads*head_dim]) from d_out / out (bf16 [batch*seq_len, heads*head_dim]) and the saved lse;
+ * probabilities are recomputed per 64x64 tile; every element is written exactly once (deterministic). */
+int mclip_bert_attention_backward(const void* qkv, const void* d_out, const void* out, const float* lse, const void* attention_mask,
+                                  const void* dropmask, float drop_scale, void* dqkv, int batch, int seq_len, int heads, int head_dim,
+                                  void* stream);
+/* Embeddings backward (BertEmbeddings): LayerNorm backward of (dout o keep-mask*scale) with the pre-LN sum recomputed from
+ * the tables, then word rows (first occurrence of an id sums all its tokens in order: deterministic, no atomics),
+ * position rows < seq_len and token-type rows.  accumulate == 0 writes ONLY the touched rows: the caller provides zeroed
+ * (or previously accumulated) tables. */
+typedef struct mclip_bert_embed_bwd_args {
+  int batch, seq_len, hidden, vocab, max_positions, n_types, slots, accumulate;
+  const void* input_ids; const void* token_type_ids;      /* int64 [batch, seq_len] (token_type_ids may be NULL) */
+  const float* word; const float* pos; const float* type; const float* gamma; float eps;
+  const void* dropmask; float drop_scale;                 /* the forward's keep-mask [batch*seq_len, hidden] or NULL */
+  const void* dout;                                       /* bf16 [batch*seq_len, hidden]: gradient of the embedding output */
+  float* dv; float* partials;                             /* workspaces: fp32 [batch*seq_len, hidden], [slots][2][hidden] */
+  float* dword; float* dpos; float* dtype; float* dgamma; float* dbeta;
+} mclip_bert_embed_bwd_args;
+int mclip_bert_embed_backward(const mclip_bert_embed_bwd_args* args, void* stream);
+
 /* fp32 master weights -> bf16 GEMM operands (and their transposes for the data-gradient GEMMs), one launch per tower. */
-typedef struct mclip_prep_entry { const void* src; void* dst; void* dst_t; int rows, cols, dst_ld, pad_; } mclip_prep_entry;   /* dst_ld: row stride of dst (0: cols) */
+typedef struct mclip_prep_entry { const void* src; void* dst; void* dst_t; int rows, cols, dst_ld, dst_t_ld; } mclip_prep_entry;   /* dst_ld / dst_t_ld: row strides of dst / dst_t (0: cols / rows) */
 int mclip_weight_prep(const void* table_dev, int n_entries, void* stream);
 
 /* CLIP head helpers: cast, x/||x|| (clip.py:90-91) forward/backward, Linear bias gradient. */

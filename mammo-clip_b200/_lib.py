@@ -89,7 +89,8 @@ def check(rc: int, what: str = ""):
 
 
 # kernels launched per ABI call (for bench.py's `gpu_launches`); default 1
-LAUNCHES = {"mclip_gemm_wgrad": 2, "mclip_dwconv_backward": 2, "mclip_se_fc_backward": 2}
+LAUNCHES = {"mclip_gemm_wgrad": 2, "mclip_dwconv_backward": 2, "mclip_se_fc_backward": 2, "mclip_layernorm_backward": 2,
+            "mclip_bert_embed_backward": 4}
 
 
 class Profiler:
@@ -209,7 +210,7 @@ class EwBwdArgs(C.Structure):
 
 
 class PrepEntry(C.Structure):
-    _fields_ = [("src", C.c_void_p), ("dst", C.c_void_p), ("dst_t", C.c_void_p), ("rows", C.c_int), ("cols", C.c_int), ("dst_ld", C.c_int), ("pad_", C.c_int)]
+    _fields_ = [("src", C.c_void_p), ("dst", C.c_void_p), ("dst_t", C.c_void_p), ("rows", C.c_int), ("cols", C.c_int), ("dst_ld", C.c_int), ("dst_t_ld", C.c_int)]
 
 
 class BertEmbedArgs(C.Structure):
@@ -220,4 +221,17 @@ class BertEmbedArgs(C.Structure):
         ("gamma", C.c_void_p), ("beta", C.c_void_p), ("eps", C.c_float),
         ("dropmask", C.c_void_p), ("drop_scale", C.c_float),
         ("out", C.c_void_p),
+    ]
+
+
+class BertEmbedBwdArgs(C.Structure):
+    _fields_ = [
+        ("batch", C.c_int), ("seq_len", C.c_int), ("hidden", C.c_int), ("vocab", C.c_int), ("max_positions", C.c_int),
+        ("n_types", C.c_int), ("slots", C.c_int), ("accumulate", C.c_int),
+        ("input_ids", C.c_void_p), ("token_type_ids", C.c_void_p),
+        ("word", C.c_void_p), ("pos", C.c_void_p), ("type", C.c_void_p), ("gamma", C.c_void_p), ("eps", C.c_float),
+        ("dropmask", C.c_void_p), ("drop_scale", C.c_float),
+        ("dout", C.c_void_p),
+        ("dv", C.c_void_p), ("partials", C.c_void_p),
+        ("dword", C.c_void_p), ("dpos", C.c_void_p), ("dtype", C.c_void_p), ("dgamma", C.c_void_p), ("dbeta", C.c_void_p),
     ]

@@ -72,7 +72,7 @@ __global__ void __launch_bounds__(128) mclip_layernorm_kernel(const bf16* __rest
 #define ATT_BK 64
 __global__ void __launch_bounds__(256) mclip_bert_attention_kernel(const bf16* __restrict__ qkv, const long long* __restrict__ amask,
                                                                    const uint8_t* __restrict__ dropmask, float drop_scale, bf16* __restrict__ out,
-                                                                   int B, int L, int heads) {
+                                                                   float* __restrict__ lse, int B, int L, int heads) {
   __shared__ float Ks[ATT_BK][ATT_D + 1];
   __shared__ float Vs[ATT_BK][ATT_D + 1];
   __shared__ int kvalid[ATT_BK];
@@ -165,6 +165,8 @@ __global__ void __launch_bounds__(256) mclip_bert_attention_kernel(const bf16* _
     bf16* op = out + ((size_t)(b * L + qi)) * H + head * ATT_D + part * 16;
     *reinterpret_cast<bf16x8*>(op) = pack8(o);
     *reinterpret_cast<bf16x8*>(op + 8) = pack8(o + 8);
+    // log-sum-exp of the scaled, masked scores (saved for the backward pass); +inf for a fully masked row => p = 0 there
+    if (lse && part == 0) lse[((size_t)(b * heads + head)) * L + qi] = lsum > 0.f ? m + __logf(lsum) : INFINITY;
   }
 }
 
@@ -189,13 +191,527 @@ extern "C" int mclip_layernorm(const void* x, const float* gamma, const float* b
   return MCLIP_OK;
 }
 
-extern "C" int mclip_bert_attention(const void* qkv, const void* attention_mask, const void* dropmask, float drop_scale, void* out, int batch,
-                                    int seq_len, int heads, int head_dim, void* stream) {
+extern "C" int mclip_bert_attention(const void* qkv, const void* attention_mask, const void* dropmask, float drop_scale, void* out, float* lse,
+                                    int batch, int seq_len, int heads, int head_dim, void* stream) {
   MCLIP_REQUIRE(qkv && attention_mask && out && batch > 0 && seq_len > 0, "mclip_bert_attention: bad arguments");
   MCLIP_REQUIRE(head_dim == ATT_D, "mclip_bert_attention: head_dim %d not built (64 only)", head_dim);
   dim3 grid(ceil_div(seq_len, ATT_BQ), heads, batch);
   mclip_bert_attention_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const bf16*)qkv, (const long long*)attention_mask, (const uint8_t*)dropmask, drop_scale,
-                                                                      (bf16*)out, batch, seq_len, heads);
+                                                                      (bf16*)out, lse, batch, seq_len, heads);
+  MCLIP_CHECK_LAUNCH();
+  return MCLIP_OK;
+}
+
+// =====================================================================================================================
+// Backward pass of the text tower (what autograd runs for transformers' BertModel in the reference: every BERT parameter
+// is trained, optimizer/__init__.py:23-31).  The Linear layers' data/weight gradients go through mclip_gemm_tn /
+// mclip_gemm_wgrad; the kernels below cover LayerNorm, GELU, attention and the embedding tables.
+// =====================================================================================================================
+
+// ---- LayerNorm backward: one warp per row, 8 rows in flight per CTA, persistent over rows ------------------------------
+// x = pre-LN input (bf16), dy = gradient of the LN output.  dx = rstd*(g - mean(g) - xhat*mean(g*xhat)), g = dy*gamma.
+// dx goes out twice when a dropout keep-mask is given: plain (residual branch) and masked*scale (sub-layer branch).
+// gamma/beta gradient partials: [gridDim.x][2][H] (fixed order => deterministic), reduced by mclip_ln_param_grad_kernel.
+#define LNB_WARPS 8
+template <int H>
+__global__ void __launch_bounds__(32 * LNB_WARPS) mclip_layernorm_bwd_kernel(const bf16* __restrict__ x, const bf16* __restrict__ dy,
+                                                                             const float* __restrict__ gamma, float eps,
+                                                                             const uint8_t* __restrict__ dropmask, float drop_scale,
+                                                                             bf16* __restrict__ dx, bf16* __restrict__ dx_drop,
+                                                                             float* __restrict__ partials, int rows) {
+  constexpr int PER = H / 32;
+  __shared__ float red[LNB_WARPS][H];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float gam[PER], dg[PER], db[PER];
+#pragma unroll
+  for (int i = 0; i < PER; ++i) { gam[i] = gamma[lane + i * 32]; dg[i] = 0.f; db[i] = 0.f; }
+  for (int row = blockIdx.x * LNB_WARPS + warp; row < rows; row += gridDim.x * LNB_WARPS) {
+    float v[PER], g[PER];
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < PER; ++i) { v[i] = __bfloat162float(x[(size_t)row * H + lane + i * 32]); s += v[i]; }
+    const float mean = warp_sum(s) * (1.0f / H);
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < PER; ++i) { v[i] -= mean; q = fmaf(v[i], v[i], q); }
+    const float rstd = rsqrtf(warp_sum(q) * (1.0f / H) + eps);
+    float m1 = 0.f, m2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < PER; ++i) {
+      const float d = __bfloat162float(dy[(size_t)row * H + lane + i * 32]);
+      v[i] *= rstd;                                   // xhat
+      g[i] = d * gam[i];
+      m1 += g[i]; m2 = fmaf(g[i], v[i], m2);
+      dg[i] = fmaf(d, v[i], dg[i]); db[i] += d;
+    }
+    m1 = warp_sum(m1) * (1.0f / H); m2 = warp_sum(m2) * (1.0f / H);
+#pragma unroll
+    for (int i = 0; i < PER; ++i) {
+      const int h = lane + i * 32;
+      const float o = rstd * (g[i] - m1 - v[i] * m2);
+      dx[(size_t)row * H + h] = __float2bfloat16_rn(o);
+      if (dx_drop) dx_drop[(size_t)row * H + h] = __float2bfloat16_rn(dropmask[(size_t)row * H + h] ? o * drop_scale : 0.f);
+    }
+  }
+  // CTA reduction of the parameter-gradient accumulators, gamma then beta through the same buffer
+#pragma unroll
+  for (int pass = 0; pass < 2; ++pass) {
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < PER; ++i) red[warp][lane + i * 32] = pass == 0 ? dg[i] : db[i];
+    __syncthreads();
+    for (int h = threadIdx.x; h < H; h += 32 * LNB_WARPS) {
+      float a = 0.f;
+#pragma unroll
+      for (int w = 0; w < LNB_WARPS; ++w) a += red[w][h];
+      partials[((size_t)blockIdx.x * 2 + pass) * H + h] = a;
+    }
+  }
+}
+
+// dgamma[h] (+)= sum_slots partials[s][0][h], dbeta likewise
+__global__ void mclip_ln_param_grad_kernel(const float* __restrict__ partials, int slots, int H, float* __restrict__ dgamma, float* __restrict__ dbeta,
+                                           int accumulate) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= 2 * H) return;
+  const int which = i / H, h = i % H;
+  float a = 0.f;
+  for (int s = 0; s < slots; ++s) a += partials[((size_t)s * 2 + which) * H + h];
+  float* o = (which == 0 ? dgamma : dbeta) + h;
+  *o = accumulate ? *o + a : a;
+}
+
+// ---- erf-GELU forward/backward on bf16 (BertIntermediate, hidden_act "gelu") -------------------------------------------
+__global__ void mclip_gelu_fwd_kernel(const bf16* __restrict__ x, bf16* __restrict__ y, long long n8) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += (long long)gridDim.x * blockDim.x) {
+    float f[8];
+    unpack8(ldg_bf16x8(x + i * 8), f);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) f[e] = 0.5f * f[e] * (1.0f + erff(f[e] * 0.70710678118654752f));
+    stg_bf16x8(y + i * 8, pack8(f));
+  }
+}
+// dx = dy * (Phi(x) + x*phi(x))
+__global__ void mclip_gelu_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x, bf16* __restrict__ dx, long long n8) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += (long long)gridDim.x * blockDim.x) {
+    float f[8], g[8];
+    unpack8(ldg_bf16x8(x + i * 8), f);
+    unpack8(ldg_bf16x8(dy + i * 8), g);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const float cdf = 0.5f * (1.0f + erff(f[e] * 0.70710678118654752f));
+      const float pdf = 0.39894228040143268f * __expf(-0.5f * f[e] * f[e]);
+      g[e] *= fmaf(f[e], pdf, cdf);
+    }
+    stg_bf16x8(dx + i * 8, pack8(g));
+  }
+}
+
+// ---- attention backward: CTA = (64-token block i, head, batch) -------------------------------------------------------
+// Recomputes P = exp(S - lse) per 64x64 tile from Q, K and the saved log-sum-exp; with M = keep-mask*scale:
+//   dV = (P o M)^T dO,  dP = (dO V^T) o M,  dS = P o (dP - delta),  delta_r = <dO_r, O_r>,  dQ = dS K / 8,  dK = dS^T Q / 8.
+// CTA i accumulates dQ of its query block over all key blocks and dK/dV of its key block over all query blocks
+// (the diagonal tile serves both), so every output element is written once: no atomics, deterministic.
+#define ATB 64
+#define ATB_LD 65
+struct AttBwdSmem {
+  float Qi[ATB][ATB_LD], dOi[ATB][ATB_LD], Ki[ATB][ATB_LD], Vi[ATB][ATB_LD];
+  float X1[ATB][ATB_LD], X2[ATB][ATB_LD], Ps[ATB][ATB_LD], dSs[ATB][ATB_LD];
+  float lse_i[ATB], delta_i[ATB], lse_j[ATB], delta_j[ATB];
+  int kv_i[ATB], kv_j[ATB];
+};
+
+// Q (pre-scaled by 1/8) and dO rows of token block `blk`, their lse and delta = <dO, O>
+__device__ __forceinline__ void attb_load_q(const bf16* __restrict__ qkv, const bf16* __restrict__ dO, const bf16* __restrict__ O,
+                                            const float* __restrict__ lse, float (*Qs)[ATB_LD], float (*dOs)[ATB_LD], float* lse_s, float* delta_s,
+                                            int blk, int b, int head, int heads, int L) {
+  const int H = heads * ATT_D;
+  for (int idx = threadIdx.x; idx < ATB * (ATT_D / 8); idx += 256) {       // 8 consecutive lanes share a row
+    const int r = idx >> 3, dv = (idx & 7) * 8;
+    const int qi = blk * ATB + r;
+    float fq[8], fd[8], fo[8];
+    if (qi < L) {
+      const size_t tok = (size_t)b * L + qi;
+      unpack8(*reinterpret_cast<const bf16x8*>(qkv + tok * 3 * H + head * ATT_D + dv), fq);
+      unpack8(*reinterpret_cast<const bf16x8*>(dO + tok * H + head * ATT_D + dv), fd);
+      unpack8(*reinterpret_cast<const bf16x8*>(O + tok * H + head * ATT_D + dv), fo);
+    } else {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) fq[e] = fd[e] = fo[e] = 0.f;
+    }
+    float dl = 0.f;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) { Qs[r][dv + e] = fq[e] * 0.125f; dOs[r][dv + e] = fd[e]; dl = fmaf(fd[e], fo[e], dl); }
+    dl += __shfl_xor_sync(0xffffffffu, dl, 1);
+    dl += __shfl_xor_sync(0xffffffffu, dl, 2);
+    dl += __shfl_xor_sync(0xffffffffu, dl, 4);
+    if ((idx & 7) == 0) {
+      delta_s[r] = dl;
+      lse_s[r] = qi < L ? lse[((size_t)(b * heads + head)) * L + qi] : INFINITY;     // +inf => p = 0 for rows past L
+    }
+  }
+}
+
+__device__ __forceinline__ void attb_load_kv(const bf16* __restrict__ qkv, const long long* __restrict__ amask, float (*Ks)[ATB_LD],
+                                             float (*Vs)[ATB_LD], int* kvalid, int blk, int b, int head, int heads, int L) {
+  const int H = heads * ATT_D;
+  for (int idx = threadIdx.x; idx < ATB * (ATT_D / 8); idx += 256) {
+    const int r = idx >> 3, dv = (idx & 7) * 8;
+    const int kj = blk * ATB + r;
+    float fk[8], fv[8];
+    if (kj < L) {
+      const bf16* base = qkv + ((size_t)b * L + kj) * 3 * H + head * ATT_D + dv;
+      unpack8(*reinterpret_cast<const bf16x8*>(base + H), fk);
+      unpack8(*reinterpret_cast<const bf16x8*>(base + 2 * H), fv);
+    } else {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) fk[e] = fv[e] = 0.f;
+    }
+#pragma unroll
+    for (int e = 0; e < 8; ++e) { Ks[r][dv + e] = fk[e]; Vs[r][dv + e] = fv[e]; }
+  }
+  if (threadIdx.x < ATB) { const int kj = blk * ATB + threadIdx.x; kvalid[threadIdx.x] = (kj < L) && (amask[(size_t)b * L + kj] != 0); }
+}
+
+// One 64x64 tile: thread (ty, tx) owns queries ty+16i and keys tx+16j.  Writes Ps = P o M and dSs = dS.
+__device__ __forceinline__ void attb_tile(float (*Qs)[ATB_LD], float (*dOs)[ATB_LD], const float* lse_s, const float* delta_s, float (*Ks)[ATB_LD],
+                                          float (*Vs)[ATB_LD], const int* kvalid, float (*Ps)[ATB_LD], float (*dSs)[ATB_LD],
+                                          const uint8_t* __restrict__ dropmask, float drop_scale, int qblk, int kblk, int b, int head, int heads, int L) {
+  const int ty = threadIdx.x >> 4, tx = threadIdx.x & 15;
+  float s[4][4], dp[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { s[i][j] = 0.f; dp[i][j] = 0.f; }
+#pragma unroll 8
+  for (int d = 0; d < ATT_D; ++d) {
+    float q[4], go[4], k[4], v[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { q[i] = Qs[ty + 16 * i][d]; go[i] = dOs[ty + 16 * i][d]; }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { k[j] = Ks[tx + 16 * j][d]; v[j] = Vs[tx + 16 * j][d]; }
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) { s[i][j] = fmaf(q[i], k[j], s[i][j]); dp[i][j] = fmaf(go[i], v[j], dp[i][j]); }
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int r = ty + 16 * i, qi = qblk * ATB + r;
+    const float l = lse_s[r], dl = delta_s[r];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int c = tx + 16 * j, kj = kblk * ATB + c;
+      const float p = kvalid[c] ? __expf(s[i][j] - l) : 0.f;
+      float m = 1.0f;
+      if (dropmask && qi < L && kj < L) m = dropmask[(((size_t)(b * heads + head)) * L + qi) * L + kj] ? drop_scale : 0.f;
+      Ps[r][c] = p * m;
+      dSs[r][c] = p * (dp[i][j] * m - dl);
+    }
+  }
+}
+
+// acc[i][j] (rows ty+16i, cols tx+16j) += sum_c A[row][c] * Bm[c][col]
+__device__ __forceinline__ void attb_acc_rows(float (*A)[ATB_LD], float (*Bm)[ATB_LD], float acc[4][4]) {
+  const int ty = threadIdx.x >> 4, tx = threadIdx.x & 15;
+#pragma unroll 8
+  for (int c = 0; c < ATB; ++c) {
+    float a[4], bb[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) a[i] = A[ty + 16 * i][c];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) bb[j] = Bm[c][tx + 16 * j];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], bb[j], acc[i][j]);
+  }
+}
+// acc[i][j] (rows ty+16i, cols tx+16j) += sum_r A[r][row] * Bm[r][col]      (A transposed)
+__device__ __forceinline__ void attb_acc_cols(float (*A)[ATB_LD], float (*Bm)[ATB_LD], float acc[4][4]) {
+  const int ty = threadIdx.x >> 4, tx = threadIdx.x & 15;
+#pragma unroll 8
+  for (int r = 0; r < ATB; ++r) {
+    float a[4], bb[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) a[i] = A[r][ty + 16 * i];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) bb[j] = Bm[r][tx + 16 * j];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], bb[j], acc[i][j]);
+  }
+}
+
+__global__ void __launch_bounds__(256) mclip_bert_attention_bwd_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ dO, const bf16* __restrict__ O,
+                                                                       const float* __restrict__ lse, const long long* __restrict__ amask,
+                                                                       const uint8_t* __restrict__ dropmask, float drop_scale, bf16* __restrict__ dqkv,
+                                                                       int B, int L, int heads) {
+  extern __shared__ uint8_t attb_raw[];
+  AttBwdSmem& sm = *reinterpret_cast<AttBwdSmem*>(attb_raw);
+  const int H = heads * ATT_D;
+  const int blk = blockIdx.x, head = blockIdx.y, b = blockIdx.z;
+  const int nblk = (L + ATB - 1) / ATB;
+  const int ty = threadIdx.x >> 4, tx = threadIdx.x & 15;
+  float dq[4][4], dk[4][4], dv[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { dq[i][j] = 0.f; dk[i][j] = 0.f; dv[i][j] = 0.f; }
+  attb_load_q(qkv, dO, O, lse, sm.Qi, sm.dOi, sm.lse_i, sm.delta_i, blk, b, head, heads, L);
+  attb_load_kv(qkv, amask, sm.Ki, sm.Vi, sm.kv_i, blk, b, head, heads, L);
+  __syncthreads();
+  for (int j = 0; j < nblk; ++j) {
+    if (j == blk) {
+      attb_tile(sm.Qi, sm.dOi, sm.lse_i, sm.delta_i, sm.Ki, sm.Vi, sm.kv_i, sm.Ps, sm.dSs, dropmask, drop_scale, blk, blk, b, head, heads, L);
+      __syncthreads();
+      attb_acc_rows(sm.dSs, sm.Ki, dq);       // dQ_i += dS K_i
+      attb_acc_cols(sm.Ps, sm.dOi, dv);       // dV_i += (P o M)^T dO_i
+      attb_acc_cols(sm.dSs, sm.Qi, dk);       // dK_i += dS^T (Q_i / 8)
+      __syncthreads();
+    } else {
+      attb_load_kv(qkv, amask, sm.X1, sm.X2, sm.kv_j, j, b, head, heads, L);
+      __syncthreads();
+      attb_tile(sm.Qi, sm.dOi, sm.lse_i, sm.delta_i, sm.X1, sm.X2, sm.kv_j, sm.Ps, sm.dSs, dropmask, drop_scale, blk, j, b, head, heads, L);
+      __syncthreads();
+      attb_acc_rows(sm.dSs, sm.X1, dq);       // dQ_i += dS K_j
+      __syncthreads();
+      attb_load_q(qkv, dO, O, lse, sm.X1, sm.X2, sm.lse_j, sm.delta_j, j, b, head, heads, L);
+      __syncthreads();
+      attb_tile(sm.X1, sm.X2, sm.lse_j, sm.delta_j, sm.Ki, sm.Vi, sm.kv_i, sm.Ps, sm.dSs, dropmask, drop_scale, j, blk, b, head, heads, L);
+      __syncthreads();
+      attb_acc_cols(sm.Ps, sm.X2, dv);        // dV_i += (P o M)^T dO_j
+      attb_acc_cols(sm.dSs, sm.X1, dk);       // dK_i += dS^T (Q_j / 8)
+      __syncthreads();
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int t = blk * ATB + ty + 16 * i;
+    if (t >= L) continue;
+    bf16* base = dqkv + ((size_t)b * L + t) * 3 * H + head * ATT_D;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int d = tx + 16 * j;
+      base[d] = __float2bfloat16_rn(dq[i][j] * 0.125f);
+      base[H + d] = __float2bfloat16_rn(dk[i][j]);
+      base[2 * H + d] = __float2bfloat16_rn(dv[i][j]);
+    }
+  }
+}
+
+// ---- embeddings backward -----------------------------------------------------------------------------------------------
+// Pass 1 (one warp per token): dv = LayerNorm-backward of (dout o keep-mask*scale) with the pre-LN sum word+pos+type
+// recomputed from the tables; fp32 dv [tokens,H] + gamma/beta partials [gridDim.x][2][H].
+template <int H>
+__global__ void __launch_bounds__(32 * LNB_WARPS) mclip_bert_embed_bwd_kernel(const long long* __restrict__ ids, const long long* __restrict__ tts,
+                                                                              const float* __restrict__ word, const float* __restrict__ pos,
+                                                                              const float* __restrict__ type, const float* __restrict__ gamma, float eps,
+                                                                              const uint8_t* __restrict__ dropmask, float drop_scale,
+                                                                              const bf16* __restrict__ dout, float* __restrict__ dvout,
+                                                                              float* __restrict__ partials, int tokens, int L, int vocab) {
+  constexpr int PER = H / 32;
+  __shared__ float red[LNB_WARPS][H];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float gam[PER], dg[PER], db[PER];
+#pragma unroll
+  for (int i = 0; i < PER; ++i) { gam[i] = gamma[lane + i * 32]; dg[i] = 0.f; db[i] = 0.f; }
+  for (int tok = blockIdx.x * LNB_WARPS + warp; tok < tokens; tok += gridDim.x * LNB_WARPS) {
+    long long id = ids[tok];
+    if (id < 0 || id >= vocab) id = 0;
+    const long long tt = tts ? tts[tok] : 0;
+    const int l = tok % L;
+    float v[PER], g[PER];
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < PER; ++i) {
+      const int h = lane + i * 32;
+      v[i] = word[(size_t)id * H + h] + pos[(size_t)l * H + h] + type[(size_t)tt * H + h];
+      s += v[i];
+    }
+    const float mean = warp_sum(s) * (1.0f / H);
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < PER; ++i) { v[i] -= mean; q = fmaf(v[i], v[i], q); }
+    const float rstd = rsqrtf(warp_sum(q) * (1.0f / H) + eps);
+    float m1 = 0.f, m2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < PER; ++i) {
+      const int h = lane + i * 32;
+      float d = __bfloat162float(dout[(size_t)tok * H + h]);
+      if (dropmask) d = dropmask[(size_t)tok * H + h] ? d * drop_scale : 0.f;
+      v[i] *= rstd;
+      g[i] = d * gam[i];
+      m1 += g[i]; m2 = fmaf(g[i], v[i], m2);
+      dg[i] = fmaf(d, v[i], dg[i]); db[i] += d;
+    }
+    m1 = warp_sum(m1) * (1.0f / H); m2 = warp_sum(m2) * (1.0f / H);
+#pragma unroll
+    for (int i = 0; i < PER; ++i) dvout[(size_t)tok * H + lane + i * 32] = rstd * (g[i] - m1 - v[i] * m2);
+  }
+#pragma unroll
+  for (int pass = 0; pass < 2; ++pass) {
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < PER; ++i) red[warp][lane + i * 32] = pass == 0 ? dg[i] : db[i];
+    __syncthreads();
+    for (int h = threadIdx.x; h < H; h += 32 * LNB_WARPS) {
+      float a = 0.f;
+#pragma unroll
+      for (int w = 0; w < LNB_WARPS; ++w) a += red[w][h];
+      partials[((size_t)blockIdx.x * 2 + pass) * H + h] = a;
+    }
+  }
+}
+
+// Pass 2a: word-embedding rows.  CTA t owns token t's id iff no earlier token carries it; the owner sums dv over every
+// token with that id in token order (deterministic, no atomics) and writes the row once.
+__global__ void __launch_bounds__(256) mclip_bert_word_grad_kernel(const long long* __restrict__ ids, const float* __restrict__ dv,
+                                                                   float* __restrict__ dword, int tokens, int H, int vocab, int accumulate) {
+  const int t = blockIdx.x;
+  long long id = ids[t];
+  if (id < 0 || id >= vocab) id = 0;
+  int dup = 0;
+  for (int u = threadIdx.x; u < t; u += 256) {
+    long long o = ids[u];
+    if (o < 0 || o >= vocab) o = 0;
+    dup |= (o == id);
+  }
+  if (__syncthreads_or(dup)) return;
+  float a[4] = {0.f, 0.f, 0.f, 0.f};                      // H <= 1024: columns threadIdx.x + 256*i
+  const int lane = threadIdx.x & 31;
+  for (int u0 = t & ~31; u0 < tokens; u0 += 32) {           // every warp scans 32 ids per step, then visits the matches in order
+    const int u = u0 + lane;
+    bool match = false;
+    if (u >= t && u < tokens) {
+      long long o = ids[u];
+      if (o < 0 || o >= vocab) o = 0;
+      match = (o == id);
+    }
+    unsigned bal = __ballot_sync(0xffffffffu, match);
+    while (bal) {
+      const int uu = u0 + __ffs(bal) - 1;
+      bal &= bal - 1;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) { const int h = threadIdx.x + 256 * i; if (h < H) a[i] += dv[(size_t)uu * H + h]; }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int h = threadIdx.x + 256 * i;
+    if (h < H) { float* dst = dword + (size_t)id * H + h; *dst = accumulate ? *dst + a[i] : a[i]; }
+  }
+}
+// Pass 2b: position rows l < L (sum over the batch) and the token-type rows (sum over the tokens of each type).
+__global__ void __launch_bounds__(256) mclip_bert_pos_type_grad_kernel(const long long* __restrict__ tts, const float* __restrict__ dv,
+                                                                       float* __restrict__ dpos, float* __restrict__ dtype, int batch, int L, int H,
+                                                                       int n_types, int accumulate) {
+  const int h = blockIdx.x * 256 + threadIdx.x;
+  if (h >= H) return;
+  const int row = blockIdx.y;
+  if (row < L) {
+    float a = 0.f;
+    for (int b = 0; b < batch; ++b) a += dv[((size_t)b * L + row) * H + h];
+    float* dst = dpos + (size_t)row * H + h;
+    *dst = accumulate ? *dst + a : a;
+  } else {
+    const int ty = row - L;
+    float a = 0.f;
+    for (int u = 0; u < batch * L; ++u) {
+      const long long tt = tts ? tts[u] : 0;
+      if (tt == ty) a += dv[(size_t)u * H + h];
+    }
+    float* dst = dtype + (size_t)ty * H + h;
+    *dst = accumulate ? *dst + a : a;
+  }
+}
+
+// ---- C ABI ---------------------------------------------------------------------------------------------------------------
+extern "C" int mclip_layernorm_backward_slots(int rows) {
+  int g = ceil_div(rows, LNB_WARPS);
+  const int cap = mclip_num_sms();
+  return g < cap ? (g < 1 ? 1 : g) : cap;
+}
+
+extern "C" int mclip_layernorm_backward(const void* x, const void* dy, const float* gamma, float eps, const void* dropmask, float drop_scale, void* dx,
+                                        void* dx_drop, float* partials, int slots, float* dgamma, float* dbeta, int accumulate, int rows, int hidden,
+                                        void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  MCLIP_REQUIRE(x && dy && gamma && dx && partials && dgamma && dbeta && rows > 0, "mclip_layernorm_backward: bad arguments");
+  MCLIP_REQUIRE((dx_drop == nullptr) == (dropmask == nullptr), "mclip_layernorm_backward: dx_drop and dropmask go together");
+  MCLIP_REQUIRE(slots == mclip_layernorm_backward_slots(rows), "mclip_layernorm_backward: slots=%d, expected %d", slots, mclip_layernorm_backward_slots(rows));
+  if (hidden == 768)
+    mclip_layernorm_bwd_kernel<768><<<slots, 32 * LNB_WARPS, 0, stream>>>((const bf16*)x, (const bf16*)dy, gamma, eps, (const uint8_t*)dropmask, drop_scale,
+                                                                          (bf16*)dx, (bf16*)dx_drop, partials, rows);
+  else if (hidden == 512)
+    mclip_layernorm_bwd_kernel<512><<<slots, 32 * LNB_WARPS, 0, stream>>>((const bf16*)x, (const bf16*)dy, gamma, eps, (const uint8_t*)dropmask, drop_scale,
+                                                                          (bf16*)dx, (bf16*)dx_drop, partials, rows);
+  else { mclip_set_error("mclip_layernorm_backward: hidden size %d not built (768, 512)", hidden); return MCLIP_ERR_INVALID; }
+  MCLIP_CHECK_LAUNCH();
+  mclip_ln_param_grad_kernel<<<ceil_div(2 * hidden, 256), 256, 0, stream>>>(partials, slots, hidden, dgamma, dbeta, accumulate);
+  MCLIP_CHECK_LAUNCH();
+  return MCLIP_OK;
+}
+
+static int ew_grid(long long n, int per_block) {
+  long long g = (n + per_block - 1) / per_block;
+  const long long cap = (long long)mclip_num_sms() * 8;
+  return (int)(g < cap ? (g < 1 ? 1 : g) : cap);
+}
+
+extern "C" int mclip_gelu_forward(const void* x, void* y, long long n, void* stream) {
+  MCLIP_REQUIRE(x && y && n > 0 && n % 8 == 0, "mclip_gelu_forward: bad arguments (n must be a multiple of 8)");
+  mclip_gelu_fwd_kernel<<<ew_grid(n / 8, 256), 256, 0, (cudaStream_t)stream>>>((const bf16*)x, (bf16*)y, n / 8);
+  MCLIP_CHECK_LAUNCH();
+  return MCLIP_OK;
+}
+
+extern "C" int mclip_gelu_backward(const void* dy, const void* x, void* dx, long long n, void* stream) {
+  MCLIP_REQUIRE(dy && x && dx && n > 0 && n % 8 == 0, "mclip_gelu_backward: bad arguments (n must be a multiple of 8)");
+  mclip_gelu_bwd_kernel<<<ew_grid(n / 8, 256), 256, 0, (cudaStream_t)stream>>>((const bf16*)dy, (const bf16*)x, (bf16*)dx, n / 8);
+  MCLIP_CHECK_LAUNCH();
+  return MCLIP_OK;
+}
+
+extern "C" int mclip_bert_attention_backward(const void* qkv, const void* d_out, const void* out, const float* lse, const void* attention_mask,
+                                             const void* dropmask, float drop_scale, void* dqkv, int batch, int seq_len, int heads, int head_dim,
+                                             void* stream) {
+  MCLIP_REQUIRE(qkv && d_out && out && lse && attention_mask && dqkv && batch > 0 && seq_len > 0, "mclip_bert_attention_backward: bad arguments");
+  MCLIP_REQUIRE(head_dim == ATT_D, "mclip_bert_attention_backward: head_dim %d not built (64 only)", head_dim);
+  static int attr_set = 0;
+  if (!attr_set) {
+    MCLIP_CHECK_CUDA(cudaFuncSetAttribute(mclip_bert_attention_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(AttBwdSmem)));
+    attr_set = 1;
+  }
+  dim3 grid(ceil_div(seq_len, ATB), heads, batch);
+  mclip_bert_attention_bwd_kernel<<<grid, 256, sizeof(AttBwdSmem), (cudaStream_t)stream>>>(
+      (const bf16*)qkv, (const bf16*)d_out, (const bf16*)out, lse, (const long long*)attention_mask, (const uint8_t*)dropmask, drop_scale, (bf16*)dqkv,
+      batch, seq_len, heads);
+  MCLIP_CHECK_LAUNCH();
+  return MCLIP_OK;
+}
+
+extern "C" int mclip_bert_embed_backward(const mclip_bert_embed_bwd_args* a, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  MCLIP_REQUIRE(a && a->input_ids && a->word && a->pos && a->type && a->gamma && a->dout && a->dv && a->partials, "mclip_bert_embed_backward: null operand");
+  MCLIP_REQUIRE(a->dword && a->dpos && a->dtype && a->dgamma && a->dbeta, "mclip_bert_embed_backward: null gradient output");
+  MCLIP_REQUIRE(a->hidden == 768, "mclip_bert_embed_backward: hidden size %d not built (768 only)", a->hidden);
+  MCLIP_REQUIRE(a->seq_len <= a->max_positions, "mclip_bert_embed_backward: seq_len %d exceeds position table %d", a->seq_len, a->max_positions);
+  const int tokens = a->batch * a->seq_len;
+  MCLIP_REQUIRE(a->slots == mclip_layernorm_backward_slots(tokens), "mclip_bert_embed_backward: slots=%d, expected %d", a->slots,
+                mclip_layernorm_backward_slots(tokens));
+  mclip_bert_embed_bwd_kernel<768><<<a->slots, 32 * LNB_WARPS, 0, stream>>>(
+      (const long long*)a->input_ids, (const long long*)a->token_type_ids, a->word, a->pos, a->type, a->gamma, a->eps, (const uint8_t*)a->dropmask,
+      a->drop_scale, (const bf16*)a->dout, a->dv, a->partials, tokens, a->seq_len, a->vocab);
+  MCLIP_CHECK_LAUNCH();
+  mclip_ln_param_grad_kernel<<<ceil_div(2 * a->hidden, 256), 256, 0, stream>>>(a->partials, a->slots, a->hidden, a->dgamma, a->dbeta, a->accumulate);
+  MCLIP_CHECK_LAUNCH();
+  mclip_bert_word_grad_kernel<<<tokens, 256, 0, stream>>>((const long long*)a->input_ids, a->dv, a->dword, tokens, a->hidden, a->vocab, a->accumulate);
+  MCLIP_CHECK_LAUNCH();
+  dim3 grid(ceil_div(a->hidden, 256), a->seq_len + a->n_types);
+  mclip_bert_pos_type_grad_kernel<<<grid, 256, 0, stream>>>((const long long*)a->token_type_ids, a->dv, a->dpos, a->dtype, a->batch, a->seq_len, a->hidden,
+                                                            a->n_types, a->accumulate);
   MCLIP_CHECK_LAUNCH();
   return MCLIP_OK;
 }

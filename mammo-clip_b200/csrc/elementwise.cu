@@ -601,7 +601,7 @@ __global__ void mclip_weight_prep_kernel(const mclip_prep_entry* __restrict__ ta
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
       const bf16 v = __float2bfloat16_rn(src[i]);
       if (dst) { if (t.dst_ld > 0) dst[(i / t.cols) * t.dst_ld + i % t.cols] = v; else dst[i] = v; }
-      if (dstT) { const long long r = i / t.cols, c = i % t.cols; dstT[c * t.rows + r] = v; }
+      if (dstT) { const long long r = i / t.cols, c = i % t.cols; dstT[c * (t.dst_t_ld > 0 ? t.dst_t_ld : t.rows) + r] = v; }
     }
   }
 }
@@ -671,9 +671,37 @@ __global__ void mclip_colsum_kernel(const bf16* __restrict__ x, float* __restric
   for (int r = 0; r < rows; ++r) s += __bfloat162float(x[(size_t)r * ld + c]);
   out[c] = accumulate ? out[c] + s : s;
 }
+// 64 columns per CTA (one bf16x2 per lane), 16 warps stride the rows, fixed-order smem reduction (deterministic)
+#define COLSUM_WARPS 16
+__global__ void __launch_bounds__(32 * COLSUM_WARPS) mclip_colsum2_kernel(const bf16* __restrict__ x, float* __restrict__ out, int rows, int cols, long long ld,
+                                                                          int accumulate) {
+  __shared__ float red[COLSUM_WARPS][64];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int c = blockIdx.x * 64 + lane * 2;
+  float s0 = 0.f, s1 = 0.f;
+  if (c < cols) {
+#pragma unroll 4
+    for (int r = warp; r < rows; r += COLSUM_WARPS) {
+      const uint32_t w = *reinterpret_cast<const uint32_t*>(x + (size_t)r * ld + c);
+      s0 += bf16_lo(w); s1 += bf16_hi(w);
+    }
+  }
+  red[warp][lane * 2] = s0; red[warp][lane * 2 + 1] = s1;
+  __syncthreads();
+  if (threadIdx.x < 64 && blockIdx.x * 64 + threadIdx.x < cols) {
+    float a = 0.f;
+#pragma unroll
+    for (int w = 0; w < COLSUM_WARPS; ++w) a += red[w][threadIdx.x];
+    float* o = out + blockIdx.x * 64 + threadIdx.x;
+    *o = accumulate ? *o + a : a;
+  }
+}
 extern "C" int mclip_colsum(const void* x, float* out, int rows, int cols, long long ld, int accumulate, void* stream) {
   MCLIP_REQUIRE(x && out && rows > 0 && cols > 0, "mclip_colsum: bad arguments");
-  mclip_colsum_kernel<<<ceil_div(cols, 128), 128, 0, (cudaStream_t)stream>>>((const bf16*)x, out, rows, cols, ld, accumulate);
+  if (cols % 2 == 0 && ld % 2 == 0 && ((uintptr_t)x & 3) == 0)
+    mclip_colsum2_kernel<<<ceil_div(cols, 64), 32 * COLSUM_WARPS, 0, (cudaStream_t)stream>>>((const bf16*)x, out, rows, cols, ld, accumulate);
+  else
+    mclip_colsum_kernel<<<ceil_div(cols, 128), 128, 0, (cudaStream_t)stream>>>((const bf16*)x, out, rows, cols, ld, accumulate);
   MCLIP_CHECK_LAUNCH();
   return MCLIP_OK;
 }

@@ -1,24 +1,23 @@
-"""BERT encoder forward on the sm_100a kernels (embedding+LayerNorm, tcgen05 Linear GEMMs with fused
-bias / GELU / dropout / residual epilogues, masked-softmax attention, LayerNorm), for a Hugging Face `BertModel`
-parameter container (names and shapes untouched, so checkpoints and DDP see the same parameters).
+"""BERT encoder forward AND backward on the sm_100a kernels (embedding+LayerNorm, tcgen05 Linear GEMMs with fused
+bias / GELU / dropout / residual epilogues, masked-softmax attention, LayerNorm and their gradients), for a Hugging Face
+`BertModel` parameter container (names and shapes untouched, so checkpoints and DDP see the same parameters).
 
 Forward = what `BertModel(**tokens)["last_hidden_state"]` computes in the reference (text_encoder.py:47-49; transformers
 modeling_bert.py BertEmbeddings / BertSelfAttention / BertSelfOutput / BertIntermediate / BertOutput), the unused pooler
 excepted.  Dropout (p = 0.1 in train mode) uses explicit keep-masks so that the backward pass sees the same draws.
 
-Backward (phase 1, SURVEY §0 "text tower" row): the reference trains every BERT parameter, the north star names only the
-text *forward* for hand-written kernels; gradients are obtained by re-running the layer stack through PyTorch autograd with
-the same dropout masks (`_bert_torch`).  BERT backward kernels are the first "next" row of SURVEY §8(f)."""
-import math
-
+Backward = the autograd of that graph (the reference trains every BERT parameter, optimizer/__init__.py:23-31), written
+out by hand on the same library: LayerNorm / GELU / attention / embedding backward kernels (csrc/bert.cu), data gradients
+on `mclip_gemm_tn` with transposed bf16 weights, weight gradients on `mclip_gemm_wgrad`, bias gradients on `mclip_colsum`.
+With a `FlatAdamW` attached, parameter gradients are written straight into the flat gradient buffer."""
 import torch
-import torch.nn.functional as F
 
 from ... import ops
 
 
 class _BertWeights:
-    """bf16 copies of the Linear weights (QKV fused into one [3H,H] operand), refreshed once per forward."""
+    """bf16 copies of the Linear weights (QKV fused into one [3H,H] operand) and their transposes for the data-gradient
+    GEMMs, refreshed once per forward by one table-driven kernel."""
 
     def __init__(self, bert):
         self.key = None
@@ -33,15 +32,19 @@ class _BertWeights:
         entries, self.layers = [], []
         for layer in bert.encoder.layer:
             a, so, it, ou = layer.attention.self, layer.attention.output, layer.intermediate, layer.output
-            h = a.query.weight.shape[0]
-            qkv = torch.empty((3 * h, a.query.weight.shape[1]), dtype=torch.bfloat16, device=dev)
+            h, hin = a.query.weight.shape
+            qkv = torch.empty((3 * h, hin), dtype=torch.bfloat16, device=dev)
+            qkv_t = torch.empty((hin, 3 * h), dtype=torch.bfloat16, device=dev)         # [in, 3*out]: B operand of dX = dQKV @ Wqkv
             for i, lin in enumerate((a.query, a.key, a.value)):
-                entries.append((lin.weight.detach(), qkv[i * h:(i + 1) * h], None))
+                entries.append((lin.weight.detach(), qkv[i * h:(i + 1) * h], qkv_t[:, i * h:(i + 1) * h], 0, 3 * h))
             wo = torch.empty_like(so.dense.weight, dtype=torch.bfloat16)
             w1 = torch.empty_like(it.dense.weight, dtype=torch.bfloat16)
             w2 = torch.empty_like(ou.dense.weight, dtype=torch.bfloat16)
-            entries += [(so.dense.weight.detach(), wo, None), (it.dense.weight.detach(), w1, None), (ou.dense.weight.detach(), w2, None)]
-            self.layers.append(dict(qkv=qkv, wo=wo, w1=w1, w2=w2))
+            wo_t = torch.empty(so.dense.weight.shape[::-1], dtype=torch.bfloat16, device=dev)
+            w1_t = torch.empty(it.dense.weight.shape[::-1], dtype=torch.bfloat16, device=dev)
+            w2_t = torch.empty(ou.dense.weight.shape[::-1], dtype=torch.bfloat16, device=dev)
+            entries += [(so.dense.weight.detach(), wo, wo_t), (it.dense.weight.detach(), w1, w1_t), (ou.dense.weight.detach(), w2, w2_t)]
+            self.layers.append(dict(qkv=qkv, wo=wo, w1=w1, w2=w2, qkv_t=qkv_t, wo_t=wo_t, w1_t=w1_t, w2_t=w2_t))
         self.entries = entries
         self.table = ops.weight_prep(entries, dev)
         self.key = self._key(bert)
@@ -63,18 +66,27 @@ def _weights(bert):
 def _make_masks(bert, b, l, device):
     cfg = bert.config
     p_h, p_a = cfg.hidden_dropout_prob, cfg.attention_probs_dropout_prob
-    hdim, heads = cfg.hidden_size, cfg.num_attention_heads
+    hdim, heads, nl = cfg.hidden_size, cfg.num_attention_heads, len(bert.encoder.layer)
 
+    # one draw per mask family for the whole tower (3 launches instead of 3 per layer)
     def keep(shape, p):
         return (torch.rand(shape, device=device) >= p).to(torch.uint8) if p > 0 else None
 
-    masks = {"emb": keep((b * l, hdim), p_h), "layers": []}
-    for _ in bert.encoder.layer:
-        masks["layers"].append({"probs": keep((b, heads, l, l), p_a), "attn_out": keep((b * l, hdim), p_h), "ffn_out": keep((b * l, hdim), p_h)})
+    hid = keep((2 * nl + 1, b * l, hdim), p_h)
+    att = keep((nl, b, heads, l, l), p_a)
+    masks = {"emb": hid[2 * nl] if hid is not None else None, "layers": []}
+    for i in range(nl):
+        masks["layers"].append({"probs": att[i] if att is not None else None,
+                                "attn_out": hid[2 * i] if hid is not None else None,
+                                "ffn_out": hid[2 * i + 1] if hid is not None else None})
     return masks
 
 
-def _kernel_forward(bert, ids, tts, amask, masks):
+_NO_MASKS = {"probs": None, "attn_out": None, "ffn_out": None}
+
+
+def _kernel_forward(bert, ids, tts, amask, masks, save=None):
+    """-> x [B*L, H] bf16.  `save`: list that receives, per layer, the activations the backward pass needs."""
     cfg = bert.config
     b, l = ids.shape
     hdim, heads = cfg.hidden_size, cfg.num_attention_heads
@@ -89,73 +101,124 @@ def _kernel_forward(bert, ids, tts, amask, masks):
     for i, layer in enumerate(bert.encoder.layer):
         a, so, it, ou = layer.attention.self, layer.attention.output, layer.intermediate, layer.output
         lw = w.layers[i]
-        mk = masks["layers"][i] if masks else {"probs": None, "attn_out": None, "ffn_out": None}
+        mk = masks["layers"][i] if masks else _NO_MASKS
         bqkv = torch.cat([a.query.bias, a.key.bias, a.value.bias]).detach()
         qkv = ops.gemm_tn(x, lw["qkv"], bias=bqkv)
-        ctx = ops.bert_attention(qkv, amask, b, l, heads, hdim // heads, mk["probs"], sa)
+        if save is not None:
+            ctx, lse = ops.bert_attention(qkv, amask, b, l, heads, hdim // heads, mk["probs"], sa, want_lse=True)
+        else:
+            ctx = ops.bert_attention(qkv, amask, b, l, heads, hdim // heads, mk["probs"], sa)
         h1 = ops.gemm_tn(ctx, lw["wo"], bias=so.dense.bias.detach(), residual=x, dropmask=mk["attn_out"], drop_scale=sh)
         x1 = ops.layernorm(h1, so.LayerNorm.weight, so.LayerNorm.bias, eps)
-        inter = ops.gemm_tn(x1, lw["w1"], bias=it.dense.bias.detach(), act=1)
+        if save is not None:
+            # pre-activation kept for GELU' (BertIntermediate); the activation runs as its own pass on the bf16 value
+            pre = ops.gemm_tn(x1, lw["w1"], bias=it.dense.bias.detach())
+            inter = ops.gelu_forward(pre)
+        else:
+            pre, inter = None, ops.gemm_tn(x1, lw["w1"], bias=it.dense.bias.detach(), act=1)
         h2 = ops.gemm_tn(inter, lw["w2"], bias=ou.dense.bias.detach(), residual=x1, dropmask=mk["ffn_out"], drop_scale=sh)
-        x = ops.layernorm(h2, ou.LayerNorm.weight, ou.LayerNorm.bias, eps)
-    return x.view(b, l, hdim)
+        x_out = ops.layernorm(h2, ou.LayerNorm.weight, ou.LayerNorm.bias, eps)
+        if save is not None:
+            save.append(dict(x=x, qkv=qkv, lse=lse, ctx=ctx, h1=h1, x1=x1, pre=pre, inter=inter, h2=h2))
+        x = x_out
+    return x
 
 
-def _bert_torch(bert, ids, tts, amask, masks):
-    """The same function in PyTorch ops with explicit dropout masks (autograd recompute path for the backward)."""
+def _kernel_backward(bert, ids, tts, amask, masks, saved, dout, G, accumulate):
+    """dout: [B*L, H] bf16, gradient of the last hidden state.  G(param) -> the tensor that receives d/d param (written, or
+    added to when `accumulate`).  Returns {id(param): gradient tensor}."""
     cfg = bert.config
     b, l = ids.shape
     hdim, heads = cfg.hidden_size, cfg.num_attention_heads
-    d = hdim // heads
+    eps = cfg.layer_norm_eps
     sh = 1.0 / (1.0 - cfg.hidden_dropout_prob) if masks else 1.0
     sa = 1.0 / (1.0 - cfg.attention_probs_dropout_prob) if masks else 1.0
-    emb = bert.embeddings
-    pos = torch.arange(l, device=ids.device)
-    x = emb.word_embeddings(ids) + emb.position_embeddings(pos)[None] + emb.token_type_embeddings(tts if tts is not None else torch.zeros_like(ids))
-    x = emb.LayerNorm(x)
-    if masks and masks["emb"] is not None:
-        x = x * (masks["emb"].view(b, l, hdim) * sh)
-    bias = (1.0 - amask[:, None, None, :].to(x.dtype)) * torch.finfo(torch.float32).min
-    for i, layer in enumerate(bert.encoder.layer):
+    w = _weights(bert)
+    grads = {}
+
+    def out(param):
+        g = G(param)
+        grads[id(param)] = g
+        return g
+
+    def linear_grads(lin, dy, xin):
+        """dW = dy^T xin, db = column sums of dy (dy may be a column slice of a wider tensor)."""
+        ops.gemm_wgrad(dy, xin, out=out(lin.weight), accumulate=accumulate)
+        ops.colsum(dy, out(lin.bias), accumulate=accumulate)
+
+    dx = dout
+    for i in reversed(range(len(bert.encoder.layer))):
+        layer = bert.encoder.layer[i]
         a, so, it, ou = layer.attention.self, layer.attention.output, layer.intermediate, layer.output
-        mk = masks["layers"][i] if masks else {"probs": None, "attn_out": None, "ffn_out": None}
-
-        def split(t):
-            return t.view(b, l, heads, d).transpose(1, 2)
-
-        q, k, v = split(a.query(x)), split(a.key(x)), split(a.value(x))
-        p = torch.softmax((q @ k.transpose(-1, -2)).float() / math.sqrt(d) + bias, dim=-1).to(v.dtype)
-        if mk["probs"] is not None:
-            p = p * (mk["probs"] * sa).to(p.dtype)
-        ctx = (p @ v).transpose(1, 2).reshape(b, l, hdim)
-        h = so.dense(ctx)
-        if mk["attn_out"] is not None:
-            h = h * (mk["attn_out"].view(b, l, hdim) * sh).to(h.dtype)
-        x1 = so.LayerNorm(h + x)
-        o = ou.dense(F.gelu(it.dense(x1)))
-        if mk["ffn_out"] is not None:
-            o = o * (mk["ffn_out"].view(b, l, hdim) * sh).to(o.dtype)
-        x = ou.LayerNorm(o + x1)
-    return x
+        lw, S = w.layers[i], saved[i]
+        mk = masks["layers"][i] if masks else _NO_MASKS
+        # BertOutput: x_out = LN(dropout(dense(inter)) + x1)
+        dh2, dh2d = ops.layernorm_backward(S["h2"], dx, ou.LayerNorm.weight, eps, out(ou.LayerNorm.weight), out(ou.LayerNorm.bias),
+                                           dropmask=mk["ffn_out"], drop_scale=sh, accumulate=accumulate)
+        d_inter = ops.gemm_tn(dh2d, lw["w2_t"])
+        linear_grads(ou.dense, dh2d, S["inter"])
+        # BertIntermediate: inter = gelu(dense(x1))
+        d_pre = ops.gelu_backward(d_inter, S["pre"])
+        dx1 = ops.gemm_tn(d_pre, lw["w1_t"], residual=dh2)
+        linear_grads(it.dense, d_pre, S["x1"])
+        # BertSelfOutput: x1 = LN(dropout(dense(ctx)) + x)
+        dh1, dh1d = ops.layernorm_backward(S["h1"], dx1, so.LayerNorm.weight, eps, out(so.LayerNorm.weight), out(so.LayerNorm.bias),
+                                           dropmask=mk["attn_out"], drop_scale=sh, accumulate=accumulate)
+        d_ctx = ops.gemm_tn(dh1d, lw["wo_t"])
+        linear_grads(so.dense, dh1d, S["ctx"])
+        # BertSelfAttention
+        dqkv = ops.bert_attention_backward(S["qkv"], d_ctx, S["ctx"], S["lse"], amask, b, l, heads, hdim // heads, mk["probs"], sa)
+        dx = ops.gemm_tn(dqkv, lw["qkv_t"], residual=dh1)
+        for j, lin in enumerate((a.query, a.key, a.value)):
+            linear_grads(lin, dqkv[:, j * hdim:(j + 1) * hdim], S["x"])
+        saved[i] = None
+    emb = bert.embeddings
+    ops.bert_embed_backward(ids, tts, emb.word_embeddings.weight, emb.position_embeddings.weight, emb.token_type_embeddings.weight,
+                            emb.LayerNorm.weight, eps, dx, out(emb.word_embeddings.weight), out(emb.position_embeddings.weight),
+                            out(emb.token_type_embeddings.weight), out(emb.LayerNorm.weight), out(emb.LayerNorm.bias),
+                            dropmask=masks["emb"] if masks else None, drop_scale=sh, accumulate=accumulate)
+    return grads
 
 
 class _BertFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, bert, ids, tts, amask, masks, *params):
-        out = _kernel_forward(bert, ids, tts, amask, masks)
-        ctx.bert, ctx.args = bert, (ids, tts, amask, masks)
-        return out.float()
+    def forward(ctx, owner, bert, ids, tts, amask, masks, need_grad, *params):
+        saved = [] if need_grad else None
+        out = _kernel_forward(bert, ids, tts, amask, masks, save=saved)
+        ctx.owner, ctx.bert, ctx.args, ctx.saved = owner, bert, (ids, tts, amask, masks), saved
+        return out.view(ids.shape[0], ids.shape[1], -1).float()
 
     @staticmethod
     def backward(ctx, dout):
-        bert = ctx.bert
+        bert, owner = ctx.bert, ctx.owner
         ids, tts, amask, masks = ctx.args
-        params = [p for p in bert.parameters() if not _is_pooler(bert, p)]
-        with torch.enable_grad(), torch.autocast("cuda", dtype=torch.bfloat16):
-            out = _bert_torch(bert, ids, tts, amask, masks)
-        grads = torch.autograd.grad(out, params, dout.to(out.dtype), allow_unused=True)
-        gmap = {id(p): g for p, g in zip(params, grads)}
-        return (None, None, None, None, None, *[gmap.get(id(p)) for p in bert.parameters()])
+        if ctx.saved is None:
+            raise RuntimeError("mammoclip_b200 BERT: backward called on a forward that ran without gradient tracking")
+        trainable = [p for p in bert.parameters() if not _is_pooler(bert, p)]
+        # direct mode: a FlatAdamW owns zeroed flat `.grad` views and this is the tower's first backward since zero_grad():
+        # the kernels write there and autograd has nothing left to accumulate (second backward of a step, e.g. the MVS loss'
+        # second text: ordinary returned gradients)
+        opt = getattr(owner, "_flat_optimizer", None) if owner is not None else None
+        direct = opt is not None and opt.zero_count != getattr(owner, "_direct_written_at", -1) and all(p.grad is not None for p in trainable)
+
+        def G(param):
+            if direct:
+                return param.grad
+            # embedding tables are only written where touched: start from zeros
+            return torch.zeros_like(param) if _is_table(bert, param) else torch.empty_like(param)
+
+        d2 = ops.cast_bf16(dout.contiguous().float().view(-1, dout.shape[-1]))
+        grads = _kernel_backward(bert, ids, tts, amask, masks, ctx.saved, d2, G, accumulate=False)
+        ctx.saved = None
+        if direct:
+            owner._direct_written_at = opt.zero_count
+            return (None,) * (7 + len(list(bert.parameters())))
+        return (None, None, None, None, None, None, None, *[grads.get(id(p)) for p in bert.parameters()])
+
+
+def _is_table(bert, p):
+    e = bert.embeddings
+    return p is e.word_embeddings.weight or p is e.position_embeddings.weight or p is e.token_type_embeddings.weight
 
 
 def _is_pooler(bert, p):
@@ -163,8 +226,9 @@ def _is_pooler(bert, p):
     return pool is not None and any(p is q for q in pool.parameters())
 
 
-def bert_forward(bert, input_ids, token_type_ids, attention_mask, training):
-    """-> last_hidden_state [B, L, H] fp32 (differentiable w.r.t. the BertModel parameters)."""
+def bert_forward(bert, input_ids, token_type_ids, attention_mask, training, owner=None):
+    """-> last_hidden_state [B, L, H] fp32 (differentiable w.r.t. the BertModel parameters).  `owner`: the module a
+    FlatAdamW may have been attached to (direct gradient writes)."""
     ids = input_ids.contiguous()
     tts = token_type_ids.contiguous() if token_type_ids is not None else None
     amask = attention_mask.contiguous().long()
@@ -173,4 +237,6 @@ def bert_forward(bert, input_ids, token_type_ids, attention_mask, training):
         raise NotImplementedError("the B200 text tower is built for BERT-base geometry (hidden 768, head dim 64, erf-GELU)")
     use_drop = training and (cfg.hidden_dropout_prob > 0 or cfg.attention_probs_dropout_prob > 0)
     masks = _make_masks(bert, ids.shape[0], ids.shape[1], ids.device) if use_drop else None
-    return _BertFn.apply(bert, ids, tts, amask, masks, *bert.parameters())
+    params = list(bert.parameters())
+    need_grad = torch.is_grad_enabled() and any(p.requires_grad for p in params)
+    return _BertFn.apply(owner, bert, ids, tts, amask, masks, need_grad, *params)

@@ -1,8 +1,8 @@
 """Text tower with the reference's contract (text_encoder.py:5-49): parameters live under `.text_encoder.*` with the
 Hugging Face BERT names, `out_dim = hidden_size`, `forward(BatchEncoding) -> last_hidden_state [B,L,H]`.
 
-Forward on CUDA runs the hand-written kernels of `bert_kernels.py` (embedding+LayerNorm, tcgen05 QKV/out/FFN GEMMs with
-fused bias/GELU/residual epilogues, masked softmax attention); see that module for the backward path."""
+Forward and backward on CUDA run the hand-written kernels of `bert_kernels.py` (embedding+LayerNorm, tcgen05 QKV/out/FFN
+GEMMs with fused bias/GELU/residual epilogues, masked softmax attention, and their gradients)."""
 import torch
 from torch import nn
 from transformers import AutoConfig, BertModel
@@ -34,10 +34,11 @@ class HuggingfaceTextEncoder(nn.Module):
             raise NotImplementedError("the B200 text tower implements the BERT architecture only")
         self.out_dim = self.text_encoder.config.hidden_size
         self.use_kernels = True
+        self._mclip_direct_grads = True      # FlatAdamW.attach(): the backward may write gradients straight into the flat buffer
 
     def forward(self, x):
         ids = x["input_ids"]
         if not ids.is_cuda:
             raise RuntimeError("mammoclip_b200 text encoder runs on a B200 only (no CPU fallback)")
         from . import bert_kernels
-        return bert_kernels.bert_forward(self.text_encoder, x["input_ids"], x.get("token_type_ids"), x["attention_mask"], self.training)
+        return bert_kernels.bert_forward(self.text_encoder, x["input_ids"], x.get("token_type_ids"), x["attention_mask"], self.training, owner=self)

@@ -359,7 +359,7 @@ def bn_bwd_finalize(partials, count, training, dgamma, dbeta):
 
 
 def weight_prep(entries, device, dst_ld=0):
-    """entries: list of (src fp32 2-D, dst bf16 or None, dst_t bf16 or None[, dst_ld]). Returns the device table (keep it alive)."""
+    """entries: list of (src fp32 2-D, dst bf16 or None, dst_t bf16 or None[, dst_ld[, dst_t_ld]]). Returns the device table (keep it alive)."""
     import numpy as np
     arr = (PrepEntry * len(entries))()
     for i, e in enumerate(entries):
@@ -367,6 +367,7 @@ def weight_prep(entries, device, dst_ld=0):
         arr[i].src, arr[i].dst, arr[i].dst_t = src.data_ptr(), _p(dst), _p(dst_t)
         arr[i].rows, arr[i].cols = src.shape[0], src[0].numel()
         arr[i].dst_ld = e[3] if len(e) > 3 else dst_ld
+        arr[i].dst_t_ld = e[4] if len(e) > 4 else 0
     raw = np.frombuffer(bytes(arr), dtype=np.uint8).copy()
     return torch.from_numpy(raw).to(device)
 
@@ -396,9 +397,10 @@ def l2norm_backward(e, de, nrm):
     return dx
 
 
-def colsum(x, out):
+def colsum(x, out, accumulate=False):
     rows, cols = x.shape
-    call("mclip_colsum", ptr(x), ptr(out), rows, cols, C.c_longlong(x.stride(0)), 0)
+    assert x.stride(1) == 1
+    call("mclip_colsum", ptr(x), ptr(out), rows, cols, C.c_longlong(x.stride(0)), int(accumulate))
     return out
 
 
@@ -431,7 +433,61 @@ def layernorm(x, gamma, beta, eps):
     return out
 
 
-def bert_attention(qkv, attention_mask, batch, seq_len, heads, head_dim, dropmask=None, drop_scale=1.0):
+def bert_attention(qkv, attention_mask, batch, seq_len, heads, head_dim, dropmask=None, drop_scale=1.0, want_lse=False):
     out = torch.empty((batch * seq_len, heads * head_dim), dtype=torch.bfloat16, device=qkv.device)
-    call("mclip_bert_attention", ptr(qkv), ptr(attention_mask), ptr(dropmask), C.c_float(drop_scale), ptr(out), batch, seq_len, heads, head_dim)
+    lse = torch.empty((batch, heads, seq_len), dtype=torch.float32, device=qkv.device) if want_lse else None
+    call("mclip_bert_attention", ptr(qkv), ptr(attention_mask), ptr(dropmask), C.c_float(drop_scale), ptr(out), ptr(lse), batch, seq_len, heads, head_dim)
+    return (out, lse) if want_lse else out
+
+
+# ------------------------------------------------------------------------------------------------ BERT backward pieces
+from ._lib import BertEmbedBwdArgs  # noqa: E402
+
+
+def layernorm_backward(x, dy, gamma, eps, dgamma, dbeta, dropmask=None, drop_scale=1.0, accumulate=False):
+    """x (pre-LN input), dy: [rows,H] bf16.  Returns (dx, dx_drop); dx_drop is dx when no mask is given.  dgamma/dbeta are written (or +=)."""
+    rows, h = x.shape
+    assert x.is_contiguous() and dy.is_contiguous() and dy.shape == x.shape and dy.dtype == torch.bfloat16
+    dx = torch.empty_like(x)
+    dxd = torch.empty_like(x) if dropmask is not None else None
+    slots = lib().mclip_layernorm_backward_slots(rows)
+    part = torch.empty((slots, 2, h), dtype=torch.float32, device=x.device)
+    call("mclip_layernorm_backward", ptr(x), ptr(dy), ptr(gamma), C.c_float(eps), ptr(dropmask), C.c_float(drop_scale), ptr(dx), ptr(dxd), ptr(part), slots,
+         ptr(dgamma), ptr(dbeta), int(accumulate), rows, h)
+    return dx, (dxd if dxd is not None else dx)
+
+
+def gelu_forward(x):
+    out = torch.empty_like(x)
+    call("mclip_gelu_forward", ptr(x), ptr(out), C.c_longlong(x.numel()))
     return out
+
+
+def gelu_backward(dy, x):
+    out = torch.empty_like(x)
+    call("mclip_gelu_backward", ptr(dy), ptr(x), ptr(out), C.c_longlong(x.numel()))
+    return out
+
+
+def bert_attention_backward(qkv, d_out, out, lse, attention_mask, batch, seq_len, heads, head_dim, dropmask=None, drop_scale=1.0):
+    dqkv = torch.empty_like(qkv)
+    call("mclip_bert_attention_backward", ptr(qkv), ptr(d_out), ptr(out), ptr(lse), ptr(attention_mask), ptr(dropmask), C.c_float(drop_scale), ptr(dqkv),
+         batch, seq_len, heads, head_dim)
+    return dqkv
+
+
+def bert_embed_backward(ids, tts, word, pos, typ, gamma, eps, dout, dword, dpos, dtype, dgamma, dbeta, dropmask=None, drop_scale=1.0, accumulate=False):
+    """dout: [B*L,H] bf16.  Writes (accumulate=False: touched rows only, the tables must be zeroed) or adds the embedding-table gradients."""
+    b, l = ids.shape
+    h = word.shape[1]
+    a = BertEmbedBwdArgs()
+    a.batch, a.seq_len, a.hidden, a.vocab, a.max_positions, a.n_types = b, l, h, word.shape[0], pos.shape[0], typ.shape[0]
+    a.slots, a.accumulate = lib().mclip_layernorm_backward_slots(b * l), int(accumulate)
+    dv = torch.empty((b * l, h), dtype=torch.float32, device=ids.device)
+    part = torch.empty((a.slots, 2, h), dtype=torch.float32, device=ids.device)
+    a.input_ids, a.token_type_ids = ids.data_ptr(), _p(tts)
+    a.word, a.pos, a.type, a.gamma, a.eps = word.data_ptr(), pos.data_ptr(), typ.data_ptr(), gamma.data_ptr(), eps
+    a.dropmask, a.drop_scale, a.dout = _p(dropmask), drop_scale, dout.data_ptr()
+    a.dv, a.partials = dv.data_ptr(), part.data_ptr()
+    a.dword, a.dpos, a.dtype, a.dgamma, a.dbeta = dword.data_ptr(), dpos.data_ptr(), dtype.data_ptr(), dgamma.data_ptr(), dbeta.data_ptr()
+    call("mclip_bert_embed_backward", C.byref(a))

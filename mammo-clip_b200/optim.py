@@ -35,7 +35,7 @@ class FlatAdamW:
         """Modules whose backward may write gradients straight into the flat buffer (first backward after each zero_grad)."""
         for m in modules:
             for sub in m.modules():
-                if hasattr(sub, "_wcache") and hasattr(sub, "geom"):
+                if (hasattr(sub, "_wcache") and hasattr(sub, "geom")) or getattr(sub, "_mclip_direct_grads", False):
                     object.__setattr__(sub, "_flat_optimizer", self)
         return self
 

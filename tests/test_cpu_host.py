@@ -18,7 +18,7 @@ def test_library_builds_and_exports_every_declared_symbol():
     assert len(names) > 25
     for n in names:
         assert hasattr(lib, n), f"{n} declared in include/mclip.h but not exported by libmclip_b200.so"
-    assert lib.mclip_version() >= 1
+    assert lib.mclip_version() >= 2
     assert lib.mclip_loss_workspace_bytes(8, 64, 512, 1) > 0
 
 
@@ -27,7 +27,8 @@ def test_ctypes_structs_match_the_header(tmp_path):
     pairs = [("mclip_loss_args", _lib.LossArgs), ("mclip_gemm_args", _lib.GemmArgs), ("mclip_wgrad_args", _lib.WgradArgs),
              ("mclip_dwconv_args", _lib.DwconvArgs), ("mclip_stem_args", _lib.StemArgs), ("mclip_bn_args", _lib.BnArgs),
              ("mclip_ew_args", _lib.EwArgs), ("mclip_se_args", _lib.SeArgs), ("mclip_ew_bwd_args", _lib.EwBwdArgs),
-             ("mclip_prep_entry", _lib.PrepEntry), ("mclip_bert_embed_args", _lib.BertEmbedArgs)]
+             ("mclip_prep_entry", _lib.PrepEntry), ("mclip_bert_embed_args", _lib.BertEmbedArgs),
+             ("mclip_bert_embed_bwd_args", _lib.BertEmbedBwdArgs)]
     src = '#include "include/mclip.h"\n#include <stdio.h>\n#include <stddef.h>\nint main(){' + \
         "".join(f'printf("%zu\\n", sizeof({c}));' for c, _ in pairs) + \
         'printf("%zu\\n", offsetof(mclip_loss_args, out)); printf("%zu\\n", offsetof(mclip_gemm_args, stats)); return 0;}'
