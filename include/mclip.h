@@ -68,7 +68,7 @@ int mclip_ipc_close_handle(void* p);
  * "pointwise" convolution of MBConv in NHWC (efficientnet_custom.py:105 _expand_conv, :122 _project_conv, :283
  * _conv_head; m = pixel, k = Cin, n = Cout), its data gradient (B = transposed weight), and every nn.Linear of the
  * text tower / projection heads (text_encoder.py:48 -> transformers BertModel; projection.py:28).
- * epi: + bias[n]; act 1 = erf-GELU; + residual[b,m,n]; optional per-column (sum, sum of squares) partials of the
+ * epi: + bias[n]; (optional bf16 copy of the pre-activation); act 1 = erf-GELU; + residual[b,m,n]; optional per-column (sum, sum of squares) partials of the
  * bf16-rounded output for train-mode BatchNorm (efficientnet_custom.py:106,123): stats[stat_slots][2][n]. */
 typedef struct mclip_gemm_args {
   const void* a; long long lda, a_batch_stride;   /* bf16 [batches, m, k], row stride lda (elements) */
@@ -80,6 +80,8 @@ typedef struct mclip_gemm_args {
   int act;                                        /* 0 none, 1 erf-GELU */
   float* stats; int stat_slots;                   /* NULL, or fp32 [stat_slots][2][n] with stat_slots from below */
   const void* dropmask; float drop_scale;         /* uint8 keep-mask [batches*m, n] applied before the residual, or NULL */
+  void* aux_pre; long long ld_aux;                /* NULL, or bf16 [batches*m, ld_aux]: the value BEFORE `act` (after the bias), kept for the
+                                                     activation's backward (BertIntermediate's GELU) */
 } mclip_gemm_args;
 int mclip_gemm_tn_stat_slots(int m, int n, int batches);
 int mclip_gemm_tn(const mclip_gemm_args* args, void* stream);
@@ -238,11 +240,11 @@ int mclip_layernorm_backward(const void* x_bf16, const void* dy_bf16, const floa
 /* erf-GELU on bf16 (BertIntermediate): y = gelu(x); dx = dy * gelu'(x).  n = element count, multiple of 8. */
 int mclip_gelu_forward(const void* x_bf16, void* y_bf16, long long n, void* stream);
 int mclip_gelu_backward(const void* dy_bf16, const void* x_bf16, void* dx_bf16, long long n, void* stream);
-/* d qkv (bf16 [batch*seq_len, 3*heads*head_dim]) from d_out / out (bf16 [batch*seq_len, heads*head_dim]) and the saved lse;
- * probabilities are recomputed per 64x64 tile; every element is written exactly once (deterministic). */
-int mclip_bert_attention_backward(const void* qkv, const void* d_out, const void* out, const float* lse, const void* attention_mask,
-                                  const void* dropmask, float drop_scale, void* dqkv, int batch, int seq_len, int heads, int head_dim,
-                                  void* stream);
+/* d qkv (bf16 [batch*seq_len, 3*heads*head_dim]) from d_out (bf16 [batch*seq_len, heads*head_dim]) and the saved lse;
+ * probabilities are recomputed per 64x64 tile; delta_ws fp32 [batch, heads, seq_len] receives sum_k P dP of a pre-pass
+ * (fp32, not the bf16-rounded <dO, O>); every output element is written exactly once (deterministic). */
+int mclip_bert_attention_backward(const void* qkv, const void* d_out, const float* lse, const void* attention_mask, const void* dropmask,
+                                  float drop_scale, float* delta_ws, void* dqkv, int batch, int seq_len, int heads, int head_dim, void* stream);
 /* Embeddings backward (BertEmbeddings): LayerNorm backward of (dout o keep-mask*scale) with the pre-LN sum recomputed from
  * the tables, then word rows (first occurrence of an id sums all its tokens in order: deterministic, no atomics),
  * position rows < seq_len and token-type rows.  accumulate == 0 writes ONLY the touched rows: the caller provides zeroed

@@ -46,6 +46,7 @@ class GemmArgs(C.Structure):
         ("act", C.c_int),
         ("stats", C.c_void_p), ("stat_slots", C.c_int),
         ("dropmask", C.c_void_p), ("drop_scale", C.c_float),
+        ("aux_pre", C.c_void_p), ("ld_aux", C.c_longlong),
     ]
 
 
@@ -90,7 +91,7 @@ def check(rc: int, what: str = ""):
 
 # kernels launched per ABI call (for bench.py's `gpu_launches`); default 1
 LAUNCHES = {"mclip_gemm_wgrad": 2, "mclip_dwconv_backward": 2, "mclip_se_fc_backward": 2, "mclip_layernorm_backward": 2,
-            "mclip_bert_embed_backward": 4}
+            "mclip_bert_embed_backward": 4, "mclip_bert_attention_backward": 2}
 
 
 class Profiler:

@@ -309,7 +309,10 @@ __global__ void mclip_gelu_bwd_kernel(const bf16* __restrict__ dy, const bf16* _
 
 // ---- attention backward: CTA = (64-token block i, head, batch) -------------------------------------------------------
 // Recomputes P = exp(S - lse) per 64x64 tile from Q, K and the saved log-sum-exp; with M = keep-mask*scale:
-//   dV = (P o M)^T dO,  dP = (dO V^T) o M,  dS = P o (dP - delta),  delta_r = <dO_r, O_r>,  dQ = dS K / 8,  dK = dS^T Q / 8.
+//   dV = (P o M)^T dO,  dP = (dO V^T) o M,  dS = P o (dP - delta),  delta_r = sum_c P_rc dP_rc,  dQ = dS K / 8,  dK = dS^T Q / 8.
+// delta comes from a pre-pass (mclip_bert_attention_delta_kernel) that sums P o dP in fp32 over the recomputed tiles: the
+// flash-attention shortcut delta = <dO, O> with the bf16-ROUNDED O loses the cancellation in dP - delta whenever the true
+// dS is small (near-uniform attention at random init), and that noise lands directly on the query/key weight gradients.
 // CTA i accumulates dQ of its query block over all key blocks and dK/dV of its key block over all query blocks
 // (the diagonal tile serves both), so every output element is written once: no atomics, deterministic.
 #define ATB 64
@@ -321,33 +324,29 @@ struct AttBwdSmem {
   int kv_i[ATB], kv_j[ATB];
 };
 
-// Q (pre-scaled by 1/8) and dO rows of token block `blk`, their lse and delta = <dO, O>
-__device__ __forceinline__ void attb_load_q(const bf16* __restrict__ qkv, const bf16* __restrict__ dO, const bf16* __restrict__ O,
-                                            const float* __restrict__ lse, float (*Qs)[ATB_LD], float (*dOs)[ATB_LD], float* lse_s, float* delta_s,
+// Q (pre-scaled by 1/8) and dO rows of token block `blk`, their lse and (when given) the pre-computed delta
+__device__ __forceinline__ void attb_load_q(const bf16* __restrict__ qkv, const bf16* __restrict__ dO, const float* __restrict__ lse,
+                                            const float* __restrict__ delta, float (*Qs)[ATB_LD], float (*dOs)[ATB_LD], float* lse_s, float* delta_s,
                                             int blk, int b, int head, int heads, int L) {
   const int H = heads * ATT_D;
-  for (int idx = threadIdx.x; idx < ATB * (ATT_D / 8); idx += 256) {       // 8 consecutive lanes share a row
+  for (int idx = threadIdx.x; idx < ATB * (ATT_D / 8); idx += 256) {
     const int r = idx >> 3, dv = (idx & 7) * 8;
     const int qi = blk * ATB + r;
-    float fq[8], fd[8], fo[8];
+    float fq[8], fd[8];
     if (qi < L) {
       const size_t tok = (size_t)b * L + qi;
       unpack8(*reinterpret_cast<const bf16x8*>(qkv + tok * 3 * H + head * ATT_D + dv), fq);
       unpack8(*reinterpret_cast<const bf16x8*>(dO + tok * H + head * ATT_D + dv), fd);
-      unpack8(*reinterpret_cast<const bf16x8*>(O + tok * H + head * ATT_D + dv), fo);
     } else {
 #pragma unroll
-      for (int e = 0; e < 8; ++e) fq[e] = fd[e] = fo[e] = 0.f;
+      for (int e = 0; e < 8; ++e) fq[e] = fd[e] = 0.f;
     }
-    float dl = 0.f;
 #pragma unroll
-    for (int e = 0; e < 8; ++e) { Qs[r][dv + e] = fq[e] * 0.125f; dOs[r][dv + e] = fd[e]; dl = fmaf(fd[e], fo[e], dl); }
-    dl += __shfl_xor_sync(0xffffffffu, dl, 1);
-    dl += __shfl_xor_sync(0xffffffffu, dl, 2);
-    dl += __shfl_xor_sync(0xffffffffu, dl, 4);
+    for (int e = 0; e < 8; ++e) { Qs[r][dv + e] = fq[e] * 0.125f; dOs[r][dv + e] = fd[e]; }
     if ((idx & 7) == 0) {
-      delta_s[r] = dl;
-      lse_s[r] = qi < L ? lse[((size_t)(b * heads + head)) * L + qi] : INFINITY;     // +inf => p = 0 for rows past L
+      const size_t li = ((size_t)(b * heads + head)) * L + qi;
+      lse_s[r] = qi < L ? lse[li] : INFINITY;                                        // +inf => p = 0 for rows past L
+      if (delta_s) delta_s[r] = (delta && qi < L) ? delta[li] : 0.f;
     }
   }
 }
@@ -373,9 +372,11 @@ __device__ __forceinline__ void attb_load_kv(const bf16* __restrict__ qkv, const
   if (threadIdx.x < ATB) { const int kj = blk * ATB + threadIdx.x; kvalid[threadIdx.x] = (kj < L) && (amask[(size_t)b * L + kj] != 0); }
 }
 
-// One 64x64 tile: thread (ty, tx) owns queries ty+16i and keys tx+16j.  Writes Ps = P o M and dSs = dS.
+// One 64x64 tile: thread (ty, tx) owns queries ty+16i and keys tx+16j.
+//   DELTA_ONLY: rowsum[i] += sum_j P o M o (dO V^T) over this thread's keys (pre-pass);  else writes Ps = P o M and dSs = dS.
+template <bool DELTA_ONLY>
 __device__ __forceinline__ void attb_tile(float (*Qs)[ATB_LD], float (*dOs)[ATB_LD], const float* lse_s, const float* delta_s, float (*Ks)[ATB_LD],
-                                          float (*Vs)[ATB_LD], const int* kvalid, float (*Ps)[ATB_LD], float (*dSs)[ATB_LD],
+                                          float (*Vs)[ATB_LD], const int* kvalid, float (*Ps)[ATB_LD], float (*dSs)[ATB_LD], float* rowsum,
                                           const uint8_t* __restrict__ dropmask, float drop_scale, int qblk, int kblk, int b, int head, int heads, int L) {
   const int ty = threadIdx.x >> 4, tx = threadIdx.x & 15;
   float s[4][4], dp[4][4];
@@ -398,16 +399,54 @@ __device__ __forceinline__ void attb_tile(float (*Qs)[ATB_LD], float (*dOs)[ATB_
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
     const int r = ty + 16 * i, qi = qblk * ATB + r;
-    const float l = lse_s[r], dl = delta_s[r];
+    const float l = lse_s[r], dl = DELTA_ONLY ? 0.f : delta_s[r];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const int c = tx + 16 * j, kj = kblk * ATB + c;
       const float p = kvalid[c] ? __expf(s[i][j] - l) : 0.f;
       float m = 1.0f;
       if (dropmask && qi < L && kj < L) m = dropmask[(((size_t)(b * heads + head)) * L + qi) * L + kj] ? drop_scale : 0.f;
-      Ps[r][c] = p * m;
-      dSs[r][c] = p * (dp[i][j] * m - dl);
+      if (DELTA_ONLY) rowsum[i] = fmaf(p * m, dp[i][j], rowsum[i]);
+      else {
+        Ps[r][c] = p * m;
+        dSs[r][c] = p * (dp[i][j] * m - dl);
+      }
     }
+  }
+}
+
+// Pre-pass: delta[b, head, q] = sum_k (P o M)_qk (dO_q . V_k), fp32, one CTA per (64-query block, head, sample)
+struct AttDeltaSmem {
+  float Qi[ATB][ATB_LD], dOi[ATB][ATB_LD], X1[ATB][ATB_LD], X2[ATB][ATB_LD];
+  float lse_i[ATB];
+  int kv_j[ATB];
+};
+__global__ void __launch_bounds__(256) mclip_bert_attention_delta_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ dO,
+                                                                         const float* __restrict__ lse, const long long* __restrict__ amask,
+                                                                         const uint8_t* __restrict__ dropmask, float drop_scale, float* __restrict__ delta,
+                                                                         int B, int L, int heads) {
+  extern __shared__ uint8_t attb_raw[];
+  AttDeltaSmem& sm = *reinterpret_cast<AttDeltaSmem*>(attb_raw);
+  const int blk = blockIdx.x, head = blockIdx.y, b = blockIdx.z;
+  const int nblk = (L + ATB - 1) / ATB;
+  const int ty = threadIdx.x >> 4, tx = threadIdx.x & 15;
+  float rowsum[4] = {0.f, 0.f, 0.f, 0.f};
+  attb_load_q(qkv, dO, lse, nullptr, sm.Qi, sm.dOi, sm.lse_i, nullptr, blk, b, head, heads, L);
+  for (int j = 0; j < nblk; ++j) {
+    __syncthreads();
+    attb_load_kv(qkv, amask, sm.X1, sm.X2, sm.kv_j, j, b, head, heads, L);
+    __syncthreads();
+    attb_tile<true>(sm.Qi, sm.dOi, sm.lse_i, nullptr, sm.X1, sm.X2, sm.kv_j, nullptr, nullptr, rowsum, dropmask, drop_scale, blk, j, b, head, heads, L);
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    float v = rowsum[i];                               // the 16 lanes of one ty hold the 64 keys of each block between them
+    v += __shfl_xor_sync(0xffffffffu, v, 1);
+    v += __shfl_xor_sync(0xffffffffu, v, 2);
+    v += __shfl_xor_sync(0xffffffffu, v, 4);
+    v += __shfl_xor_sync(0xffffffffu, v, 8);
+    const int qi = blk * ATB + ty + 16 * i;
+    if (tx == 0 && qi < L) delta[((size_t)(b * heads + head)) * L + qi] = v;
   }
 }
 
@@ -444,8 +483,9 @@ __device__ __forceinline__ void attb_acc_cols(float (*A)[ATB_LD], float (*Bm)[AT
   }
 }
 
-__global__ void __launch_bounds__(256) mclip_bert_attention_bwd_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ dO, const bf16* __restrict__ O,
-                                                                       const float* __restrict__ lse, const long long* __restrict__ amask,
+__global__ void __launch_bounds__(256) mclip_bert_attention_bwd_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ dO,
+                                                                       const float* __restrict__ lse, const float* __restrict__ delta,
+                                                                       const long long* __restrict__ amask,
                                                                        const uint8_t* __restrict__ dropmask, float drop_scale, bf16* __restrict__ dqkv,
                                                                        int B, int L, int heads) {
   extern __shared__ uint8_t attb_raw[];
@@ -459,12 +499,12 @@ __global__ void __launch_bounds__(256) mclip_bert_attention_bwd_kernel(const bf1
   for (int i = 0; i < 4; ++i)
 #pragma unroll
     for (int j = 0; j < 4; ++j) { dq[i][j] = 0.f; dk[i][j] = 0.f; dv[i][j] = 0.f; }
-  attb_load_q(qkv, dO, O, lse, sm.Qi, sm.dOi, sm.lse_i, sm.delta_i, blk, b, head, heads, L);
+  attb_load_q(qkv, dO, lse, delta, sm.Qi, sm.dOi, sm.lse_i, sm.delta_i, blk, b, head, heads, L);
   attb_load_kv(qkv, amask, sm.Ki, sm.Vi, sm.kv_i, blk, b, head, heads, L);
   __syncthreads();
   for (int j = 0; j < nblk; ++j) {
     if (j == blk) {
-      attb_tile(sm.Qi, sm.dOi, sm.lse_i, sm.delta_i, sm.Ki, sm.Vi, sm.kv_i, sm.Ps, sm.dSs, dropmask, drop_scale, blk, blk, b, head, heads, L);
+      attb_tile<false>(sm.Qi, sm.dOi, sm.lse_i, sm.delta_i, sm.Ki, sm.Vi, sm.kv_i, sm.Ps, sm.dSs, nullptr, dropmask, drop_scale, blk, blk, b, head, heads, L);
       __syncthreads();
       attb_acc_rows(sm.dSs, sm.Ki, dq);       // dQ_i += dS K_i
       attb_acc_cols(sm.Ps, sm.dOi, dv);       // dV_i += (P o M)^T dO_i
@@ -473,13 +513,13 @@ __global__ void __launch_bounds__(256) mclip_bert_attention_bwd_kernel(const bf1
     } else {
       attb_load_kv(qkv, amask, sm.X1, sm.X2, sm.kv_j, j, b, head, heads, L);
       __syncthreads();
-      attb_tile(sm.Qi, sm.dOi, sm.lse_i, sm.delta_i, sm.X1, sm.X2, sm.kv_j, sm.Ps, sm.dSs, dropmask, drop_scale, blk, j, b, head, heads, L);
+      attb_tile<false>(sm.Qi, sm.dOi, sm.lse_i, sm.delta_i, sm.X1, sm.X2, sm.kv_j, sm.Ps, sm.dSs, nullptr, dropmask, drop_scale, blk, j, b, head, heads, L);
       __syncthreads();
       attb_acc_rows(sm.dSs, sm.X1, dq);       // dQ_i += dS K_j
       __syncthreads();
-      attb_load_q(qkv, dO, O, lse, sm.X1, sm.X2, sm.lse_j, sm.delta_j, j, b, head, heads, L);
+      attb_load_q(qkv, dO, lse, delta, sm.X1, sm.X2, sm.lse_j, sm.delta_j, j, b, head, heads, L);
       __syncthreads();
-      attb_tile(sm.X1, sm.X2, sm.lse_j, sm.delta_j, sm.Ki, sm.Vi, sm.kv_i, sm.Ps, sm.dSs, dropmask, drop_scale, j, blk, b, head, heads, L);
+      attb_tile<false>(sm.X1, sm.X2, sm.lse_j, sm.delta_j, sm.Ki, sm.Vi, sm.kv_i, sm.Ps, sm.dSs, nullptr, dropmask, drop_scale, j, blk, b, head, heads, L);
       __syncthreads();
       attb_acc_cols(sm.Ps, sm.X2, dv);        // dV_i += (P o M)^T dO_j
       attb_acc_cols(sm.dSs, sm.X1, dk);       // dK_i += dS^T (Q_j / 8)
@@ -674,19 +714,23 @@ extern "C" int mclip_gelu_backward(const void* dy, const void* x, void* dx, long
   return MCLIP_OK;
 }
 
-extern "C" int mclip_bert_attention_backward(const void* qkv, const void* d_out, const void* out, const float* lse, const void* attention_mask,
-                                             const void* dropmask, float drop_scale, void* dqkv, int batch, int seq_len, int heads, int head_dim,
+extern "C" int mclip_bert_attention_backward(const void* qkv, const void* d_out, const float* lse, const void* attention_mask, const void* dropmask,
+                                             float drop_scale, float* delta_ws, void* dqkv, int batch, int seq_len, int heads, int head_dim,
                                              void* stream) {
-  MCLIP_REQUIRE(qkv && d_out && out && lse && attention_mask && dqkv && batch > 0 && seq_len > 0, "mclip_bert_attention_backward: bad arguments");
+  MCLIP_REQUIRE(qkv && d_out && lse && attention_mask && delta_ws && dqkv && batch > 0 && seq_len > 0, "mclip_bert_attention_backward: bad arguments");
   MCLIP_REQUIRE(head_dim == ATT_D, "mclip_bert_attention_backward: head_dim %d not built (64 only)", head_dim);
   static int attr_set = 0;
   if (!attr_set) {
     MCLIP_CHECK_CUDA(cudaFuncSetAttribute(mclip_bert_attention_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(AttBwdSmem)));
+    MCLIP_CHECK_CUDA(cudaFuncSetAttribute(mclip_bert_attention_delta_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(AttDeltaSmem)));
     attr_set = 1;
   }
   dim3 grid(ceil_div(seq_len, ATB), heads, batch);
+  mclip_bert_attention_delta_kernel<<<grid, 256, sizeof(AttDeltaSmem), (cudaStream_t)stream>>>(
+      (const bf16*)qkv, (const bf16*)d_out, lse, (const long long*)attention_mask, (const uint8_t*)dropmask, drop_scale, delta_ws, batch, seq_len, heads);
+  MCLIP_CHECK_LAUNCH();
   mclip_bert_attention_bwd_kernel<<<grid, 256, sizeof(AttBwdSmem), (cudaStream_t)stream>>>(
-      (const bf16*)qkv, (const bf16*)d_out, (const bf16*)out, lse, (const long long*)attention_mask, (const uint8_t*)dropmask, drop_scale, (bf16*)dqkv,
+      (const bf16*)qkv, (const bf16*)d_out, lse, delta_ws, (const long long*)attention_mask, (const uint8_t*)dropmask, drop_scale, (bf16*)dqkv,
       batch, seq_len, heads);
   MCLIP_CHECK_LAUNCH();
   return MCLIP_OK;

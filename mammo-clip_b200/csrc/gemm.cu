@@ -34,6 +34,7 @@ struct GemmDev {
   int act;
   float* stats;     // [(gridDim.x / n_blocks) * 4][2][N]
   const uint8_t* dropmask; float drop_scale;
+  bf16* aux; long long aux_ld;   // optional bf16 copy of the pre-activation value (after the bias), [batches*M, aux_ld]
   int small_k;      // K <= 64 and shared B: B panel resident in smem, A tiles staged with cp.async by warp 0
   const bf16* a_ptr; long long lda, a_bs;
   int debug;        // MCLIP_GEMM_DEBUG bitmask (experiments only): 1 no stats, 2 no TMA store, 4 no TMEM load/convert
@@ -246,6 +247,12 @@ mclip_gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
 #pragma unroll
             for (int i = 0; i < 16; ++i) if (cc + i < p.N) v[i] += __ldg(p.bias + cc + i);
           }
+          if (p.aux && row < p.M) {
+            bf16* ap = p.aux + ((size_t)b * p.M + row) * p.aux_ld + cc;
+#pragma unroll
+            for (int g = 0; g < 2; ++g)
+              if (cc + g * 8 < p.N) stg_bf16x8(ap + g * 8, pack8(v + g * 8));
+          }
           if (p.act == 1) {
 #pragma unroll
             for (int i = 0; i < 16; ++i) v[i] = gelu_erf(v[i]);
@@ -372,6 +379,8 @@ extern "C" int mclip_gemm_tn(const mclip_gemm_args* g, void* stream_) {
   { const char* e = getenv("MCLIP_GEMM_DEBUG"); p.debug = e ? atoi(e) : 0; if (p.debug & 1) p.stats = nullptr; }
   p.dropmask = (const uint8_t*)g->dropmask; p.drop_scale = g->drop_scale;
   if (g->dropmask) MCLIP_REQUIRE(g->n % 16 == 0, "mclip_gemm_tn: dropout mask needs N %% 16 == 0");
+  p.aux = (bf16*)g->aux_pre; p.aux_ld = g->ld_aux;
+  if (g->aux_pre) MCLIP_REQUIRE(g->ld_aux >= g->n && g->ld_aux % 8 == 0 && ((uintptr_t)g->aux_pre & 15) == 0, "mclip_gemm_tn: aux_pre needs a 16-byte aligned row layout");
   p.small_k = (p.k_blocks == 1 && !p.b_batched && g->lda % 8 == 0 && g->a_batch_stride % 8 == 0 && ((uintptr_t)g->a & 15) == 0) ? 1 : 0;
   if (getenv("MCLIP_GEMM_NO_SMALLK")) p.small_k = 0;
   p.a_ptr = (const bf16*)g->a; p.lda = g->lda; p.a_bs = g->a_batch_stride;

@@ -110,12 +110,9 @@ def _kernel_forward(bert, ids, tts, amask, masks, save=None):
             ctx = ops.bert_attention(qkv, amask, b, l, heads, hdim // heads, mk["probs"], sa)
         h1 = ops.gemm_tn(ctx, lw["wo"], bias=so.dense.bias.detach(), residual=x, dropmask=mk["attn_out"], drop_scale=sh)
         x1 = ops.layernorm(h1, so.LayerNorm.weight, so.LayerNorm.bias, eps)
-        if save is not None:
-            # pre-activation kept for GELU' (BertIntermediate); the activation runs as its own pass on the bf16 value
-            pre = ops.gemm_tn(x1, lw["w1"], bias=it.dense.bias.detach())
-            inter = ops.gelu_forward(pre)
-        else:
-            pre, inter = None, ops.gemm_tn(x1, lw["w1"], bias=it.dense.bias.detach(), act=1)
+        # the fused erf-GELU epilogue also stores the pre-activation (bf16) when the backward pass will need GELU'
+        pre = torch.empty((x1.shape[0], lw["w1"].shape[0]), dtype=torch.bfloat16, device=x1.device) if save is not None else None
+        inter = ops.gemm_tn(x1, lw["w1"], bias=it.dense.bias.detach(), act=1, aux_pre=pre)
         h2 = ops.gemm_tn(inter, lw["w2"], bias=ou.dense.bias.detach(), residual=x1, dropmask=mk["ffn_out"], drop_scale=sh)
         x_out = ops.layernorm(h2, ou.LayerNorm.weight, ou.LayerNorm.bias, eps)
         if save is not None:
@@ -167,7 +164,7 @@ def _kernel_backward(bert, ids, tts, amask, masks, saved, dout, G, accumulate):
         d_ctx = ops.gemm_tn(dh1d, lw["wo_t"])
         linear_grads(so.dense, dh1d, S["ctx"])
         # BertSelfAttention
-        dqkv = ops.bert_attention_backward(S["qkv"], d_ctx, S["ctx"], S["lse"], amask, b, l, heads, hdim // heads, mk["probs"], sa)
+        dqkv = ops.bert_attention_backward(S["qkv"], d_ctx, S["lse"], amask, b, l, heads, hdim // heads, mk["probs"], sa)
         dx = ops.gemm_tn(dqkv, lw["qkv_t"], residual=dh1)
         for j, lin in enumerate((a.query, a.key, a.value)):
             linear_grads(lin, dqkv[:, j * hdim:(j + 1) * hdim], S["x"])

@@ -15,7 +15,7 @@ def _require_cuda(*tensors):
 
 # ------------------------------------------------------------------------------------------------ GEMMs
 
-def gemm_tn(a, b, out=None, bias=None, residual=None, act=0, want_stats=None, dropmask=None, drop_scale=1.0):
+def gemm_tn(a, b, out=None, bias=None, residual=None, act=0, want_stats=None, dropmask=None, drop_scale=1.0, aux_pre=None):
     """out[b,m,n] = epi(sum_k a[b,m,k] * w[b|0,n,k]).  a: [M,K] or [Bt,M,K] bf16; b: [N,K] or [Bt,N,K] bf16.
     want_stats=None: returns out (bf16).  want_stats=True/False: returns (out, stats[slots,2,N] fp32 or None)."""
     _require_cuda(a, b)
@@ -42,6 +42,9 @@ def gemm_tn(a, b, out=None, bias=None, residual=None, act=0, want_stats=None, dr
     if dropmask is not None:
         assert dropmask.dtype == torch.uint8 and dropmask.is_contiguous() and dropmask.numel() == bt * m * n
         g.dropmask, g.drop_scale = dropmask.data_ptr(), drop_scale
+    if aux_pre is not None:       # bf16 [bt*m, n]: receives the pre-activation value
+        assert aux_pre.dtype == torch.bfloat16 and aux_pre.is_contiguous() and aux_pre.numel() == bt * m * n
+        g.aux_pre, g.ld_aux = aux_pre.data_ptr(), n
     stats = None
     if want_stats:
         slots = lib().mclip_gemm_tn_stat_slots(m, n, bt)
@@ -469,9 +472,10 @@ def gelu_backward(dy, x):
     return out
 
 
-def bert_attention_backward(qkv, d_out, out, lse, attention_mask, batch, seq_len, heads, head_dim, dropmask=None, drop_scale=1.0):
+def bert_attention_backward(qkv, d_out, lse, attention_mask, batch, seq_len, heads, head_dim, dropmask=None, drop_scale=1.0):
     dqkv = torch.empty_like(qkv)
-    call("mclip_bert_attention_backward", ptr(qkv), ptr(d_out), ptr(out), ptr(lse), ptr(attention_mask), ptr(dropmask), C.c_float(drop_scale), ptr(dqkv),
+    delta = torch.empty_like(lse)
+    call("mclip_bert_attention_backward", ptr(qkv), ptr(d_out), ptr(lse), ptr(attention_mask), ptr(dropmask), C.c_float(drop_scale), ptr(delta), ptr(dqkv),
          batch, seq_len, heads, head_dim)
     return dqkv
 
