@@ -169,6 +169,10 @@ typedef struct mclip_ew_args {
   void* out; float* pool_partials;      /* pool_partials fp32 [n][chunks][c], chunks = mclip_ew_chunks(n,hw,c) */
 } mclip_ew_args;
 int mclip_ew_chunks(int n, int hw, int c);
+/* Tuning switch of the streaming passes: bit m (0..2) = mclip_ew_backward mode m, bit 3 = mclip_ew_forward stage their
+ * inputs through a per-thread cp.async ring in shared memory (more bytes in flight per SM) instead of registers.
+ * Same results bit for bit; returns the previous mask.  Initial value: env MCLIP_EW_ASYNC, else the built-in default. */
+int mclip_set_ew_async(int mask);
 int mclip_ew_forward(const mclip_ew_args* args, void* stream);
 int mclip_pool_finalize(const float* partials, int n, int chunks, int c, int hw, const float* mult, float* out, void* stream);
 

@@ -13,10 +13,12 @@
 //   autograd of all of the above                            mclip_bn_bwd_reduce / _finalize / _apply, mclip_se_bwd_pass1, mclip_se_fc_bwd
 #include "common.cuh"
 #include "mclip_internal.h"
+#include <stdlib.h>
 
 #define EW_MAX_THREADS 256
 #define EW_CPT 4            // channels per thread (8-byte vectors; a warp still covers 256 contiguous bytes)
 #define EW_UNR 4            // pixels in flight per thread
+#define EW_ASYNC_DEFAULT 4   // see mclip_ew_backward: which passes stage their inputs through the cp.async ring
 
 typedef unsigned long long u64;
 __device__ __forceinline__ float2 bf2_to_f2(uint32_t u) { return make_float2(__uint_as_float(u << 16), __uint_as_float(u & 0xffff0000u)); }
@@ -40,11 +42,36 @@ __device__ __forceinline__ uint2 ldg_b64(const bf16* p) {
 __device__ __forceinline__ void stg_b64(bf16* p, uint2 v) {
   asm volatile("st.global.L1::no_allocate.v2.u32 [%0], {%1,%2};" ::"l"(p), "r"(v.x), "r"(v.y) : "memory");
 }
+// ---- per-thread cp.async ring: the bytes in flight live in shared memory instead of registers, so a register-heavy pass
+//      (SE pass 1: 5 accumulators + 10 per-channel constants) still keeps ~100 KB per SM outstanding towards HBM.
+//      A thread only ever reads the slots it filled itself: cp.async.wait_group is the only synchronisation needed.
+#define EW_RING 8            // slots per thread (EW_RING-1 pixels in flight); slot = 16 B: y (8 B) | dU or residual (8 B)
+__device__ __forceinline__ void cp_async8(uint32_t dst, const void* src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ uint4 lds128(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+  return v;
+}
+
 // sigma(t) via one MUFU; returns (sigma(t.x), sigma(t.y))
 __device__ __forceinline__ float2 sigmoid2(const float2& t) {
   const float2 h = make_float2(fast_tanh(0.5f * t.x), fast_tanh(0.5f * t.y));
   return ffma2r(h, make_float2(0.5f, 0.5f), make_float2(0.5f, 0.5f));
 }
+
+// Which streaming passes stage their inputs through the cp.async ring: bit m = backward mode m, bit 3 = forward pass.
+// Initialised from MCLIP_EW_ASYNC (default EW_ASYNC_DEFAULT); mclip_set_ew_async() overrides it (tests, tuning).
+static int g_ew_async = -1;
+static int ew_async_mask() {
+  if (g_ew_async < 0) { const char* e = getenv("MCLIP_EW_ASYNC"); g_ew_async = e ? atoi(e) : EW_ASYNC_DEFAULT; }
+  return g_ew_async;
+}
+extern "C" int mclip_set_ew_async(int mask) { const int old = ew_async_mask(); g_ew_async = mask & 15; return old; }
 
 struct EwGeom {
   int N, HW, C, G, CG, TPP, PL, chunks, pix_per_chunk;
@@ -163,6 +190,7 @@ struct EwFwdDev {
   bf16* out; float* pool_part;     // pool_part: [N][chunks][C]
 };
 
+template <bool ASYNC>
 __global__ void __launch_bounds__(EW_MAX_THREADS, 4) mclip_ew_fwd_kernel(const EwFwdDev p) {
   extern __shared__ float ew_smem[];
   const EwGeom& g = p.g;
@@ -182,33 +210,64 @@ __global__ void __launch_bounds__(EW_MAX_THREADS, 4) mclip_ew_fwd_kernel(const E
   const float rsv = p.rowscale ? p.rowscale[n] : 1.f;
   const float2 rs = make_float2(rsv, rsv), one = make_float2(1.f, 1.f);
   const size_t base = (size_t)n * g.HW * g.C + c;
-  for (int px0 = p0 + pl; px0 < p1; px0 += g.PL * EW_UNR) {
-    uint2 yv[EW_UNR], rv[EW_UNR];
+  auto pixel = [&](int px, const uint32_t (&yw)[2], const uint32_t (&rw)[2]) {
+    uint32_t ow[2];
 #pragma unroll
-    for (int u = 0; u < EW_UNR; ++u) {
-      const int px = px0 + u * g.PL;
-      if (px < p1) {
-        const size_t off = base + (size_t)px * g.C;
-        yv[u] = ldg_b64(p.y + off);
-        if (p.residual) rv[u] = ldg_b64(p.residual + off);
-      }
+    for (int i = 0; i < 2; ++i) {
+      float2 h = ffma2r(bf2_to_f2(yw[i]), a[i], b[i]);
+      if (p.act) h = ffma2r(h, make_float2(fast_tanh(h.x), fast_tanh(h.y)), h);
+      if (p.rowscale) h = fmul2(h, rs);
+      if (p.residual) h = ffma2r(bf2_to_f2(rw[i]), one, h);
+      ow[i] = pack_bf16(h.x, h.y);
+      if (p.pool_part) ffma2(acc[i], bf2_to_f2(ow[i]), one);     // pool what the consumer reads (bf16-rounded)
     }
-#pragma unroll
-    for (int u = 0; u < EW_UNR; ++u) {
-      const int px = px0 + u * g.PL;
-      if (px >= p1) break;
-      const uint32_t yw[2] = {yv[u].x, yv[u].y}, rw[2] = {rv[u].x, rv[u].y};
-      uint32_t ow[2];
-#pragma unroll
-      for (int i = 0; i < 2; ++i) {
-        float2 h = ffma2r(bf2_to_f2(yw[i]), a[i], b[i]);
-        if (p.act) h = ffma2r(h, make_float2(fast_tanh(h.x), fast_tanh(h.y)), h);
-        if (p.rowscale) h = fmul2(h, rs);
-        if (p.residual) h = ffma2r(bf2_to_f2(rw[i]), one, h);
-        ow[i] = pack_bf16(h.x, h.y);
-        if (p.pool_part) ffma2(acc[i], bf2_to_f2(ow[i]), one);     // pool what the consumer reads (bf16-rounded)
+    if (p.out) stg_b64(p.out + base + (size_t)px * g.C, make_uint2(ow[0], ow[1]));
+  };
+  if (ASYNC) {
+    const uint32_t slot_stride = blockDim.x * 16u;
+    const uint32_t my = smem_u32(ew_smem) + (uint32_t)(g.PL * g.CG) * 4u + threadIdx.x * 16u;
+    const bool has_res = p.residual != nullptr;
+    int px_issue = p0 + pl;
+    auto issue = [&](int slot) {
+      if (px_issue < p1) {
+        const size_t off = base + (size_t)px_issue * g.C;
+        cp_async8(my + slot * slot_stride, p.y + off);
+        if (has_res) cp_async8(my + slot * slot_stride + 8u, p.residual + off);
       }
-      if (p.out) stg_b64(p.out + base + (size_t)px * g.C, make_uint2(ow[0], ow[1]));
+      cp_async_commit();
+      px_issue += g.PL;
+    };
+#pragma unroll
+    for (int s = 0; s < EW_RING - 1; ++s) issue(s);
+    int slot = 0;
+    for (int px = p0 + pl; px < p1; px += g.PL) {
+      issue(slot == 0 ? EW_RING - 1 : slot - 1);
+      cp_async_wait<EW_RING - 1>();
+      const uint4 v = lds128(my + slot * slot_stride);
+      const uint32_t yw[2] = {v.x, v.y}, rw[2] = {v.z, v.w};
+      pixel(px, yw, rw);
+      slot = slot == EW_RING - 1 ? 0 : slot + 1;
+    }
+    cp_async_wait<0>();
+  } else {
+    for (int px0 = p0 + pl; px0 < p1; px0 += g.PL * EW_UNR) {
+      uint2 yv[EW_UNR], rv[EW_UNR];
+#pragma unroll
+      for (int u = 0; u < EW_UNR; ++u) {
+        const int px = px0 + u * g.PL;
+        if (px < p1) {
+          const size_t off = base + (size_t)px * g.C;
+          yv[u] = ldg_b64(p.y + off);
+          if (p.residual) rv[u] = ldg_b64(p.residual + off);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < EW_UNR; ++u) {
+        const int px = px0 + u * g.PL;
+        if (px >= p1) break;
+        const uint32_t yw[2] = {yv[u].x, yv[u].y}, rw[2] = {rv[u].x, rv[u].y};
+        pixel(px, yw, rw);
+      }
     }
   }
   if (p.pool_part) ew_block_reduce4(ew_smem, acc, cv, pl, g.CG, g.PL, p.pool_part + ((size_t)n * g.chunks + chunk) * g.C + grp * g.CG);
@@ -223,7 +282,13 @@ extern "C" int mclip_ew_forward(const mclip_ew_args* a, void* stream) {
   p.y = (const bf16*)a->y; p.scale = a->scale; p.shift = a->shift; p.act = a->act; p.rowscale = a->rowscale;
   p.residual = (const bf16*)a->residual; p.out = (bf16*)a->out; p.pool_part = a->pool_partials;
   const int smem = p.g.PL * p.g.CG * 4;
-  mclip_ew_fwd_kernel<<<a->n * p.g.chunks * p.g.G, threads, smem, (cudaStream_t)stream>>>(p);
+  static int carveout_set = 0;
+  if (!carveout_set) {
+    MCLIP_CHECK_CUDA(cudaFuncSetAttribute(mclip_ew_fwd_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, 70));
+    carveout_set = 1;
+  }
+  if ((ew_async_mask() >> 3) & 1) mclip_ew_fwd_kernel<true><<<a->n * p.g.chunks * p.g.G, threads, smem + EW_RING * threads * 16, (cudaStream_t)stream>>>(p);
+  else mclip_ew_fwd_kernel<false><<<a->n * p.g.chunks * p.g.G, threads, smem, (cudaStream_t)stream>>>(p);
   MCLIP_CHECK_LAUNCH();
   return MCLIP_OK;
 }
@@ -340,7 +405,7 @@ struct EwBwdDev {
   bf16* out;                              // apply: dY ; se1: A2
 };
 
-template <int MODE>   // 0 reduce, 1 apply, 2 se pass 1
+template <int MODE, bool ASYNC>   // MODE 0 reduce, 1 apply, 2 se pass 1; ASYNC: inputs staged through the per-thread cp.async ring
 __global__ void __launch_bounds__(EW_MAX_THREADS, 3) mclip_ew_bwd_kernel(const EwBwdDev p) {
   extern __shared__ float ew_smem[];
   const EwGeom& g = p.g;
@@ -367,62 +432,95 @@ __global__ void __launch_bounds__(EW_MAX_THREADS, 3) mclip_ew_bwd_kernel(const E
   }
   const float2 one = make_float2(1.f, 1.f);
   const size_t base = (size_t)n * g.HW * g.C + c;
-  constexpr int UNR = (MODE == 2) ? 2 : EW_UNR;
-  for (int px0 = p0 + pl; px0 < p1; px0 += g.PL * UNR) {
-    uint2 yv[UNR], dv_[UNR];
+  // one pixel of this thread's 4 channels: yw = y (2 x bf16x2), dw_ = dU (ignored when p.dU == nullptr)
+  auto pixel = [&](int px, const uint32_t (&yw)[2], const uint32_t (&dw_)[2]) {
+    uint32_t ow[2];
 #pragma unroll
-    for (int u = 0; u < UNR; ++u) {
-      const int px = px0 + u * g.PL;
-      if (px < p1) {
-        const size_t off = base + (size_t)px * g.C;
-        yv[u] = ldg_b64(p.y + off);
-        if (p.dU) dv_[u] = ldg_b64(p.dU + off);
-      }
-    }
-#pragma unroll
-    for (int u = 0; u < UNR; ++u) {
-      const int px = px0 + u * g.PL;
-      if (px >= p1) break;
-      const uint32_t yw[2] = {yv[u].x, yv[u].y}, dw_[2] = {dv_[u].x, dv_[u].y};
-      uint32_t ow[2];
-#pragma unroll
-      for (int i = 0; i < 2; ++i) {
-        const float2 y = bf2_to_f2(yw[i]);
-        const float2 du = p.dU ? bf2_to_f2(dw_[i]) : dvv[i];
-        const float2 yh = fmul2(make_float2(y.x - mu[i].x, y.y - mu[i].y), is[i]);
-        if (MODE == 2) {
-          const float2 v = ffma2r(y, a[i], b[i]);
-          const float2 sg = sigmoid2(v);
-          const float2 u_ = fmul2(v, sg);                                             // swish(v)
-          const float2 sp = fmul2(sg, ffma2r(v, make_float2(1.f - sg.x, 1.f - sg.y), one));   // swish'(v)
-          const float2 dsp = fmul2(du, sp);
-          ffma2(acc[0][i], du, u_);          // d gate
-          ffma2(acc[1][i], dsp, one);        // sum dU s'
-          ffma2(acc[2][i], sp, one);         // sum s'
-          ffma2(acc[3][i], dsp, yh);         // sum dU s' yhat
-          ffma2(acc[4][i], sp, yh);          // sum s' yhat
-          const float2 o = fmul2(u_, gt[i]);
-          ow[i] = pack_bf16(o.x, o.y);
-        } else {
-          float2 dv;
-          if (p.dv_given) dv = du;
-          else {
-            dv = ffma2r(du, gt[i], dp[i]);
-            if (p.act) {
-              const float2 v = ffma2r(y, a[i], b[i]);
-              const float2 sg = sigmoid2(v);
-              dv = fmul2(dv, fmul2(sg, ffma2r(v, make_float2(1.f - sg.x, 1.f - sg.y), one)));
-            }
-          }
-          if (MODE == 0) { ffma2(acc[0][i], dv, one); ffma2(acc[1][i], dv, yh); }
-          else {
-            const float2 t = ffma2r(yh, make_float2(-k2[i].x, -k2[i].y), make_float2(dv.x - k1[i].x, dv.y - k1[i].y));
-            const float2 o = fmul2(a[i], t);
-            ow[i] = pack_bf16(o.x, o.y);
+    for (int i = 0; i < 2; ++i) {
+      const float2 y = bf2_to_f2(yw[i]);
+      const float2 du = p.dU ? bf2_to_f2(dw_[i]) : dvv[i];
+      const float2 yh = fmul2(make_float2(y.x - mu[i].x, y.y - mu[i].y), is[i]);
+      if (MODE == 2) {
+        const float2 v = ffma2r(y, a[i], b[i]);
+        const float2 sg = sigmoid2(v);
+        const float2 u_ = fmul2(v, sg);                                             // swish(v)
+        const float2 sp = fmul2(sg, ffma2r(v, make_float2(1.f - sg.x, 1.f - sg.y), one));   // swish'(v)
+        const float2 dsp = fmul2(du, sp);
+        ffma2(acc[0][i], du, u_);          // d gate
+        ffma2(acc[1][i], dsp, one);        // sum dU s'
+        ffma2(acc[2][i], sp, one);         // sum s'
+        ffma2(acc[3][i], dsp, yh);         // sum dU s' yhat
+        ffma2(acc[4][i], sp, yh);          // sum s' yhat
+        const float2 o = fmul2(u_, gt[i]);
+        ow[i] = pack_bf16(o.x, o.y);
+      } else {
+        float2 dv;
+        if (p.dv_given) dv = du;
+        else {
+          dv = ffma2r(du, gt[i], dp[i]);
+          if (p.act) {
+            const float2 v = ffma2r(y, a[i], b[i]);
+            const float2 sg = sigmoid2(v);
+            dv = fmul2(dv, fmul2(sg, ffma2r(v, make_float2(1.f - sg.x, 1.f - sg.y), one)));
           }
         }
+        if (MODE == 0) { ffma2(acc[0][i], dv, one); ffma2(acc[1][i], dv, yh); }
+        else {
+          const float2 t = ffma2r(yh, make_float2(-k2[i].x, -k2[i].y), make_float2(dv.x - k1[i].x, dv.y - k1[i].y));
+          const float2 o = fmul2(a[i], t);
+          ow[i] = pack_bf16(o.x, o.y);
+        }
       }
-      if (MODE != 0) stg_b64(p.out + base + (size_t)px * g.C, make_uint2(ow[0], ow[1]));
+    }
+    if (MODE != 0) stg_b64(p.out + base + (size_t)px * g.C, make_uint2(ow[0], ow[1]));
+  };
+  if (ASYNC) {
+    // ring slots follow the block-reduction scratch ([PL][CG] floats); slot s of thread t at (s*blockDim + t)*16
+    const uint32_t slot_stride = blockDim.x * 16u;
+    const uint32_t my = smem_u32(ew_smem) + (uint32_t)(g.PL * g.CG) * 4u + threadIdx.x * 16u;
+    const bool has_du = p.dU != nullptr;
+    int px_issue = p0 + pl;
+    auto issue = [&](int slot) {
+      if (px_issue < p1) {
+        const size_t off = base + (size_t)px_issue * g.C;
+        cp_async8(my + slot * slot_stride, p.y + off);
+        if (has_du) cp_async8(my + slot * slot_stride + 8u, p.dU + off);
+      }
+      cp_async_commit();                   // always commit: the wait below counts groups
+      px_issue += g.PL;
+    };
+#pragma unroll
+    for (int s = 0; s < EW_RING - 1; ++s) issue(s);
+    int slot = 0;
+    for (int px = p0 + pl; px < p1; px += g.PL) {
+      issue(slot == 0 ? EW_RING - 1 : slot - 1);          // refill the slot consumed by the previous iteration
+      cp_async_wait<EW_RING - 1>();
+      const uint4 v = lds128(my + slot * slot_stride);
+      const uint32_t yw[2] = {v.x, v.y}, dw_[2] = {v.z, v.w};
+      pixel(px, yw, dw_);
+      slot = slot == EW_RING - 1 ? 0 : slot + 1;
+    }
+    cp_async_wait<0>();
+  } else {
+    constexpr int UNR = (MODE == 2) ? 2 : EW_UNR;
+    for (int px0 = p0 + pl; px0 < p1; px0 += g.PL * UNR) {
+      uint2 yv[UNR], dv_[UNR];
+#pragma unroll
+      for (int u = 0; u < UNR; ++u) {
+        const int px = px0 + u * g.PL;
+        if (px < p1) {
+          const size_t off = base + (size_t)px * g.C;
+          yv[u] = ldg_b64(p.y + off);
+          if (p.dU) dv_[u] = ldg_b64(p.dU + off);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < UNR; ++u) {
+        const int px = px0 + u * g.PL;
+        if (px >= p1) break;
+        const uint32_t yw[2] = {yv[u].x, yv[u].y}, dw_[2] = {dv_[u].x, dv_[u].y};
+        pixel(px, yw, dw_);
+      }
     }
   }
   if (MODE == 0) {
@@ -472,11 +570,28 @@ extern "C" int mclip_ew_backward(const mclip_ew_bwd_args* a, void* stream) {
   p.y = (const bf16*)a->y; p.scale = a->scale; p.shift = a->shift; p.act = a->act; p.dv_given = a->dv_given;
   p.dU = (const bf16*)a->du; p.dvec = a->dvec; p.gate = a->gate; p.dpool = a->dpool; p.rowscale = a->rowscale;
   p.mean = a->mean; p.invstd = a->invstd; p.c1 = a->c1; p.c2 = a->c2; p.part = a->partials; p.out = (bf16*)a->out;
-  const int smem = p.g.PL * p.g.CG * 4;
+  const int red_smem = p.g.PL * p.g.CG * 4;                               // multiple of 16 bytes (CG % 4 == 0)
   const int grid = a->n * p.g.chunks * p.g.G;
-  if (a->mode == 0) mclip_ew_bwd_kernel<0><<<grid, threads, smem, (cudaStream_t)stream>>>(p);
-  else if (a->mode == 1) mclip_ew_bwd_kernel<1><<<grid, threads, smem, (cudaStream_t)stream>>>(p);
-  else mclip_ew_bwd_kernel<2><<<grid, threads, smem, (cudaStream_t)stream>>>(p);
+  cudaStream_t st = (cudaStream_t)stream;
+  // MCLIP_EW_ASYNC: bit m selects the cp.async ring for backward mode m (bit 3: forward pass); default: SE pass 1 only
+  const int async_mask = ew_async_mask();
+  const int ring_smem = red_smem + EW_RING * threads * 16;
+  static int carveout_set = 0;
+  if (!carveout_set) {       // three 36 KB blocks per SM: ask for a shared-memory carveout that holds them
+    MCLIP_CHECK_CUDA(cudaFuncSetAttribute(mclip_ew_bwd_kernel<0, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 60));
+    MCLIP_CHECK_CUDA(cudaFuncSetAttribute(mclip_ew_bwd_kernel<1, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 60));
+    MCLIP_CHECK_CUDA(cudaFuncSetAttribute(mclip_ew_bwd_kernel<2, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 60));
+    carveout_set = 1;
+  }
+  if ((async_mask >> a->mode) & 1) {
+    if (a->mode == 0) mclip_ew_bwd_kernel<0, true><<<grid, threads, ring_smem, st>>>(p);
+    else if (a->mode == 1) mclip_ew_bwd_kernel<1, true><<<grid, threads, ring_smem, st>>>(p);
+    else mclip_ew_bwd_kernel<2, true><<<grid, threads, ring_smem, st>>>(p);
+  } else {
+    if (a->mode == 0) mclip_ew_bwd_kernel<0, false><<<grid, threads, red_smem, st>>>(p);
+    else if (a->mode == 1) mclip_ew_bwd_kernel<1, false><<<grid, threads, red_smem, st>>>(p);
+    else mclip_ew_bwd_kernel<2, false><<<grid, threads, red_smem, st>>>(p);
+  }
   MCLIP_CHECK_LAUNCH();
   return MCLIP_OK;
 }

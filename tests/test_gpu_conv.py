@@ -101,8 +101,42 @@ def test_stem(n, h, w, c, pads, nhwc):
     assert rel_err(dwt, wref.grad) < 2e-3
 
 
+@pytest.fixture(params=[0, 15], ids=["regs", "cp_async_ring"])
+def ew_async(request):
+    """Both staging variants of the streaming passes (registers / per-thread cp.async ring)."""
+    from mammoclip_b200 import _lib
+    old = _lib.lib().mclip_set_ew_async(request.param)
+    yield request.param
+    _lib.lib().mclip_set_ew_async(old)
+
+
+def test_ew_staging_variants_are_bit_identical():
+    from mammoclip_b200 import _lib, ops
+    lib = _lib.lib()
+    n, hw, c = 3, 2011, 240
+    y, du, res = _rand((n, hw, c), 1), _rand((n, hw, c), 2), _rand((n, hw, c), 3)
+    st = ops.BNState(c, "cuda")
+    st.scale.uniform_(0.5, 1.5); st.shift.normal_(0, 0.3); st.mean.normal_(0, 0.2); st.invstd.uniform_(0.5, 1.5)
+    gate, dpool, rs = torch.rand(n, c, device="cuda"), torch.randn(n, c, device="cuda") * 0.01, torch.rand(n, device="cuda") + 0.5
+    c1 = torch.randn(c, device="cuda") * 0.01
+    outs = []
+    old = lib.mclip_set_ew_async(0)
+    try:
+        for mask in (0, 15):
+            lib.mclip_set_ew_async(mask)
+            o, pool = ops.ew_forward(y, bn=st, act=1, rowscale=rs, residual=res, pool=True)
+            part = ops.ew_backward(0, y, st, 1, du=du, gate=gate, dpool=dpool)
+            dy = ops.ew_backward(1, y, st, 1, du=du, gate=gate, dpool=dpool, c1=c1, c2=c1)
+            a2, sep = ops.ew_backward(2, y, st, 1, du=du, gate=gate)
+            outs.append((o, pool, part, dy, a2, sep))
+    finally:
+        lib.mclip_set_ew_async(old)
+    for a, b in zip(*outs):
+        assert torch.equal(a, b)
+
+
 @pytest.mark.parametrize("n,hw,c", [(2, 500, 144), (3, 1392, 1824), (1, 77, 3072), (4, 3000, 24), (2, 999, 1056)])
-def test_bn_and_elementwise(n, hw, c):
+def test_bn_and_elementwise(n, hw, c, ew_async):
     from mammoclip_b200 import ops
     y = _rand((n, hw, c), 8)
     # statistics -> finalize vs torch batch_norm
