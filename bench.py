@@ -42,6 +42,16 @@ def _peaks():
         return 6650.0, 1590.0, "of fallback (B200_PROFILING.md: 6.65 TB/s, 1.59 PFLOP/s)"
 
 
+def _traffic(kernel):
+    """DRAM bytes per launch of the dominant kernel class from the committed ncu capture (profiles/ncu_traffic.json:
+    dram__bytes_read.sum + dram__bytes_write.sum summed over that class' launches of one c3 step / launches), or None."""
+    try:
+        t = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
+        return t.get(kernel)
+    except Exception:
+        return None
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons DURING the timed region."""
     Q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
@@ -354,7 +364,9 @@ def run_ours(args):
                 "steps": e2e_steps},
         "gpu_launches": launches,
         "roofline": {"bound": "hbm", "kernel": dominant, "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
-                     "traffic": None, "launches": dom[0], "avg_launch_ms": dom[1] / max(dom[0], 1), "peak_source": peak_src,
+                     "traffic": (_traffic(dominant) or {}).get("bytes_per_launch") if args.workload == "c3" else None,
+                     "traffic_note": (_traffic(dominant) or {}).get("note"),
+                     "algorithmic_bytes_per_launch": dom[2] / max(dom[0], 1), "launches": dom[0], "avg_launch_ms": dom[1] / max(dom[0], 1), "peak_source": peak_src,
                      "step_share_ms": share,
                      "whole_step": {"algorithmic_gb_per_pair": bytes_pair / 1e9, "achieved_gbs": value / world * bytes_pair / 1e9,
                                     "frac_of_hbm": value / world * bytes_pair / 1e9 / hbm_peak,

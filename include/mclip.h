@@ -272,7 +272,9 @@ int mclip_weight_prep(const void* table_dev, int n_entries, void* stream);
 int mclip_cast_bf16(const float* in, void* out_bf16, long long n, void* stream);
 int mclip_l2norm_forward(const void* x_bf16, float* e, float* norm, int rows, int d, void* stream);
 int mclip_l2norm_backward(const float* e, const float* de, const float* norm, void* dx_bf16, int rows, int d, void* stream);
-int mclip_colsum(const void* x_bf16, float* out, int rows, int cols, long long ld, int accumulate, void* stream);
+long long mclip_colsum_workspace_bytes(int rows, int cols);
+int mclip_colsum(const void* x_bf16, float* out, int rows, int cols, long long ld, int accumulate, void* workspace, long long workspace_bytes,
+                 void* stream);   /* out[c] (+)= sum_r x[r,c]; workspace: fp32 row-split partials (NULL: slow single-pass kernel) */
 
 /* AdamW over a flat fp32 buffer (breastclip/optimizer/__init__.py:23-31: torch.optim.AdamW on all parameters). */
 int mclip_adamw_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, long long n, float lr, float beta1,

@@ -77,6 +77,7 @@ def lib():
     L.mclip_last_error.restype = C.c_char_p
     L.mclip_loss_workspace_bytes.restype = C.c_longlong
     L.mclip_gemm_wgrad_workspace_bytes.restype = C.c_longlong
+    L.mclip_colsum_workspace_bytes.restype = C.c_longlong
     for name in dir(L):
         pass
     _lib = L
@@ -91,7 +92,7 @@ def check(rc: int, what: str = ""):
 
 # kernels launched per ABI call (for bench.py's `gpu_launches`); default 1
 LAUNCHES = {"mclip_gemm_wgrad": 2, "mclip_dwconv_backward": 2, "mclip_se_fc_backward": 2, "mclip_layernorm_backward": 2,
-            "mclip_bert_embed_backward": 4, "mclip_bert_attention_backward": 2}
+            "mclip_bert_embed_backward": 4, "mclip_colsum": 2, "mclip_bert_attention_backward": 2}
 
 
 class Profiler:

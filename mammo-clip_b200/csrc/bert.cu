@@ -606,9 +606,14 @@ __global__ void __launch_bounds__(32 * LNB_WARPS) mclip_bert_embed_bwd_kernel(co
 }
 
 // Pass 2a: word-embedding rows.  CTA t owns token t's id iff no earlier token carries it; the owner sums dv over every
-// token with that id in token order (deterministic, no atomics) and writes the row once.
+// token with that id and writes the row once (no atomics).  The 8 warps take the 32-token groups round-robin and a lane
+// holds H/32 columns, so a heavy hitter (the pad id) is summed by 8 warps with H/32 independent loads in flight each;
+// the cross-warp sum runs in a fixed order => deterministic.
+template <int H>
 __global__ void __launch_bounds__(256) mclip_bert_word_grad_kernel(const long long* __restrict__ ids, const float* __restrict__ dv,
-                                                                   float* __restrict__ dword, int tokens, int H, int vocab, int accumulate) {
+                                                                   float* __restrict__ dword, int tokens, int vocab, int accumulate) {
+  constexpr int PER = H / 32;
+  __shared__ float red[8][H];
   const int t = blockIdx.x;
   long long id = ids[t];
   if (id < 0 || id >= vocab) id = 0;
@@ -619,10 +624,12 @@ __global__ void __launch_bounds__(256) mclip_bert_word_grad_kernel(const long lo
     dup |= (o == id);
   }
   if (__syncthreads_or(dup)) return;
-  float a[4] = {0.f, 0.f, 0.f, 0.f};                      // H <= 1024: columns threadIdx.x + 256*i
-  const int lane = threadIdx.x & 31;
-  for (int u0 = t & ~31; u0 < tokens; u0 += 32) {           // every warp scans 32 ids per step, then visits the matches in order
-    const int u = u0 + lane;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float a[PER];
+#pragma unroll
+  for (int i = 0; i < PER; ++i) a[i] = 0.f;
+  for (int g = (t >> 5) + warp; g * 32 < tokens; g += 8) {
+    const int u = g * 32 + lane;
     bool match = false;
     if (u >= t && u < tokens) {
       long long o = ids[u];
@@ -631,39 +638,59 @@ __global__ void __launch_bounds__(256) mclip_bert_word_grad_kernel(const long lo
     }
     unsigned bal = __ballot_sync(0xffffffffu, match);
     while (bal) {
-      const int uu = u0 + __ffs(bal) - 1;
+      const float* r0 = dv + (size_t)(g * 32 + __ffs(bal) - 1) * H + lane;
       bal &= bal - 1;
+      if (bal) {                                           // two matches per trip: 2*PER loads in flight
+        const float* r1 = dv + (size_t)(g * 32 + __ffs(bal) - 1) * H + lane;
+        bal &= bal - 1;
 #pragma unroll
-      for (int i = 0; i < 4; ++i) { const int h = threadIdx.x + 256 * i; if (h < H) a[i] += dv[(size_t)uu * H + h]; }
+        for (int i = 0; i < PER; ++i) a[i] += r0[i * 32] + r1[i * 32];
+      } else {
+#pragma unroll
+        for (int i = 0; i < PER; ++i) a[i] += r0[i * 32];
+      }
     }
   }
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const int h = threadIdx.x + 256 * i;
-    if (h < H) { float* dst = dword + (size_t)id * H + h; *dst = accumulate ? *dst + a[i] : a[i]; }
+  for (int i = 0; i < PER; ++i) red[warp][lane + i * 32] = a[i];
+  __syncthreads();
+  for (int h = threadIdx.x; h < H; h += 256) {
+    float v = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) v += red[w][h];
+    float* dst = dword + (size_t)id * H + h;
+    *dst = accumulate ? *dst + v : v;
   }
 }
 // Pass 2b: position rows l < L (sum over the batch) and the token-type rows (sum over the tokens of each type).
+// CTA = (32-column chunk, row); the 8 warps stride the samples / tokens, fixed-order smem reduction.
 __global__ void __launch_bounds__(256) mclip_bert_pos_type_grad_kernel(const long long* __restrict__ tts, const float* __restrict__ dv,
                                                                        float* __restrict__ dpos, float* __restrict__ dtype, int batch, int L, int H,
                                                                        int n_types, int accumulate) {
-  const int h = blockIdx.x * 256 + threadIdx.x;
-  if (h >= H) return;
+  __shared__ float red[8][32];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int h = blockIdx.x * 32 + lane;
   const int row = blockIdx.y;
-  if (row < L) {
-    float a = 0.f;
-    for (int b = 0; b < batch; ++b) a += dv[((size_t)b * L + row) * H + h];
-    float* dst = dpos + (size_t)row * H + h;
-    *dst = accumulate ? *dst + a : a;
-  } else {
-    const int ty = row - L;
-    float a = 0.f;
-    for (int u = 0; u < batch * L; ++u) {
-      const long long tt = tts ? tts[u] : 0;
-      if (tt == ty) a += dv[(size_t)u * H + h];
+  float a = 0.f;
+  if (h < H) {
+    if (row < L) {
+      for (int b = warp; b < batch; b += 8) a += dv[((size_t)b * L + row) * H + h];
+    } else {
+      const int ty = row - L;
+      for (int u = warp; u < batch * L; u += 8) {
+        const long long tt = tts ? tts[u] : 0;
+        if (tt == ty) a += dv[(size_t)u * H + h];
+      }
     }
-    float* dst = dtype + (size_t)ty * H + h;
-    *dst = accumulate ? *dst + a : a;
+  }
+  red[warp][lane] = a;
+  __syncthreads();
+  if (warp == 0 && h < H) {
+    float v = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) v += red[w][lane];
+    float* dst = row < L ? dpos + (size_t)row * H + h : dtype + (size_t)(row - L) * H + h;
+    *dst = accumulate ? *dst + v : v;
   }
 }
 
@@ -751,9 +778,9 @@ extern "C" int mclip_bert_embed_backward(const mclip_bert_embed_bwd_args* a, voi
   MCLIP_CHECK_LAUNCH();
   mclip_ln_param_grad_kernel<<<ceil_div(2 * a->hidden, 256), 256, 0, stream>>>(a->partials, a->slots, a->hidden, a->dgamma, a->dbeta, a->accumulate);
   MCLIP_CHECK_LAUNCH();
-  mclip_bert_word_grad_kernel<<<tokens, 256, 0, stream>>>((const long long*)a->input_ids, a->dv, a->dword, tokens, a->hidden, a->vocab, a->accumulate);
+  mclip_bert_word_grad_kernel<768><<<tokens, 256, 0, stream>>>((const long long*)a->input_ids, a->dv, a->dword, tokens, a->vocab, a->accumulate);
   MCLIP_CHECK_LAUNCH();
-  dim3 grid(ceil_div(a->hidden, 256), a->seq_len + a->n_types);
+  dim3 grid(ceil_div(a->hidden, 32), a->seq_len + a->n_types);
   mclip_bert_pos_type_grad_kernel<<<grid, 256, 0, stream>>>((const long long*)a->token_type_ids, a->dv, a->dpos, a->dtype, a->batch, a->seq_len, a->hidden,
                                                             a->n_types, a->accumulate);
   MCLIP_CHECK_LAUNCH();

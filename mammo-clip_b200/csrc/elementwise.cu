@@ -18,7 +18,7 @@
 #define EW_MAX_THREADS 256
 #define EW_CPT 4            // channels per thread (8-byte vectors; a warp still covers 256 contiguous bytes)
 #define EW_UNR 4            // pixels in flight per thread
-#define EW_ASYNC_DEFAULT 4   // see mclip_ew_backward: which passes stage their inputs through the cp.async ring
+#define EW_ASYNC_DEFAULT 15  // see mclip_ew_backward: which passes stage their inputs through the cp.async ring
 
 typedef unsigned long long u64;
 __device__ __forceinline__ float2 bf2_to_f2(uint32_t u) { return make_float2(__uint_as_float(u << 16), __uint_as_float(u & 0xffff0000u)); }
@@ -116,9 +116,9 @@ __device__ __forceinline__ void ew_block_reduce4(float* smem, const float2* v, i
 // ------------------------------------------------------------------------------------------------
 // BatchNorm statistics -> affine (a = gamma*invstd, b = beta - mean*a), running-stat update
 // ------------------------------------------------------------------------------------------------
-// 256 threads = 32 channels x 8 slot lanes: each lane strides over the partial slots, fp64 tree-combine in smem
+// 1024 threads = 32 channels x 32 slot lanes: each lane strides over the partial slots (up to N*chunks ~ 2400 of them), fp64 combine in smem
 #define BNF_CH 32
-#define BNF_LANES 8
+#define BNF_LANES 32
 __device__ __forceinline__ void bn_reduce_slots(const float* __restrict__ partials, int slots, int C, int c, int lane, double& s, double& q,
                                                 double (*sm)[BNF_LANES][BNF_CH]) {
   s = 0.0; q = 0.0;
@@ -706,24 +706,44 @@ extern "C" int mclip_se_fc_backward(const mclip_se_args* a, void* stream) {
 // ------------------------------------------------------------------------------------------------
 // fp32 master weights -> bf16 operands (straight and transposed), table driven: one launch for a whole tower
 // ------------------------------------------------------------------------------------------------
-__global__ void mclip_weight_prep_kernel(const mclip_prep_entry* __restrict__ table, int n_entries) {
+// 32x32 tiles through shared memory: coalesced fp32 reads, coalesced bf16 writes of both the straight and the transposed copy
+__global__ void __launch_bounds__(256) mclip_weight_prep_kernel(const mclip_prep_entry* __restrict__ table, int n_entries) {
+  __shared__ bf16 tile[32][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;          // 32 x 8
   for (int e = blockIdx.y; e < n_entries; e += gridDim.y) {
     const mclip_prep_entry t = table[e];
-    const long long total = (long long)t.rows * t.cols;
     const float* src = (const float*)t.src;
     bf16* dst = (bf16*)t.dst;
     bf16* dstT = (bf16*)t.dst_t;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-      const bf16 v = __float2bfloat16_rn(src[i]);
-      if (dst) { if (t.dst_ld > 0) dst[(i / t.cols) * t.dst_ld + i % t.cols] = v; else dst[i] = v; }
-      if (dstT) { const long long r = i / t.cols, c = i % t.cols; dstT[c * (t.dst_t_ld > 0 ? t.dst_t_ld : t.rows) + r] = v; }
+    const int ld = t.dst_ld > 0 ? t.dst_ld : t.cols, ldt = t.dst_t_ld > 0 ? t.dst_t_ld : t.rows;
+    const int tiles_c = (t.cols + 31) >> 5, tiles_r = (t.rows + 31) >> 5;
+    for (int tl = blockIdx.x; tl < tiles_c * tiles_r; tl += gridDim.x) {
+      const int r0 = (tl / tiles_c) << 5, c0 = (tl % tiles_c) << 5;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int r = r0 + ty + 8 * i, c = c0 + tx;
+        if (r < t.rows && c < t.cols) {
+          const bf16 v = __float2bfloat16_rn(src[(size_t)r * t.cols + c]);
+          if (dst) dst[(size_t)r * ld + c] = v;
+          tile[ty + 8 * i][tx] = v;
+        }
+      }
+      if (dstT) {
+        __syncthreads();
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int c = c0 + ty + 8 * i, r = r0 + tx;              // transposed copy: row c, column r
+          if (r < t.rows && c < t.cols) dstT[(size_t)c * ldt + r] = tile[tx][ty + 8 * i];
+        }
+        __syncthreads();
+      }
     }
   }
 }
 
 extern "C" int mclip_weight_prep(const void* table_dev, int n_entries, void* stream) {
   MCLIP_REQUIRE(table_dev && n_entries > 0, "mclip_weight_prep: empty table");
-  dim3 grid(16, n_entries < 1024 ? n_entries : 1024);
+  dim3 grid(32, n_entries < 1024 ? n_entries : 1024);
   mclip_weight_prep_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const mclip_prep_entry*)table_dev, n_entries);
   MCLIP_CHECK_LAUNCH();
   return MCLIP_OK;
@@ -786,17 +806,20 @@ __global__ void mclip_colsum_kernel(const bf16* __restrict__ x, float* __restric
   for (int r = 0; r < rows; ++r) s += __bfloat162float(x[(size_t)r * ld + c]);
   out[c] = accumulate ? out[c] + s : s;
 }
-// 64 columns per CTA (one bf16x2 per lane), 16 warps stride the rows, fixed-order smem reduction (deterministic)
-#define COLSUM_WARPS 16
-__global__ void __launch_bounds__(32 * COLSUM_WARPS) mclip_colsum2_kernel(const bf16* __restrict__ x, float* __restrict__ out, int rows, int cols, long long ld,
-                                                                          int accumulate) {
+// Stage 1: CTA (column chunk of 64, row split): 8 warps stride the split's rows, one bf16x2 per lane, fixed-order smem
+// reduction -> partial[split][cols].  Stage 2: out[c] (+)= sum_splits partial (fixed order => deterministic).
+#define COLSUM_WARPS 8
+#define COLSUM_MAX_SPLITS 64
+__global__ void __launch_bounds__(32 * COLSUM_WARPS) mclip_colsum_part_kernel(const bf16* __restrict__ x, float* __restrict__ partial, int rows, int cols,
+                                                                              long long ld, int rows_per_split) {
   __shared__ float red[COLSUM_WARPS][64];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int c = blockIdx.x * 64 + lane * 2;
+  const int r0 = blockIdx.y * rows_per_split, r1 = min(rows, r0 + rows_per_split);
   float s0 = 0.f, s1 = 0.f;
   if (c < cols) {
 #pragma unroll 4
-    for (int r = warp; r < rows; r += COLSUM_WARPS) {
+    for (int r = r0 + warp; r < r1; r += COLSUM_WARPS) {
       const uint32_t w = *reinterpret_cast<const uint32_t*>(x + (size_t)r * ld + c);
       s0 += bf16_lo(w); s1 += bf16_hi(w);
     }
@@ -807,16 +830,35 @@ __global__ void __launch_bounds__(32 * COLSUM_WARPS) mclip_colsum2_kernel(const 
     float a = 0.f;
 #pragma unroll
     for (int w = 0; w < COLSUM_WARPS; ++w) a += red[w][threadIdx.x];
-    float* o = out + blockIdx.x * 64 + threadIdx.x;
-    *o = accumulate ? *o + a : a;
+    partial[(size_t)blockIdx.y * cols + blockIdx.x * 64 + threadIdx.x] = a;
   }
 }
-extern "C" int mclip_colsum(const void* x, float* out, int rows, int cols, long long ld, int accumulate, void* stream) {
+__global__ void mclip_colsum_final_kernel(const float* __restrict__ partial, float* __restrict__ out, int splits, int cols, int accumulate) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= cols) return;
+  float a = 0.f;
+  for (int s = 0; s < splits; ++s) a += partial[(size_t)s * cols + c];
+  out[c] = accumulate ? out[c] + a : a;
+}
+static int colsum_splits(int rows) {
+  int s = ceil_div(rows, 64);                      // >= 64 rows (8 per warp) per split
+  return s < 1 ? 1 : (s > COLSUM_MAX_SPLITS ? COLSUM_MAX_SPLITS : s);
+}
+extern "C" long long mclip_colsum_workspace_bytes(int rows, int cols) { return (long long)colsum_splits(rows) * cols * 4; }
+extern "C" int mclip_colsum(const void* x, float* out, int rows, int cols, long long ld, int accumulate, void* workspace, long long workspace_bytes,
+                            void* stream) {
   MCLIP_REQUIRE(x && out && rows > 0 && cols > 0, "mclip_colsum: bad arguments");
-  if (cols % 2 == 0 && ld % 2 == 0 && ((uintptr_t)x & 3) == 0)
-    mclip_colsum2_kernel<<<ceil_div(cols, 64), 32 * COLSUM_WARPS, 0, (cudaStream_t)stream>>>((const bf16*)x, out, rows, cols, ld, accumulate);
-  else
+  if (cols % 2 == 0 && ld % 2 == 0 && ((uintptr_t)x & 3) == 0 && workspace) {
+    const int splits = colsum_splits(rows);
+    MCLIP_REQUIRE(workspace_bytes >= (long long)splits * cols * 4, "mclip_colsum: workspace too small (%lld < %lld)", workspace_bytes,
+                  (long long)splits * cols * 4);
+    dim3 grid(ceil_div(cols, 64), splits);
+    mclip_colsum_part_kernel<<<grid, 32 * COLSUM_WARPS, 0, (cudaStream_t)stream>>>((const bf16*)x, (float*)workspace, rows, cols, ld, ceil_div(rows, splits));
+    MCLIP_CHECK_LAUNCH();
+    mclip_colsum_final_kernel<<<ceil_div(cols, 256), 256, 0, (cudaStream_t)stream>>>((const float*)workspace, out, splits, cols, accumulate);
+  } else {
     mclip_colsum_kernel<<<ceil_div(cols, 128), 128, 0, (cudaStream_t)stream>>>((const bf16*)x, out, rows, cols, ld, accumulate);
+  }
   MCLIP_CHECK_LAUNCH();
   return MCLIP_OK;
 }

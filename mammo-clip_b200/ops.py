@@ -400,10 +400,18 @@ def l2norm_backward(e, de, nrm):
     return dx
 
 
+_colsum_ws = {}
+
+
 def colsum(x, out, accumulate=False):
     rows, cols = x.shape
     assert x.stride(1) == 1
-    call("mclip_colsum", ptr(x), ptr(out), rows, cols, C.c_longlong(x.stride(0)), int(accumulate))
+    need = lib().mclip_colsum_workspace_bytes(rows, cols)
+    ws = _colsum_ws.get(x.device.index)
+    if ws is None or ws.numel() < need:
+        ws = torch.empty(max(need, 1 << 20), dtype=torch.uint8, device=x.device)
+        _colsum_ws[x.device.index] = ws
+    call("mclip_colsum", ptr(x), ptr(out), rows, cols, C.c_longlong(x.stride(0)), int(accumulate), ptr(ws), C.c_longlong(ws.numel()))
     return out
 
 

@@ -79,3 +79,35 @@ def test_gemm_wgrad(r, i, j):
     assert err < 2e-3, f"wgrad {r}x{i}x{j}: rel err {err}"
     out2 = ops.gemm_wgrad(a, b, out=out.clone(), accumulate=True)
     assert rel_err(out2, 2 * ref) < 2e-3
+
+
+@pytest.mark.parametrize("rows,cols,ld_extra", [(4096, 768, 0), (4096, 768, 1536), (513, 3072, 0), (7, 512, 0), (64, 6, 2)])
+def test_colsum(rows, cols, ld_extra):
+    """Bias gradients: column sums of a (possibly column-sliced) bf16 matrix, written or accumulated."""
+    from mammoclip_b200 import ops
+    torch.manual_seed(rows + cols)
+    full = torch.randn(rows, cols + ld_extra, device="cuda").bfloat16()
+    x = full[:, ld_extra // 2: ld_extra // 2 + cols]
+    out = torch.empty(cols, device="cuda")
+    ops.colsum(x, out)
+    ref = x.double().sum(0)
+    assert ((out.double() - ref).abs().max() / ref.abs().max()).item() < 1e-5
+    ops.colsum(x, out, accumulate=True)
+    assert ((out.double() - 2 * ref).abs().max() / ref.abs().max()).item() < 1e-5
+
+
+def test_weight_prep_straight_and_transposed_copies():
+    """fp32 master weights -> bf16 operands: row-strided destination (stem), transposed copy, fused-QKV layout with strides."""
+    from mammoclip_b200 import ops
+    torch.manual_seed(0)
+    a, b, q = torch.randn(100, 27, device="cuda"), torch.randn(3072, 768, device="cuda"), [torch.randn(768, 768, device="cuda") for _ in range(3)]
+    a_d = torch.zeros(100, 32, dtype=torch.bfloat16, device="cuda")
+    b_d, b_t = torch.empty(3072, 768, dtype=torch.bfloat16, device="cuda"), torch.empty(768, 3072, dtype=torch.bfloat16, device="cuda")
+    qkv, qkv_t = torch.empty(2304, 768, dtype=torch.bfloat16, device="cuda"), torch.empty(768, 2304, dtype=torch.bfloat16, device="cuda")
+    entries = [(a, a_d, None, 32), (b, b_d, b_t), (b, None, b_t)]
+    entries += [(q[i], qkv[i * 768:(i + 1) * 768], qkv_t[:, i * 768:(i + 1) * 768], 0, 2304) for i in range(3)]
+    table = ops.weight_prep(entries, a.device)
+    ops.weight_prep_run(table, len(entries))
+    assert torch.equal(a_d[:, :27], a.bfloat16()) and a_d[:, 27:].abs().max().item() == 0
+    assert torch.equal(b_d, b.bfloat16()) and torch.equal(b_t, b.bfloat16().t())
+    assert torch.equal(qkv, torch.cat(q).bfloat16()) and torch.equal(qkv_t, torch.cat(q).bfloat16().t())
