@@ -17,8 +17,10 @@
 #include <cudaTypedefs.h>
 #include <stdlib.h>
 
-#define GEMM_EPI_WARPS 8
-#define GEMM_THREADS (64 + 32 * GEMM_EPI_WARPS)
+// Epilogue warps per CTA: 8 (two 64-column slabs per warp and tile, double-buffered staging) or 16 (one slab per warp, single
+// staging buffer: twice the warps to hide the tcgen05.ld -> pack -> st.shared -> TMA-store -> statistics chain of the
+// write-heavy small-K GEMMs).  Selected per launch (MCLIP_GEMM_EPI16 / mclip_set_gemm_epi16).
+#define GEMM_STAGING_BYTES (64 * 1024)   // 8 warps x 2 buffers or 16 warps x 1 buffer of one 32x64 bf16 slab
 #define GEMM_BM 128
 #define GEMM_BK 64
 #define GEMM_SLAB_BYTES 4096          // 32 rows x 64 bf16, 128B-swizzled
@@ -81,7 +83,8 @@ static int make_tmap_bf16_3d(CUtensorMap* m, const void* ptr, unsigned long long
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ float gelu_erf(float v) { return 0.5f * v * (1.0f + erff(v * 0.70710678118654752f)); }
 
-__global__ void __launch_bounds__(GEMM_THREADS, 1)
+template <int GEMM_EPI_WARPS>
+__global__ void __launch_bounds__(64 + 32 * GEMM_EPI_WARPS, 1)
 mclip_gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                      const __grid_constant__ CUtensorMap tmD, const GemmDev p) {
   extern __shared__ uint8_t smem_raw[];
@@ -91,7 +94,9 @@ mclip_gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
   const uint32_t stage_bytes = p.small_k ? a_bytes : a_bytes + b_bytes;
   uint8_t* bpanel = smem + (size_t)p.stages * stage_bytes;
   uint8_t* dstage = bpanel + (p.small_k ? b_bytes : 0);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(dstage + GEMM_EPI_WARPS * 2 * GEMM_SLAB_BYTES);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(dstage + GEMM_STAGING_BYTES);
+  constexpr int NBUF = GEMM_STAGING_BYTES / (GEMM_EPI_WARPS * GEMM_SLAB_BYTES);     // staging buffers per epilogue warp (2 or 1)
+  constexpr int SLAB_STEP = GEMM_EPI_WARPS / 4;                                       // slabs between two of a warp's slabs
   uint64_t* full = bars;
   uint64_t* empty = bars + p.stages;
   uint64_t* tfull = bars + 2 * p.stages;
@@ -214,9 +219,9 @@ mclip_gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
     // ---------------- epilogue warps ----------------
     const int ew = warp - 2;
     const int q = warp & 3;                 // TMEM lane quarter this warp may read
-    const int h = ew >> 2;                  // which half of the 64-column slabs
+    const int h = ew >> 2;                  // first 64-column slab of this warp
     const int nslabs = (p.block_n + 63) >> 6;
-    uint8_t* my_buf = dstage + (size_t)ew * 2 * GEMM_SLAB_BYTES;
+    uint8_t* my_buf = dstage + (size_t)ew * NBUF * GEMM_SLAB_BYTES;
     float st_sum[2][2] = {{0.f, 0.f}, {0.f, 0.f}}, st_sq[2][2] = {{0.f, 0.f}, {0.f, 0.f}};
     int as = 0; uint32_t aphase = 0; int buf = 0;
     for (int mt = mt0; mt < p.m_tiles_total; mt += mt_step) {
@@ -226,22 +231,31 @@ mclip_gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
       mbar_wait(&tfull[as], aphase);
       tc_fence_after();
       for (int si = 0; si < 2; ++si) {
-        const int s = h + 2 * si;
+        const int s = h + SLAB_STEP * si;
         if (s >= nslabs) break;
         const int c0 = n0 + s * 64;
         if (c0 >= p.N) break;
         uint8_t* sb = my_buf + (size_t)buf * GEMM_SLAB_BYTES;
-        if (lane == 0) tma_store_wait_read1();     // the store issued two slabs ago (same buffer) has drained
+        if (lane == 0) { if (NBUF == 2) tma_store_wait_read1(); else tma_store_wait_read0(); }   // the last store from this buffer has drained
         __syncwarp();
-        uint32_t r[64];
-        if (!(p.debug & 4)) tmem_ld64(tmem_base + (uint32_t)as * 256u + (uint32_t)(s * 64) + ((uint32_t)(q * 32) << 16), r);
-        tmem_ld_wait();
+        // 8 warps: one 64-column load per slab; 16 warps (tighter register budget): two 32-column loads
+        constexpr int LDW = GEMM_EPI_WARPS == 8 ? 64 : 32;
+        uint32_t r[LDW];
+        const uint32_t taddr = tmem_base + (uint32_t)as * 256u + (uint32_t)(s * 64) + ((uint32_t)(q * 32) << 16);
+        if (LDW == 64) {
+          if (!(p.debug & 4)) tmem_ld64(taddr, r);
+          tmem_ld_wait();
+        }
 #pragma unroll
         for (int ch = 0; ch < 4; ++ch) {
           if (s * 64 + ch * 16 >= p.block_n) break;          // warp-uniform: columns past block_n hold no result
+          if (LDW == 32 && (ch & 1) == 0) {
+            if (!(p.debug & 4)) tmem_ld32(taddr + (uint32_t)(ch * 16), r);
+            tmem_ld_wait();
+          }
           float v[16];
 #pragma unroll
-          for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[ch * 16 + i]);
+          for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[(ch * 16) % LDW + i]);
           const int cc = c0 + ch * 16;
           if (p.bias) {
 #pragma unroll
@@ -308,7 +322,7 @@ mclip_gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
           }
           st_sum[si][0] += s0; st_sum[si][1] += s1; st_sq[si][0] += q0; st_sq[si][1] += q1;
         }
-        buf ^= 1;
+        if (NBUF == 2) buf ^= 1;
       }
       tc_fence_before();
       __syncwarp();
@@ -318,7 +332,7 @@ mclip_gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
     if (p.stats) {
       const int slot = (blockIdx.x / p.n_blocks) * 4 + q;
       for (int si = 0; si < 2; ++si) {
-        const int s = h + 2 * si;
+        const int s = h + SLAB_STEP * si;
         if (s >= nslabs) break;
         const int col = n0 + s * 64 + lane * 2;
         // columns of this n block that belong to a later n block (block_n not a multiple of 64) are skipped
@@ -350,6 +364,14 @@ static int pick_block_n(int N, int* n_blocks) {
   *n_blocks = ceil_div(N, best);
   return best;
 }
+
+#define GEMM_EPI16_DEFAULT 0
+static int g_gemm_epi16 = -1;
+static int gemm_epi16() {
+  if (g_gemm_epi16 < 0) { const char* e = getenv("MCLIP_GEMM_EPI16"); g_gemm_epi16 = e ? (atoi(e) != 0) : GEMM_EPI16_DEFAULT; }
+  return g_gemm_epi16;
+}
+extern "C" int mclip_set_gemm_epi16(int on) { const int old = gemm_epi16(); g_gemm_epi16 = on != 0; return old; }
 
 extern "C" int mclip_gemm_tn_stat_slots(int M, int N, int batches) {
   int nb; pick_block_n(N, &nb);
@@ -385,7 +407,7 @@ extern "C" int mclip_gemm_tn(const mclip_gemm_args* g, void* stream_) {
   if (getenv("MCLIP_GEMM_NO_SMALLK")) p.small_k = 0;
   p.a_ptr = (const bf16*)g->a; p.lda = g->lda; p.a_bs = g->a_batch_stride;
   const int stage_bytes = p.small_k ? GEMM_BM * GEMM_BK * 2 : GEMM_BM * GEMM_BK * 2 + p.block_n * GEMM_BK * 2;
-  const int fixed = GEMM_EPI_WARPS * 2 * GEMM_SLAB_BYTES + 256 + 1024 + (p.small_k ? p.block_n * GEMM_BK * 2 : 0);
+  const int fixed = GEMM_STAGING_BYTES + 256 + 1024 + (p.small_k ? p.block_n * GEMM_BK * 2 : 0);
   p.stages = (GEMM_SMEM_LIMIT - fixed) / stage_bytes;
   if (p.stages > 8) p.stages = 8;
   if (p.small_k) MCLIP_REQUIRE(p.stages >= 6, "mclip_gemm_tn: small-K mode needs 6 stages");   // always true for block_n <= 256
@@ -403,10 +425,12 @@ extern "C" int mclip_gemm_tn(const mclip_gemm_args* g, void* stream_) {
   if (g->stats) MCLIP_REQUIRE(g->stat_slots == grid / p.n_blocks * 4, "mclip_gemm_tn: stat_slots=%d, expected %d", g->stat_slots, grid / p.n_blocks * 4);
   static int attr_set = 0;
   if (!attr_set) {
-    MCLIP_CHECK_CUDA(cudaFuncSetAttribute(mclip_gemm_tn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_LIMIT));
+    MCLIP_CHECK_CUDA(cudaFuncSetAttribute(mclip_gemm_tn_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_LIMIT));
+    MCLIP_CHECK_CUDA(cudaFuncSetAttribute(mclip_gemm_tn_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_LIMIT));
     attr_set = 1;
   }
-  mclip_gemm_tn_kernel<<<grid, GEMM_THREADS, smem, stream>>>(tmA, tmB, tmD, p);
+  if (gemm_epi16()) mclip_gemm_tn_kernel<16><<<grid, 64 + 32 * 16, smem, stream>>>(tmA, tmB, tmD, p);
+  else mclip_gemm_tn_kernel<8><<<grid, 64 + 32 * 8, smem, stream>>>(tmA, tmB, tmD, p);
   MCLIP_CHECK_LAUNCH();
   return MCLIP_OK;
 }

@@ -111,3 +111,40 @@ def test_weight_prep_straight_and_transposed_copies():
     assert torch.equal(a_d[:, :27], a.bfloat16()) and a_d[:, 27:].abs().max().item() == 0
     assert torch.equal(b_d, b.bfloat16()) and torch.equal(b_t, b.bfloat16().t())
     assert torch.equal(qkv, torch.cat(q).bfloat16()) and torch.equal(qkv_t, torch.cat(q).bfloat16().t())
+
+
+def test_gemm_tn_pre_activation_copy_and_dropout_epilogue():
+    """aux_pre receives the bf16 value before GELU (BertIntermediate backward); dropout keep-mask + residual epilogue."""
+    from mammoclip_b200 import ops
+    m, n, k = 1000, 3072, 768
+    a, w = _mk((m, k), 12), _mk((n, k), 13, 1.0 / k ** 0.5)
+    bias = torch.randn(n, device="cuda")
+    pre = torch.empty((m, n), dtype=torch.bfloat16, device="cuda")
+    out = ops.gemm_tn(a, w, bias=bias, act=1, aux_pre=pre)
+    ref_pre = a.float() @ w.float().T + bias
+    assert rel_err(pre.float(), ref_pre) < 6e-3
+    assert rel_err(out.float(), torch.nn.functional.gelu(ref_pre)) < 6e-3
+    keep = (torch.rand(m, n, device="cuda") >= 0.1).to(torch.uint8)
+    res = _mk((m, n), 14)
+    out = ops.gemm_tn(a, w, bias=bias, residual=res, dropmask=keep, drop_scale=1.0 / 0.9)
+    assert rel_err(out.float(), ref_pre * keep / 0.9 + res.float()) < 6e-3
+
+
+@pytest.mark.parametrize("bt,m,n,k", [(1, 4096, 240, 40), (1, 20000, 24, 144), (1, 4096, 3072, 768), (1, 2784, 304, 1824), (3, 1392, 176, 1056)])
+def test_gemm_tn_epilogue_warp_variants_are_bit_identical(bt, m, n, k):
+    """8 epilogue warps (two slabs each) vs 16 (one slab each): same output and BatchNorm partials, bit for bit."""
+    from mammoclip_b200 import _lib, ops
+    lib = _lib.lib()
+    a = _mk((bt, m, k) if bt > 1 else (m, k), 15)
+    w = _mk((bt, n, k) if bt > 1 else (n, k), 16, 1.0 / k ** 0.5)
+    bias = torch.randn(n, device="cuda")
+    old = lib.mclip_set_gemm_epi16(0)
+    try:
+        o8, s8 = ops.gemm_tn(a, w, bias=bias, want_stats=True)
+        lib.mclip_set_gemm_epi16(1)
+        o16, s16 = ops.gemm_tn(a, w, bias=bias, want_stats=True)
+    finally:
+        lib.mclip_set_gemm_epi16(old)
+    assert torch.equal(o8, o16) and torch.equal(s8, s16)
+    ref = (torch.einsum("bmk,bnk->bmn", a.float(), w.float()) if bt > 1 else a.float() @ w.float().T) + bias
+    assert rel_err(o16.float(), ref) < 6e-3
