@@ -83,7 +83,10 @@ static int make_tmap_bf16_3d(CUtensorMap* m, const void* ptr, unsigned long long
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ float gelu_erf(float v) { return 0.5f * v * (1.0f + erff(v * 0.70710678118654752f)); }
 
-template <int GEMM_EPI_WARPS>
+// PLAIN: no bias / activation / pre-activation copy / dropout mask / residual in the epilogue (the MBConv forward convs and
+// most data gradients).  Compiling those paths out shrinks the unrolled epilogue (the generic kernel is ~5000 SASS
+// instructions and stalls on instruction fetch: smsp "no_instruction" ~ 0.9 per issue in profiles/r01c_ncu_gemm_expand_blk4).
+template <int GEMM_EPI_WARPS, bool PLAIN>
 __global__ void __launch_bounds__(64 + 32 * GEMM_EPI_WARPS, 1)
 mclip_gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                      const __grid_constant__ CUtensorMap tmD, const GemmDev p) {
@@ -257,27 +260,27 @@ mclip_gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
 #pragma unroll
           for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[(ch * 16) % LDW + i]);
           const int cc = c0 + ch * 16;
-          if (p.bias) {
+          if (!PLAIN && p.bias) {
 #pragma unroll
             for (int i = 0; i < 16; ++i) if (cc + i < p.N) v[i] += __ldg(p.bias + cc + i);
           }
-          if (p.aux && row < p.M) {
+          if (!PLAIN && p.aux && row < p.M) {
             bf16* ap = p.aux + ((size_t)b * p.M + row) * p.aux_ld + cc;
 #pragma unroll
             for (int g = 0; g < 2; ++g)
               if (cc + g * 8 < p.N) stg_bf16x8(ap + g * 8, pack8(v + g * 8));
           }
-          if (p.act == 1) {
+          if (!PLAIN && p.act == 1) {
 #pragma unroll
             for (int i = 0; i < 16; ++i) v[i] = gelu_erf(v[i]);
           }
-          if (p.dropmask && row < p.M) {
+          if (!PLAIN && p.dropmask && row < p.M) {
             const uint4 mk = *reinterpret_cast<const uint4*>(p.dropmask + ((size_t)b * p.M + row) * p.N + cc);   // N % 16 == 0 required
             const uint32_t mw[4] = {mk.x, mk.y, mk.z, mk.w};
 #pragma unroll
             for (int i = 0; i < 16; ++i) v[i] *= ((mw[i >> 2] >> ((i & 3) * 8)) & 0xffu) ? p.drop_scale : 0.f;
           }
-          if (p.residual && row < p.M) {
+          if (!PLAIN && p.residual && row < p.M) {
             const bf16* rp = p.residual + (size_t)b * p.res_bs + (size_t)row * p.res_ld + cc;
 #pragma unroll
             for (int g = 0; g < 2; ++g) {
@@ -425,12 +428,20 @@ extern "C" int mclip_gemm_tn(const mclip_gemm_args* g, void* stream_) {
   if (g->stats) MCLIP_REQUIRE(g->stat_slots == grid / p.n_blocks * 4, "mclip_gemm_tn: stat_slots=%d, expected %d", g->stat_slots, grid / p.n_blocks * 4);
   static int attr_set = 0;
   if (!attr_set) {
-    MCLIP_CHECK_CUDA(cudaFuncSetAttribute(mclip_gemm_tn_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_LIMIT));
-    MCLIP_CHECK_CUDA(cudaFuncSetAttribute(mclip_gemm_tn_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_LIMIT));
+    MCLIP_CHECK_CUDA(cudaFuncSetAttribute(mclip_gemm_tn_kernel<8, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_LIMIT));
+    MCLIP_CHECK_CUDA(cudaFuncSetAttribute(mclip_gemm_tn_kernel<8, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_LIMIT));
+    MCLIP_CHECK_CUDA(cudaFuncSetAttribute(mclip_gemm_tn_kernel<16, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_LIMIT));
+    MCLIP_CHECK_CUDA(cudaFuncSetAttribute(mclip_gemm_tn_kernel<16, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_LIMIT));
     attr_set = 1;
   }
-  if (gemm_epi16()) mclip_gemm_tn_kernel<16><<<grid, 64 + 32 * 16, smem, stream>>>(tmA, tmB, tmD, p);
-  else mclip_gemm_tn_kernel<8><<<grid, 64 + 32 * 8, smem, stream>>>(tmA, tmB, tmD, p);
+  const bool plain = !p.bias && !p.residual && !p.dropmask && !p.aux && p.act == 0 && !getenv("MCLIP_GEMM_NO_PLAIN");
+  if (gemm_epi16()) {
+    if (plain) mclip_gemm_tn_kernel<16, true><<<grid, 64 + 32 * 16, smem, stream>>>(tmA, tmB, tmD, p);
+    else mclip_gemm_tn_kernel<16, false><<<grid, 64 + 32 * 16, smem, stream>>>(tmA, tmB, tmD, p);
+  } else {
+    if (plain) mclip_gemm_tn_kernel<8, true><<<grid, 64 + 32 * 8, smem, stream>>>(tmA, tmB, tmD, p);
+    else mclip_gemm_tn_kernel<8, false><<<grid, 64 + 32 * 8, smem, stream>>>(tmA, tmB, tmD, p);
+  }
   MCLIP_CHECK_LAUNCH();
   return MCLIP_OK;
 }
