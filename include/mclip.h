@@ -84,9 +84,6 @@ typedef struct mclip_gemm_args {
                                                      activation's backward (BertIntermediate's GELU) */
 } mclip_gemm_args;
 int mclip_gemm_tn_stat_slots(int m, int n, int batches);
-/* Tuning switch: 16 epilogue warps per CTA (one 64-column slab each) instead of 8 (two slabs each).  Same results bit for
- * bit; returns the previous setting.  Initial value: env MCLIP_GEMM_EPI16, else the built-in default. */
-int mclip_set_gemm_epi16(int on);
 int mclip_gemm_tn(const mclip_gemm_args* args, void* stream);
 
 /* mclip_gemm_wgrad: out[i,j] (+)= sum_r A[r,i] B[r,j]  (bf16 in, fp32 out) — weight gradient of a 1x1 convolution /

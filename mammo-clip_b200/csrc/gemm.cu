@@ -17,10 +17,9 @@
 #include <cudaTypedefs.h>
 #include <stdlib.h>
 
-// Epilogue warps per CTA: 8 (two 64-column slabs per warp and tile, double-buffered staging) or 16 (one slab per warp, single
-// staging buffer: twice the warps to hide the tcgen05.ld -> pack -> st.shared -> TMA-store -> statistics chain of the
-// write-heavy small-K GEMMs).  Selected per launch (MCLIP_GEMM_EPI16 / mclip_set_gemm_epi16).
-#define GEMM_STAGING_BYTES (64 * 1024)   // 8 warps x 2 buffers or 16 warps x 1 buffer of one 32x64 bf16 slab
+#define GEMM_EPI_WARPS 8              // two 64-column slabs per warp and tile, double-buffered staging
+#define GEMM_THREADS (64 + 32 * GEMM_EPI_WARPS)
+#define GEMM_STAGING_BYTES (GEMM_EPI_WARPS * 2 * 4096)
 #define GEMM_BM 128
 #define GEMM_BK 64
 #define GEMM_SLAB_BYTES 4096          // 32 rows x 64 bf16, 128B-swizzled
@@ -83,11 +82,14 @@ static int make_tmap_bf16_3d(CUtensorMap* m, const void* ptr, unsigned long long
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ float gelu_erf(float v) { return 0.5f * v * (1.0f + erff(v * 0.70710678118654752f)); }
 
-// PLAIN: no bias / activation / pre-activation copy / dropout mask / residual in the epilogue (the MBConv forward convs and
-// most data gradients).  Compiling those paths out shrinks the unrolled epilogue (the generic kernel is ~5000 SASS
-// instructions and stalls on instruction fetch: smsp "no_instruction" ~ 0.9 per issue in profiles/r01c_ncu_gemm_expand_blk4).
-template <int GEMM_EPI_WARPS, bool PLAIN>
-__global__ void __launch_bounds__(64 + 32 * GEMM_EPI_WARPS, 1)
+// Epilogue instantiations.  MODE 0: plain (the MBConv forward convs and most data gradients); 1: + residual (the
+// data gradient of a block with a skip connection); 2: everything (bias, pre-activation copy, erf-GELU, dropout mask,
+// residual: the BERT / head Linears).  STATS: BatchNorm (sum, sum sq) partials.  The epilogue is straight-line code that
+// every warp runs once per tile, so its SIZE is its cost: the all-in-one, fully unrolled version (~5000 SASS
+// instructions) stalled on instruction fetch (smsp "no_instruction" ~0.9 per issue, profiles/r01c_ncu_gemm_expand_blk4)
+// and ran the small-K convolutions at 2-3 TB/s; compiling unused paths out and rolling the 32-column loop gives 5+.
+template <int MODE, bool STATS>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
 mclip_gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                      const __grid_constant__ CUtensorMap tmD, const GemmDev p) {
   extern __shared__ uint8_t smem_raw[];
@@ -98,8 +100,7 @@ mclip_gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
   uint8_t* bpanel = smem + (size_t)p.stages * stage_bytes;
   uint8_t* dstage = bpanel + (p.small_k ? b_bytes : 0);
   uint64_t* bars = reinterpret_cast<uint64_t*>(dstage + GEMM_STAGING_BYTES);
-  constexpr int NBUF = GEMM_STAGING_BYTES / (GEMM_EPI_WARPS * GEMM_SLAB_BYTES);     // staging buffers per epilogue warp (2 or 1)
-  constexpr int SLAB_STEP = GEMM_EPI_WARPS / 4;                                       // slabs between two of a warp's slabs
+
   uint64_t* full = bars;
   uint64_t* empty = bars + p.stages;
   uint64_t* tfull = bars + 2 * p.stages;
@@ -222,9 +223,9 @@ mclip_gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
     // ---------------- epilogue warps ----------------
     const int ew = warp - 2;
     const int q = warp & 3;                 // TMEM lane quarter this warp may read
-    const int h = ew >> 2;                  // first 64-column slab of this warp
+    const int h = ew >> 2;                  // which half of the 64-column slabs
     const int nslabs = (p.block_n + 63) >> 6;
-    uint8_t* my_buf = dstage + (size_t)ew * NBUF * GEMM_SLAB_BYTES;
+    uint8_t* my_buf = dstage + (size_t)ew * 2 * GEMM_SLAB_BYTES;
     float st_sum[2][2] = {{0.f, 0.f}, {0.f, 0.f}}, st_sq[2][2] = {{0.f, 0.f}, {0.f, 0.f}};
     int as = 0; uint32_t aphase = 0; int buf = 0;
     for (int mt = mt0; mt < p.m_tiles_total; mt += mt_step) {
@@ -233,109 +234,101 @@ mclip_gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
       const int nvalid = min(32, max(0, p.M - (m0 + q * 32)));
       mbar_wait(&tfull[as], aphase);
       tc_fence_after();
+#pragma unroll
       for (int si = 0; si < 2; ++si) {
-        const int s = h + SLAB_STEP * si;
+        const int s = h + 2 * si;
         if (s >= nslabs) break;
         const int c0 = n0 + s * 64;
         if (c0 >= p.N) break;
         uint8_t* sb = my_buf + (size_t)buf * GEMM_SLAB_BYTES;
-        if (lane == 0) { if (NBUF == 2) tma_store_wait_read1(); else tma_store_wait_read0(); }   // the last store from this buffer has drained
+        if (lane == 0) tma_store_wait_read1();     // the store issued two slabs ago (same buffer) has drained
         __syncwarp();
-        // 8 warps: one 64-column load per slab; 16 warps (tighter register budget): two 32-column loads
-        constexpr int LDW = GEMM_EPI_WARPS == 8 ? 64 : 32;
-        uint32_t r[LDW];
         const uint32_t taddr = tmem_base + (uint32_t)as * 256u + (uint32_t)(s * 64) + ((uint32_t)(q * 32) << 16);
-        if (LDW == 64) {
-          if (!(p.debug & 4)) tmem_ld64(taddr, r);
+#pragma unroll 1
+        for (int hf = 0; hf < 2; ++hf) {                      // rolled on purpose: 32 columns per trip keeps the code small
+          if (s * 64 + hf * 32 >= p.block_n) break;           // warp-uniform: columns past block_n hold no result
+          uint32_t r[32];
+          if (!(p.debug & 4)) tmem_ld32(taddr + (uint32_t)(hf * 32), r);
           tmem_ld_wait();
-        }
 #pragma unroll
-        for (int ch = 0; ch < 4; ++ch) {
-          if (s * 64 + ch * 16 >= p.block_n) break;          // warp-uniform: columns past block_n hold no result
-          if (LDW == 32 && (ch & 1) == 0) {
-            if (!(p.debug & 4)) tmem_ld32(taddr + (uint32_t)(ch * 16), r);
-            tmem_ld_wait();
-          }
-          float v[16];
+          for (int c2 = 0; c2 < 2; ++c2) {
+            const int ch = hf * 2 + c2;
+            float v[16];
 #pragma unroll
-          for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[(ch * 16) % LDW + i]);
-          const int cc = c0 + ch * 16;
-          if (!PLAIN && p.bias) {
+            for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[c2 * 16 + i]);
+            const int cc = c0 + ch * 16;
+            if (MODE == 2) {
+              if (p.bias) {
 #pragma unroll
-            for (int i = 0; i < 16; ++i) if (cc + i < p.N) v[i] += __ldg(p.bias + cc + i);
-          }
-          if (!PLAIN && p.aux && row < p.M) {
-            bf16* ap = p.aux + ((size_t)b * p.M + row) * p.aux_ld + cc;
+                for (int i = 0; i < 16; ++i) if (cc + i < p.N) v[i] += __ldg(p.bias + cc + i);
+              }
+              if (p.aux && row < p.M) {
+                bf16* ap = p.aux + ((size_t)b * p.M + row) * p.aux_ld + cc;
 #pragma unroll
-            for (int g = 0; g < 2; ++g)
-              if (cc + g * 8 < p.N) stg_bf16x8(ap + g * 8, pack8(v + g * 8));
-          }
-          if (!PLAIN && p.act == 1) {
+                for (int g = 0; g < 2; ++g)
+                  if (cc + g * 8 < p.N) stg_bf16x8(ap + g * 8, pack8(v + g * 8));
+              }
+              if (p.act == 1) {
 #pragma unroll
-            for (int i = 0; i < 16; ++i) v[i] = gelu_erf(v[i]);
-          }
-          if (!PLAIN && p.dropmask && row < p.M) {
-            const uint4 mk = *reinterpret_cast<const uint4*>(p.dropmask + ((size_t)b * p.M + row) * p.N + cc);   // N % 16 == 0 required
-            const uint32_t mw[4] = {mk.x, mk.y, mk.z, mk.w};
+                for (int i = 0; i < 16; ++i) v[i] = gelu_erf(v[i]);
+              }
+              if (p.dropmask && row < p.M && cc < p.N) {
+                const uint4 mk = *reinterpret_cast<const uint4*>(p.dropmask + ((size_t)b * p.M + row) * p.N + cc);   // N % 16 == 0 required
+                const uint32_t mw[4] = {mk.x, mk.y, mk.z, mk.w};
 #pragma unroll
-            for (int i = 0; i < 16; ++i) v[i] *= ((mw[i >> 2] >> ((i & 3) * 8)) & 0xffu) ? p.drop_scale : 0.f;
-          }
-          if (!PLAIN && p.residual && row < p.M) {
-            const bf16* rp = p.residual + (size_t)b * p.res_bs + (size_t)row * p.res_ld + cc;
-#pragma unroll
-            for (int g = 0; g < 2; ++g) {
-              if (cc + g * 8 < p.N) {                // N is a multiple of 8
-                bf16x8 rv = ldg_bf16x8(rp + g * 8);
-                float f[8]; unpack8(rv, f);
-#pragma unroll
-                for (int i = 0; i < 8; ++i) v[g * 8 + i] += f[i];
+                for (int i = 0; i < 16; ++i) v[i] *= ((mw[i >> 2] >> ((i & 3) * 8)) & 0xffu) ? p.drop_scale : 0.f;
               }
             }
-          }
+            if (MODE >= 1 && p.residual && row < p.M) {
+              const bf16* rp = p.residual + (size_t)b * p.res_bs + (size_t)row * p.res_ld + cc;
 #pragma unroll
-          for (int g = 0; g < 2; ++g) {
-            const int chunk = ch * 2 + g;
-            uint4 pk;
-            pk.x = pack_bf16(v[g * 8 + 0], v[g * 8 + 1]); pk.y = pack_bf16(v[g * 8 + 2], v[g * 8 + 3]);
-            pk.z = pack_bf16(v[g * 8 + 4], v[g * 8 + 5]); pk.w = pack_bf16(v[g * 8 + 6], v[g * 8 + 7]);
-            *reinterpret_cast<uint4*>(sb + lane * 128 + ((chunk ^ (lane & 7)) << 4)) = pk;
+              for (int g = 0; g < 2; ++g) {
+                if (cc + g * 8 < p.N) {                // N is a multiple of 8
+                  bf16x8 rv = ldg_bf16x8(rp + g * 8);
+                  float f[8]; unpack8(rv, f);
+#pragma unroll
+                  for (int i = 0; i < 8; ++i) v[g * 8 + i] += f[i];
+                }
+              }
+            }
+#pragma unroll
+            for (int g = 0; g < 2; ++g) {
+              const int chunk = ch * 2 + g;
+              uint4 pk;
+              pk.x = pack_bf16(v[g * 8 + 0], v[g * 8 + 1]); pk.y = pack_bf16(v[g * 8 + 2], v[g * 8 + 3]);
+              pk.z = pack_bf16(v[g * 8 + 4], v[g * 8 + 5]); pk.w = pack_bf16(v[g * 8 + 6], v[g * 8 + 7]);
+              *reinterpret_cast<uint4*>(sb + lane * 128 + ((chunk ^ (lane & 7)) << 4)) = pk;
+            }
           }
         }
         fence_proxy_async_smem();
         __syncwarp();
         if (lane == 0 && !(p.debug & 2)) { tma_store_3d(&tmD, sb, c0, m0 + q * 32, b); tma_store_commit(); }
-        if (p.stats) {
-          // column sums over this warp's valid rows, read back from the swizzled slab (conflict-free)
+        if (STATS) {
+          // column sums over this warp's valid rows, read back from the swizzled slab (conflict-free); rows in order
           float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
           const uint8_t* colp = sb + (lane & 3) * 4;
           const int cq = lane >> 2;
-          if (nvalid == 32) {
-#pragma unroll
-            for (int r2 = 0; r2 < 32; ++r2) {
-              uint32_t w = *reinterpret_cast<const uint32_t*>(colp + r2 * 128 + ((cq ^ (r2 & 7)) << 4));
-              float a0 = bf16_lo(w), a1 = bf16_hi(w);
-              s0 += a0; s1 += a1; q0 = fmaf(a0, a0, q0); q1 = fmaf(a1, a1, q1);
-            }
-          } else {
-            for (int r2 = 0; r2 < nvalid; ++r2) {
-              uint32_t w = *reinterpret_cast<const uint32_t*>(colp + r2 * 128 + ((cq ^ (r2 & 7)) << 4));
-              float a0 = bf16_lo(w), a1 = bf16_hi(w);
-              s0 += a0; s1 += a1; q0 = fmaf(a0, a0, q0); q1 = fmaf(a1, a1, q1);
-            }
+#pragma unroll 4
+          for (int r2 = 0; r2 < nvalid; ++r2) {
+            uint32_t w = *reinterpret_cast<const uint32_t*>(colp + r2 * 128 + ((cq ^ (r2 & 7)) << 4));
+            float a0 = bf16_lo(w), a1 = bf16_hi(w);
+            s0 += a0; s1 += a1; q0 = fmaf(a0, a0, q0); q1 = fmaf(a1, a1, q1);
           }
           st_sum[si][0] += s0; st_sum[si][1] += s1; st_sq[si][0] += q0; st_sq[si][1] += q1;
         }
-        if (NBUF == 2) buf ^= 1;
+        buf ^= 1;
       }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty[as]);
       as ^= 1; if (as == 0) aphase ^= 1;
     }
-    if (p.stats) {
+    if (STATS) {
       const int slot = (blockIdx.x / p.n_blocks) * 4 + q;
+#pragma unroll
       for (int si = 0; si < 2; ++si) {
-        const int s = h + SLAB_STEP * si;
+        const int s = h + 2 * si;
         if (s >= nslabs) break;
         const int col = n0 + s * 64 + lane * 2;
         // columns of this n block that belong to a later n block (block_n not a multiple of 64) are skipped
@@ -367,14 +360,6 @@ static int pick_block_n(int N, int* n_blocks) {
   *n_blocks = ceil_div(N, best);
   return best;
 }
-
-#define GEMM_EPI16_DEFAULT 0
-static int g_gemm_epi16 = -1;
-static int gemm_epi16() {
-  if (g_gemm_epi16 < 0) { const char* e = getenv("MCLIP_GEMM_EPI16"); g_gemm_epi16 = e ? (atoi(e) != 0) : GEMM_EPI16_DEFAULT; }
-  return g_gemm_epi16;
-}
-extern "C" int mclip_set_gemm_epi16(int on) { const int old = gemm_epi16(); g_gemm_epi16 = on != 0; return old; }
 
 extern "C" int mclip_gemm_tn_stat_slots(int M, int N, int batches) {
   int nb; pick_block_n(N, &nb);
@@ -426,22 +411,19 @@ extern "C" int mclip_gemm_tn(const mclip_gemm_args* g, void* stream_) {
   long long tiles = (long long)p.m_tiles_total * p.n_blocks;
   int grid = tiles < cap ? (int)tiles : cap;
   if (g->stats) MCLIP_REQUIRE(g->stat_slots == grid / p.n_blocks * 4, "mclip_gemm_tn: stat_slots=%d, expected %d", g->stat_slots, grid / p.n_blocks * 4);
+  typedef void (*kern_t)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const GemmDev);
+  static const kern_t kerns[3][2] = {{mclip_gemm_tn_kernel<0, false>, mclip_gemm_tn_kernel<0, true>},
+                                     {mclip_gemm_tn_kernel<1, false>, mclip_gemm_tn_kernel<1, true>},
+                                     {mclip_gemm_tn_kernel<2, false>, mclip_gemm_tn_kernel<2, true>}};
   static int attr_set = 0;
   if (!attr_set) {
-    MCLIP_CHECK_CUDA(cudaFuncSetAttribute(mclip_gemm_tn_kernel<8, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_LIMIT));
-    MCLIP_CHECK_CUDA(cudaFuncSetAttribute(mclip_gemm_tn_kernel<8, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_LIMIT));
-    MCLIP_CHECK_CUDA(cudaFuncSetAttribute(mclip_gemm_tn_kernel<16, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_LIMIT));
-    MCLIP_CHECK_CUDA(cudaFuncSetAttribute(mclip_gemm_tn_kernel<16, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_LIMIT));
+    for (int m = 0; m < 3; ++m)
+      for (int t = 0; t < 2; ++t) MCLIP_CHECK_CUDA(cudaFuncSetAttribute(kerns[m][t], cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_LIMIT));
     attr_set = 1;
   }
-  const bool plain = !p.bias && !p.residual && !p.dropmask && !p.aux && p.act == 0 && !getenv("MCLIP_GEMM_NO_PLAIN");
-  if (gemm_epi16()) {
-    if (plain) mclip_gemm_tn_kernel<16, true><<<grid, 64 + 32 * 16, smem, stream>>>(tmA, tmB, tmD, p);
-    else mclip_gemm_tn_kernel<16, false><<<grid, 64 + 32 * 16, smem, stream>>>(tmA, tmB, tmD, p);
-  } else {
-    if (plain) mclip_gemm_tn_kernel<8, true><<<grid, 64 + 32 * 8, smem, stream>>>(tmA, tmB, tmD, p);
-    else mclip_gemm_tn_kernel<8, false><<<grid, 64 + 32 * 8, smem, stream>>>(tmA, tmB, tmD, p);
-  }
+  int mode = (p.bias || p.dropmask || p.aux || p.act != 0) ? 2 : (p.residual ? 1 : 0);
+  if (getenv("MCLIP_GEMM_GENERIC")) mode = 2;                 // experiments: force the all-in-one epilogue
+  kerns[mode][p.stats ? 1 : 0]<<<grid, GEMM_THREADS, smem, stream>>>(tmA, tmB, tmD, p);
   MCLIP_CHECK_LAUNCH();
   return MCLIP_OK;
 }

@@ -38,14 +38,10 @@ def main():
     ap.add_argument("--w", type=int, default=912)
     ap.add_argument("--only", default="")
     ap.add_argument("--ew-async", type=int, default=-1, help="mclip_set_ew_async mask (-1: library default)")
-    ap.add_argument("--gemm-epi16", type=int, default=-1, help="mclip_set_gemm_epi16 (-1: library default)")
     args = ap.parse_args()
     if args.ew_async >= 0:
         from mammoclip_b200 import _lib
         _lib.lib().mclip_set_ew_async(args.ew_async)
-    if args.gemm_epi16 >= 0:
-        from mammoclip_b200 import _lib
-        _lib.lib().mclip_set_gemm_epi16(args.gemm_epi16)
     g = net_geometry(args.name)
     n = args.batch
     pl, pr, pt, pb = g.stem_pads
