@@ -87,7 +87,8 @@ __device__ __forceinline__ float gelu_erf(float v) { return 0.5f * v * (1.0f + e
 // residual: the BERT / head Linears).  STATS: BatchNorm (sum, sum sq) partials.  The epilogue is straight-line code that
 // every warp runs once per tile, so its SIZE is its cost: the all-in-one, fully unrolled version (~5000 SASS
 // instructions) stalled on instruction fetch (smsp "no_instruction" ~0.9 per issue, profiles/r01c_ncu_gemm_expand_blk4)
-// and ran the small-K convolutions at 2-3 TB/s; compiling unused paths out and rolling the 32-column loop gives 5+.
+// and ran the small-K convolutions at 2-3 TB/s; compiling the unused paths out gives 3.5-5.  (Rolling the column loop into two
+// 32-column trips shrinks the code further but pays a second TMEM-load wait per slab: measured slower, not kept.)
 template <int MODE, bool STATS>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 mclip_gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
@@ -244,76 +245,80 @@ mclip_gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         if (lane == 0) tma_store_wait_read1();     // the store issued two slabs ago (same buffer) has drained
         __syncwarp();
         const uint32_t taddr = tmem_base + (uint32_t)as * 256u + (uint32_t)(s * 64) + ((uint32_t)(q * 32) << 16);
-#pragma unroll 1
-        for (int hf = 0; hf < 2; ++hf) {                      // rolled on purpose: 32 columns per trip keeps the code small
-          if (s * 64 + hf * 32 >= p.block_n) break;           // warp-uniform: columns past block_n hold no result
-          uint32_t r[32];
-          if (!(p.debug & 4)) tmem_ld32(taddr + (uint32_t)(hf * 32), r);
-          tmem_ld_wait();
+        uint32_t r[64];                                       // one 64-column TMEM load and ONE wait per slab
+        if (!(p.debug & 4)) tmem_ld64(taddr, r);
+        tmem_ld_wait();
 #pragma unroll
-          for (int c2 = 0; c2 < 2; ++c2) {
-            const int ch = hf * 2 + c2;
-            float v[16];
+        for (int ch = 0; ch < 4; ++ch) {
+          if (s * 64 + ch * 16 >= p.block_n) break;           // warp-uniform: columns past block_n hold no result
+          float v[16];
 #pragma unroll
-            for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[c2 * 16 + i]);
-            const int cc = c0 + ch * 16;
-            if (MODE == 2) {
-              if (p.bias) {
+          for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[ch * 16 + i]);
+          const int cc = c0 + ch * 16;
+          if (MODE == 2) {
+            if (p.bias) {
 #pragma unroll
-                for (int i = 0; i < 16; ++i) if (cc + i < p.N) v[i] += __ldg(p.bias + cc + i);
-              }
-              if (p.aux && row < p.M) {
-                bf16* ap = p.aux + ((size_t)b * p.M + row) * p.aux_ld + cc;
-#pragma unroll
-                for (int g = 0; g < 2; ++g)
-                  if (cc + g * 8 < p.N) stg_bf16x8(ap + g * 8, pack8(v + g * 8));
-              }
-              if (p.act == 1) {
-#pragma unroll
-                for (int i = 0; i < 16; ++i) v[i] = gelu_erf(v[i]);
-              }
-              if (p.dropmask && row < p.M && cc < p.N) {
-                const uint4 mk = *reinterpret_cast<const uint4*>(p.dropmask + ((size_t)b * p.M + row) * p.N + cc);   // N % 16 == 0 required
-                const uint32_t mw[4] = {mk.x, mk.y, mk.z, mk.w};
-#pragma unroll
-                for (int i = 0; i < 16; ++i) v[i] *= ((mw[i >> 2] >> ((i & 3) * 8)) & 0xffu) ? p.drop_scale : 0.f;
-              }
+              for (int i = 0; i < 16; ++i) if (cc + i < p.N) v[i] += __ldg(p.bias + cc + i);
             }
-            if (MODE >= 1 && p.residual && row < p.M) {
-              const bf16* rp = p.residual + (size_t)b * p.res_bs + (size_t)row * p.res_ld + cc;
+            if (p.aux && row < p.M) {
+              bf16* ap = p.aux + ((size_t)b * p.M + row) * p.aux_ld + cc;
 #pragma unroll
-              for (int g = 0; g < 2; ++g) {
-                if (cc + g * 8 < p.N) {                // N is a multiple of 8
-                  bf16x8 rv = ldg_bf16x8(rp + g * 8);
-                  float f[8]; unpack8(rv, f);
-#pragma unroll
-                  for (int i = 0; i < 8; ++i) v[g * 8 + i] += f[i];
-                }
-              }
+              for (int g = 0; g < 2; ++g)
+                if (cc + g * 8 < p.N) stg_bf16x8(ap + g * 8, pack8(v + g * 8));
             }
+            if (p.act == 1) {
+#pragma unroll
+              for (int i = 0; i < 16; ++i) v[i] = gelu_erf(v[i]);
+            }
+            if (p.dropmask && row < p.M && cc < p.N) {
+              const uint4 mk = *reinterpret_cast<const uint4*>(p.dropmask + ((size_t)b * p.M + row) * p.N + cc);   // N % 16 == 0 required
+              const uint32_t mw[4] = {mk.x, mk.y, mk.z, mk.w};
+#pragma unroll
+              for (int i = 0; i < 16; ++i) v[i] *= ((mw[i >> 2] >> ((i & 3) * 8)) & 0xffu) ? p.drop_scale : 0.f;
+            }
+          }
+          if (MODE >= 1 && p.residual && row < p.M) {
+            const bf16* rp = p.residual + (size_t)b * p.res_bs + (size_t)row * p.res_ld + cc;
 #pragma unroll
             for (int g = 0; g < 2; ++g) {
-              const int chunk = ch * 2 + g;
-              uint4 pk;
-              pk.x = pack_bf16(v[g * 8 + 0], v[g * 8 + 1]); pk.y = pack_bf16(v[g * 8 + 2], v[g * 8 + 3]);
-              pk.z = pack_bf16(v[g * 8 + 4], v[g * 8 + 5]); pk.w = pack_bf16(v[g * 8 + 6], v[g * 8 + 7]);
-              *reinterpret_cast<uint4*>(sb + lane * 128 + ((chunk ^ (lane & 7)) << 4)) = pk;
+              if (cc + g * 8 < p.N) {                // N is a multiple of 8
+                bf16x8 rv = ldg_bf16x8(rp + g * 8);
+                float f[8]; unpack8(rv, f);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) v[g * 8 + i] += f[i];
+              }
             }
+          }
+#pragma unroll
+          for (int g = 0; g < 2; ++g) {
+            const int chunk = ch * 2 + g;
+            uint4 pk;
+            pk.x = pack_bf16(v[g * 8 + 0], v[g * 8 + 1]); pk.y = pack_bf16(v[g * 8 + 2], v[g * 8 + 3]);
+            pk.z = pack_bf16(v[g * 8 + 4], v[g * 8 + 5]); pk.w = pack_bf16(v[g * 8 + 6], v[g * 8 + 7]);
+            *reinterpret_cast<uint4*>(sb + lane * 128 + ((chunk ^ (lane & 7)) << 4)) = pk;
           }
         }
         fence_proxy_async_smem();
         __syncwarp();
         if (lane == 0 && !(p.debug & 2)) { tma_store_3d(&tmD, sb, c0, m0 + q * 32, b); tma_store_commit(); }
-        if (STATS) {
+        if (STATS && (MODE != 2 || p.stats)) {
           // column sums over this warp's valid rows, read back from the swizzled slab (conflict-free); rows in order
           float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
           const uint8_t* colp = sb + (lane & 3) * 4;
           const int cq = lane >> 2;
-#pragma unroll 4
-          for (int r2 = 0; r2 < nvalid; ++r2) {
-            uint32_t w = *reinterpret_cast<const uint32_t*>(colp + r2 * 128 + ((cq ^ (r2 & 7)) << 4));
-            float a0 = bf16_lo(w), a1 = bf16_hi(w);
-            s0 += a0; s1 += a1; q0 = fmaf(a0, a0, q0); q1 = fmaf(a1, a1, q1);
+          if (nvalid == 32) {
+#pragma unroll
+            for (int r2 = 0; r2 < 32; ++r2) {
+              uint32_t w = *reinterpret_cast<const uint32_t*>(colp + r2 * 128 + ((cq ^ (r2 & 7)) << 4));
+              float a0 = bf16_lo(w), a1 = bf16_hi(w);
+              s0 += a0; s1 += a1; q0 = fmaf(a0, a0, q0); q1 = fmaf(a1, a1, q1);
+            }
+          } else {
+            for (int r2 = 0; r2 < nvalid; ++r2) {
+              uint32_t w = *reinterpret_cast<const uint32_t*>(colp + r2 * 128 + ((cq ^ (r2 & 7)) << 4));
+              float a0 = bf16_lo(w), a1 = bf16_hi(w);
+              s0 += a0; s1 += a1; q0 = fmaf(a0, a0, q0); q1 = fmaf(a1, a1, q1);
+            }
           }
           st_sum[si][0] += s0; st_sum[si][1] += s1; st_sq[si][0] += q0; st_sq[si][1] += q1;
         }
@@ -324,7 +329,7 @@ mclip_gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
       if (lane == 0) mbar_arrive(&tempty[as]);
       as ^= 1; if (as == 0) aphase ^= 1;
     }
-    if (STATS) {
+    if (STATS && (MODE != 2 || p.stats)) {
       const int slot = (blockIdx.x / p.n_blocks) * 4 + q;
 #pragma unroll
       for (int si = 0; si < 2; ++si) {
@@ -423,7 +428,8 @@ extern "C" int mclip_gemm_tn(const mclip_gemm_args* g, void* stream_) {
   }
   int mode = (p.bias || p.dropmask || p.aux || p.act != 0) ? 2 : (p.residual ? 1 : 0);
   if (getenv("MCLIP_GEMM_GENERIC")) mode = 2;                 // experiments: force the all-in-one epilogue
-  kerns[mode][p.stats ? 1 : 0]<<<grid, GEMM_THREADS, smem, stream>>>(tmA, tmB, tmD, p);
+  // the generic epilogue is instantiated once (STATS checked at run time there: its no-statistics build spills)
+  kerns[mode][(p.stats || mode == 2) ? 1 : 0]<<<grid, GEMM_THREADS, smem, stream>>>(tmA, tmB, tmD, p);
   MCLIP_CHECK_LAUNCH();
   return MCLIP_OK;
 }
