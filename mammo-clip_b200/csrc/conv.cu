@@ -192,6 +192,9 @@ __global__ void __launch_bounds__(DW_THREADS, 4) mclip_dwconv_fwd_kernel(const _
       dw_transform_tile(tile, pix, oy0 * S - p.pt, ox0 * S - p.pl, IH, IW, p.H, p.W, p.C, c0, p.scale, p.shift, p.act);
       named_bar_sync(1, DW_THREADS);
     }
+    // patch loops stay ROLLED: their trip counts are small constants and nvcc would unroll them into several thousand SASS
+    // instructions that every warp walks through once per tile (instruction-fetch stalls, cf. the GEMM epilogue)
+#pragma unroll 1
     for (int pa = warp; pa < (TH / PRO) * (TW / 4); pa += DW_WARPS) {
       const int py = (pa / (TW / 4)) * PRO, px = (pa % (TW / 4)) * 4;
       const int y0 = oy0 + py, x0 = ox0 + px;
@@ -350,6 +353,7 @@ mclip_dwconv_bwd_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_c
     };
 
     // ---- weight gradient over the owned outputs: dW[ky,kx] += dY[oy,ox] * A[oy*S+ky, ox*S+kx] ----
+#pragma unroll 1
     for (int pa = warp; pa < (TH / 2) * (TW / 4); pa += DW_WARPS) {
       const int py = (pa / (TW / 4)) * 2, px = (pa % (TW / 4)) * 4;
       if (oy0 + py >= p.Ho || ox0 + px >= p.Wo) continue;
@@ -383,6 +387,7 @@ mclip_dwconv_bwd_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_c
 
     // ---- data gradient over the owned inputs ----
     if constexpr (S == 1) {
+#pragma unroll 1
       for (int pa = warp; pa < (TH / 2) * (TW / 4); pa += DW_WARPS) {
         const int ly = (pa / (TW / 4)) * 2, lx = (pa % (TW / 4)) * 4;
         const int y0 = iy0 + ly, x0 = ix0 + lx;
@@ -407,6 +412,7 @@ mclip_dwconv_bwd_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_c
       // work item = one input row, one x parity, 4 same-parity pixels (consecutive dY columns).
       constexpr int NT = (K + 1) / 2;                                // taps per axis per parity class (max)
       constexpr int OWN_H = TH * 2, OWN_W = TW * 2;
+#pragma unroll 1
       for (int it = warp; it < OWN_H * 2 * (OWN_W / 8); it += DW_WARPS) {
         const int ly = it / (2 * (OWN_W / 8)), rem = it % (2 * (OWN_W / 8));
         const int par = rem / (OWN_W / 8), strip = rem % (OWN_W / 8);
