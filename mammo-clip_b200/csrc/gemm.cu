@@ -303,27 +303,23 @@ mclip_gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         if (lane == 0 && !(p.debug & 2)) { tma_store_3d(&tmD, sb, c0, m0 + q * 32, b); tma_store_commit(); }
         if (STATS && (MODE != 2 || p.stats)) {
           // column sums over this warp's valid rows, read back from the swizzled slab (conflict-free); rows in order
-          // packed fp32x2 math (FADD2 / FFMA2): the two columns of a lane advance with one instruction each
-          unsigned long long sq2 = 0ull, ss2 = 0ull;           // (q0, q1) and (s0, s1) as f32x2 bit patterns
-          const unsigned long long one2 = 0x3f8000003f800000ull;
+          float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
           const uint8_t* colp = sb + (lane & 3) * 4;
           const int cq = lane >> 2;
-          auto add_row = [&](int r2) {
-            const uint32_t w = *reinterpret_cast<const uint32_t*>(colp + r2 * 128 + ((cq ^ (r2 & 7)) << 4));
-            unsigned long long a2;
-            asm("mov.b64 %0, {%1, %2};" : "=l"(a2) : "r"(w << 16), "r"(w & 0xffff0000u));
-            asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(ss2) : "l"(a2), "l"(one2));
-            asm("fma.rn.f32x2 %0, %1, %1, %0;" : "+l"(sq2) : "l"(a2));
-          };
           if (nvalid == 32) {
-#pragma unroll 8
-            for (int r2 = 0; r2 < 32; ++r2) add_row(r2);
+#pragma unroll
+            for (int r2 = 0; r2 < 32; ++r2) {
+              uint32_t w = *reinterpret_cast<const uint32_t*>(colp + r2 * 128 + ((cq ^ (r2 & 7)) << 4));
+              float a0 = bf16_lo(w), a1 = bf16_hi(w);
+              s0 += a0; s1 += a1; q0 = fmaf(a0, a0, q0); q1 = fmaf(a1, a1, q1);
+            }
           } else {
-            for (int r2 = 0; r2 < nvalid; ++r2) add_row(r2);
+            for (int r2 = 0; r2 < nvalid; ++r2) {
+              uint32_t w = *reinterpret_cast<const uint32_t*>(colp + r2 * 128 + ((cq ^ (r2 & 7)) << 4));
+              float a0 = bf16_lo(w), a1 = bf16_hi(w);
+              s0 += a0; s1 += a1; q0 = fmaf(a0, a0, q0); q1 = fmaf(a1, a1, q1);
+            }
           }
-          float s0, s1, q0, q1;
-          asm("mov.b64 {%0, %1}, %2;" : "=f"(s0), "=f"(s1) : "l"(ss2));
-          asm("mov.b64 {%0, %1}, %2;" : "=f"(q0), "=f"(q1) : "l"(sq2));
           st_sum[si][0] += s0; st_sum[si][1] += s1; st_sq[si][0] += q0; st_sq[si][1] += q1;
         }
         buf ^= 1;
