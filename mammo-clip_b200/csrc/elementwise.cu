@@ -316,7 +316,7 @@ extern "C" int mclip_pool_finalize(const float* partials, int n, int chunks, int
 // squeeze-excite FC stack, one CTA per sample
 //   s = pooled mean ; z1 = W1 s + b1 ; h = swish(z1) ; z2 = W2 h + b2 ; g = sigmoid(z2)
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) mclip_se_fc_kernel(const float* __restrict__ part, int chunks, int C, int Cse, float inv_hw,
+__global__ void __launch_bounds__(1024) mclip_se_fc_kernel(const float* __restrict__ part, int chunks, int C, int Cse, float inv_hw,
                                                           const float* __restrict__ W1, const float* __restrict__ b1, const float* __restrict__ W2,
                                                           const float* __restrict__ b2, float* __restrict__ s_out, float* __restrict__ z1_out,
                                                           float* __restrict__ gate) {
@@ -344,19 +344,20 @@ __global__ void __launch_bounds__(256) mclip_se_fc_kernel(const float* __restric
     }
   }
   __syncthreads();
-  // one warp per output channel, lanes over the squeeze dimension: W2 rows are read coalesced
-  for (int c = warp; c < C; c += nw) {
-    float v = 0.f;
-    for (int j = lane; j < Cse; j += 32) v = fmaf(W2[(size_t)c * Cse + j], h[j], v);
-    v = warp_sum(v);
-    if (lane == 0) gate[(size_t)n * C + c] = sigmoid_precise(v + b2[c]);
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float v = b2[c];
+    for (int j = 0; j < Cse; ++j) v = fmaf(W2[(size_t)c * Cse + j], h[j], v);
+    gate[(size_t)n * C + c] = sigmoid_precise(v);
   }
 }
 
 extern "C" int mclip_se_fc(const mclip_se_args* a, void* stream) {
   MCLIP_REQUIRE(a && a->pool_partials && a->w1 && a->b1 && a->w2 && a->b2 && a->pooled && a->z1 && a->gate, "mclip_se_fc: null operand");
   const int smem = (a->c + a->cse) * 4;
-  mclip_se_fc_kernel<<<a->n, 256, smem, (cudaStream_t)stream>>>(a->pool_partials, a->chunks, a->c, a->cse, 1.0f / (float)a->hw, a->w1, a->b1, a->w2, a->b2,
+  // one CTA per sample: the FC stack is latency bound (a few hundred dependent L2 loads per thread at 256 threads for the
+  // 1824/3072-channel blocks), so wide layers get more threads
+  const int se_threads = a->c >= 1024 ? 1024 : a->c >= 512 ? 512 : 256;
+  mclip_se_fc_kernel<<<a->n, se_threads, smem, (cudaStream_t)stream>>>(a->pool_partials, a->chunks, a->c, a->cse, 1.0f / (float)a->hw, a->w1, a->b1, a->w2, a->b2,
                                                                  a->pooled, a->z1, a->gate);
   MCLIP_CHECK_LAUNCH();
   return MCLIP_OK;
@@ -626,8 +627,7 @@ extern "C" int mclip_bn_bwd_finalize(const float* partials, int slots, int c, lo
 //   k1 (per sample): dz2 = dg*g*(1-g) ; dh = W2^T dz2 ; dz1 = dh*swish'(z1) ; ds = W1^T dz1 ; dpool = ds/HW
 //   k2 (per output element): dW2 = sum_n dz2 h^T ; db2 = sum_n dz2 ; dW1 = sum_n dz1 s^T ; db1 = sum_n dz1
 // ------------------------------------------------------------------------------------------------
-#define SE_MAX_JT 8       // squeeze width <= 256
-__global__ void __launch_bounds__(256) mclip_se_bwd1_kernel(const float* __restrict__ dg_part, int chunks, int cstride, int C, int Cse, float inv_hw,
+__global__ void __launch_bounds__(1024) mclip_se_bwd1_kernel(const float* __restrict__ dg_part, int chunks, int cstride, int C, int Cse, float inv_hw,
                                                             const float* __restrict__ W1, const float* __restrict__ W2, const float* __restrict__ z1,
                                                             const float* __restrict__ gate, float* __restrict__ dz2_out, float* __restrict__ dz1_out,
                                                             float* __restrict__ dpool) {
@@ -645,36 +645,17 @@ __global__ void __launch_bounds__(256) mclip_se_bwd1_kernel(const float* __restr
   }
   __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
-  // dh[j] = sum_c W2[c][j] dz2[c]: every warp takes a stripe of channels with its lanes over j (coalesced W2 rows),
-  // then the warps' partials are summed in a fixed order
-  float* red = se_smem + C + Cse;      // [nw][Cse]
-  {
-    float part[SE_MAX_JT];
-#pragma unroll
-    for (int t = 0; t < SE_MAX_JT; ++t) part[t] = 0.f;
-    for (int c = warp; c < C; c += nw) {
-      const float d = dz2[c];
-#pragma unroll
-      for (int t = 0; t < SE_MAX_JT; ++t) {
-        const int j = lane + 32 * t;
-        if (j < Cse) part[t] = fmaf(W2[(size_t)c * Cse + j], d, part[t]);
-      }
-    }
-#pragma unroll
-    for (int t = 0; t < SE_MAX_JT; ++t) {
-      const int j = lane + 32 * t;
-      if (j < Cse) red[warp * Cse + j] = part[t];
-    }
-  }
-  __syncthreads();
-  for (int j = threadIdx.x; j < Cse; j += blockDim.x) {
+  for (int j = warp; j < Cse; j += nw) {
     float v = 0.f;
-    for (int w = 0; w < nw; ++w) v += red[w * Cse + j];
-    const float z = z1[(size_t)n * Cse + j];
-    const float sg = sigmoid_precise(z);
-    v *= sg * (1.f + z * (1.f - sg));
-    dz1[j] = v;
-    dz1_out[(size_t)n * Cse + j] = v;
+    for (int c = lane; c < C; c += 32) v = fmaf(W2[(size_t)c * Cse + j], dz2[c], v);
+    v = warp_sum(v);
+    if (lane == 0) {
+      const float z = z1[(size_t)n * Cse + j];
+      const float s = sigmoid_precise(z);
+      v *= s * (1.f + z * (1.f - s));
+      dz1[j] = v;
+      dz1_out[(size_t)n * Cse + j] = v;
+    }
   }
   __syncthreads();
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
@@ -714,9 +695,9 @@ __global__ void mclip_se_bwd2_kernel(int N, int C, int Cse, const float* __restr
 extern "C" int mclip_se_fc_backward(const mclip_se_args* a, void* stream) {
   MCLIP_REQUIRE(a && a->dgate_partials && a->w1 && a->w2 && a->z1 && a->gate && a->pooled && a->dz2 && a->dz1 && a->dpool && a->dw1 && a->db1 && a->dw2 && a->db2,
                 "mclip_se_fc_backward: null operand");
-  MCLIP_REQUIRE(a->cse <= 32 * SE_MAX_JT, "mclip_se_fc_backward: squeeze width %d > %d", a->cse, 32 * SE_MAX_JT);
-  const int smem = (a->c + a->cse + 8 * a->cse) * 4;
-  mclip_se_bwd1_kernel<<<a->n, 256, smem, (cudaStream_t)stream>>>(a->dgate_partials, a->chunks, a->dgate_chunk_stride > 0 ? a->dgate_chunk_stride : a->c, a->c, a->cse, 1.0f / (float)a->hw, a->w1, a->w2, a->z1, a->gate,
+  const int smem = (a->c + a->cse) * 4;
+  const int se_threads = a->c >= 1024 ? 1024 : a->c >= 512 ? 512 : 256;
+  mclip_se_bwd1_kernel<<<a->n, se_threads, smem, (cudaStream_t)stream>>>(a->dgate_partials, a->chunks, a->dgate_chunk_stride > 0 ? a->dgate_chunk_stride : a->c, a->c, a->cse, 1.0f / (float)a->hw, a->w1, a->w2, a->z1, a->gate,
                                                                    a->dz2, a->dz1, a->dpool);
   MCLIP_CHECK_LAUNCH();
   const int total = 2 * a->c * a->cse + a->c + a->cse;
