@@ -116,9 +116,10 @@ __device__ __forceinline__ void ew_block_reduce4(float* smem, const float2* v, i
 // ------------------------------------------------------------------------------------------------
 // BatchNorm statistics -> affine (a = gamma*invstd, b = beta - mean*a), running-stat update
 // ------------------------------------------------------------------------------------------------
-// 1024 threads = 32 channels x 32 slot lanes: each lane strides over the partial slots (up to N*chunks ~ 2400 of them), fp64 combine in smem
-#define BNF_CH 32
-#define BNF_LANES 32
+// 1024 threads = 8 channels x 128 slot lanes (a warp reads 4 slot rows x 32 B): narrow layers still get C/8 CTAs and a lane
+// strides over at most ~20 of the up to N*chunks ~ 2400 partial slots; fp64 combine in smem, fixed order
+#define BNF_CH 8
+#define BNF_LANES 128
 __device__ __forceinline__ void bn_reduce_slots(const float* __restrict__ partials, int slots, int C, int c, int lane, double& s, double& q,
                                                 double (*sm)[BNF_LANES][BNF_CH]) {
   s = 0.0; q = 0.0;
