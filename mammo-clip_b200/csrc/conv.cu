@@ -501,10 +501,12 @@ __global__ void mclip_dw_wgrad_reduce_kernel(const float* __restrict__ part, flo
 // ------------------------------------------------------------------------------------------------
 template <int K, int S>
 struct DwCfg {
-  static constexpr int TH = 8;                      // forward tile (outputs)
+  // forward tile (outputs).  Stride 2 halves the tile height: an 8x16 tile needs a 17x33 (k3) / 19x35 (k5) input window =
+  // 72 / 85 KB per stage, i.e. ONE or two 4-warp CTAs per SM; 4x16 keeps the window at 38 / 49 KB and 4 CTAs resident.
+  static constexpr int TH = (S == 1) ? 8 : 4;
   static constexpr int TW = 16;
   static constexpr int BTH = (S == 1) ? 8 : 4;      // backward tile height
-  static constexpr int FST = (K == 3) ? 2 : 1;      // TMA stages, forward (k5: one stage keeps 4 CTAs per SM)
+  static constexpr int FST = (K == 3 && S == 1) ? 2 : 1;   // TMA stages, forward (k5 / stride 2: one stage keeps 4 CTAs per SM)
   static constexpr int BST = 1;                     // backward stages two tensors per tile: one stage, occupancy hides the TMA latency
 };
 
@@ -568,9 +570,8 @@ static int dw_launch_bwd(DwDev& p, cudaStream_t stream, int slots_given) {
 }
 
 static int dw_tiles(const mclip_dwconv_args* a, bool bwd) {
-  int TH = 8, TW = 16;
+  const int TH = a->stride == 1 ? 8 : 4, TW = 16;
   if (!bwd) return a->n * ceil_div(a->ho, TH) * ceil_div(a->wo, TW);
-  TH = a->stride == 1 ? 8 : 4;
   const int hy = max(a->ho, ceil_div(a->h, a->stride)), wx = max(a->wo, ceil_div(a->w, a->stride));
   return a->n * ceil_div(hy, TH) * ceil_div(wx, TW);
 }
