@@ -6,7 +6,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libmclip_b200.so")
+LIB_PATH = os.environ.get("MCLIP_LIB") or os.path.join(_HERE, "lib", "libmclip_b200.so")     # MCLIP_LIB: A/B builds of the same ABI
 
 MAX_TENSORS, MAX_PAIRS = 4, 8
 
