@@ -103,3 +103,33 @@ def test_bert_second_backward_accumulates_and_flat_optimizer_gets_direct_writes(
         if "pooler" in k:
             continue
         assert torch.allclose(p.grad, 2 * single[k], rtol=1e-5, atol=1e-6 * single[k].abs().max().item() + 1e-12), k
+
+
+@pytest.mark.parametrize("drop", [False, True])
+def test_mlp_projection_head_orchestration(monkeypatch, drop):
+    """MLP head (projection.py:4-20) forward/backward routing on the emulated kernels vs fp32 autograd of the reference formula."""
+    from mammoclip_b200 import ops
+    from mammoclip_b200.model.modules.projection import MLPProjectionHead, _MLPHeadFn
+    emulated_ops.install(monkeypatch, ops)
+    torch.manual_seed(0)
+    head = MLPProjectionHead(768, 512, 0.1)
+    ref = copy.deepcopy(head)
+    x = torch.randn(6, 768)
+    mask = (torch.rand(6, 512) >= 0.1).to(torch.uint8) if drop else None
+    scale = 1.0 / 0.9 if drop else 1.0
+    xa = x.clone().requires_grad_(True)
+    out = _MLPHeadFn.apply(xa, head.projection.weight, head.projection.bias, head.fc.weight, head.fc.bias, head.layer_norm.weight,
+                           head.layer_norm.bias, mask, scale, head.layer_norm.eps)
+    xb = x.clone().requires_grad_(True)
+    p = ref.projection(xb)
+    y = ref.fc(torch.nn.functional.gelu(p))
+    if drop:
+        y = y * (mask.float() * scale)
+    r = ref.layer_norm(y + p)
+    assert rel_err(out, r) < 2e-2
+    g = torch.randn(6, 512)
+    (out * g).sum().backward()
+    (r * g).sum().backward()
+    assert rel_err(xa.grad, xb.grad) < 3e-2
+    for (k, a), (_, b) in zip(head.named_parameters(), ref.named_parameters()):
+        assert rel_err(a.grad, b.grad) < 3e-2, k

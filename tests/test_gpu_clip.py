@@ -170,3 +170,35 @@ def test_flat_adamw_matches_torch_adamw_and_direct_grads():
                 assert (pa - pb).abs().max().item() < 2e-6 + 1e-5 * pb.abs().max().item(), (step, k)
             else:              # Adam normalises by sqrt(v): noise-level gradients may flip sign, |delta| <= 2*lr per step
                 assert (pa - pb).abs().max().item() < 2.5e-3, (step, k)
+
+
+@pytest.mark.parametrize("training", [False, True])
+def test_mlp_projection_head_on_kernels(training, monkeypatch):
+    """`load_projection_head({"name": "mlp"})` (projection.py:4-20): Linear -> GELU -> Linear -> dropout -> +residual -> LayerNorm
+    forward and backward on the kernels vs fp32 PyTorch with the same keep-mask."""
+    import copy
+    from mammoclip_b200.model.modules import load_projection_head
+    torch.manual_seed(0)
+    head = load_projection_head(768, {"name": "mlp", "proj_dim": 512, "dropout": 0.1}).cuda()
+    ref = copy.deepcopy(head)
+    head.train(training)
+    x = torch.randn(37, 768, device="cuda")
+    keep = (torch.rand(37, 512, device="cuda") >= 0.1)
+    if training:
+        monkeypatch.setattr(torch, "rand", lambda *a, **k: (~keep).float())      # mask = (rand >= p) reproduces `keep`
+    xa = x.clone().requires_grad_(True)
+    out = head(xa)
+    monkeypatch.undo()
+    xb = x.clone().requires_grad_(True)
+    p = ref.projection(xb)
+    y = ref.fc(torch.nn.functional.gelu(p))
+    if training:
+        y = y * (keep.float() / 0.9)
+    r = ref.layer_norm(y + p)
+    assert rel_err(out, r) < 2e-2
+    g = torch.randn(37, 512, device="cuda")
+    (out * g).sum().backward()
+    (r * g).sum().backward()
+    assert rel_err(xa.grad, xb.grad) < 3e-2
+    for (k, a), (_, b) in zip(head.named_parameters(), ref.named_parameters()):
+        assert rel_err(a.grad, b.grad) < 3e-2, k
