@@ -185,7 +185,7 @@ def test_mlp_projection_head_on_kernels(training, monkeypatch):
     x = torch.randn(37, 768, device="cuda")
     keep = (torch.rand(37, 512, device="cuda") >= 0.1)
     if training:
-        monkeypatch.setattr(torch, "rand", lambda *a, **k: (~keep).float())      # mask = (rand >= p) reproduces `keep`
+        monkeypatch.setattr(torch, "rand", lambda *a, **k: keep.float())         # mask = (rand >= p) reproduces `keep`
     xa = x.clone().requires_grad_(True)
     out = head(xa)
     monkeypatch.undo()
