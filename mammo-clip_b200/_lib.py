@@ -78,8 +78,6 @@ def lib():
     L.mclip_loss_workspace_bytes.restype = C.c_longlong
     L.mclip_gemm_wgrad_workspace_bytes.restype = C.c_longlong
     L.mclip_colsum_workspace_bytes.restype = C.c_longlong
-    for name in dir(L):
-        pass
     _lib = L
     return L
 
