@@ -151,3 +151,16 @@ def test_global_env_contract():
     env = GlobalEnv.reset()
     assert env.world_size == 1 and env.world_rank == 0 and env.master and env.summary_writer.global_step == 0
     assert env.summary_writer.train is None
+
+
+def test_bench_reference_arm_prints_the_contract_line():
+    """`bench.py --impl reference` (the CPU arm the driver runs next to ours): one JSON line with the agreed keys; c1 keeps it short."""
+    import json
+    import sys
+    out = subprocess.check_output([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--workload", "c1", "--steps", "1", "--warmup", "0"],
+                                  text=True, timeout=600)
+    line = json.loads(out.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["unit"] == "pairs/s" and line["value"] > 0 and line["higher_is_better"] is True
+    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1 and "sample" in line["cpu_baseline"]
+    assert line["e2e"] == {"value": line["value"], "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert line["gpu_launches"] == 0 and "workload" in line["config"]
