@@ -245,6 +245,27 @@ def golden_loss(world, B, tag, port_no):
     print("wrote", tag)
 
 
+# ----------------------------------------------------------------------------- MLP projection head
+
+def golden_mlp_head(bc, tag="mlp_head_768_512"):
+    """projection.py:4-20 of the reference, eval mode (dropout off), weights from (name, seed): output + every gradient."""
+    from breastclip.model.modules import load_projection_head
+    head = load_projection_head(768, {"name": "mlp", "proj_dim": 512, "dropout": 0.1})
+    port.fill_deterministic(head, 3)
+    head.eval()
+    g = torch.Generator().manual_seed(11)
+    x = torch.randn(9, 768, generator=g).requires_grad_(True)
+    probe = torch.randn(9, 512, generator=g)
+    out = head(x)
+    (out * probe).sum().backward()
+    arrays = {"x": x.detach().numpy(), "probe": probe.numpy(), "out": out.detach().numpy(), "dx": x.grad.numpy()}
+    for k, v in head.named_parameters():       # weight gradients: an 8x8-strided sample keeps the fixture small
+        arrays["grad." + k] = (v.grad[::8, ::8] if v.dim() == 2 else v.grad).numpy().copy()
+    meta = {"versions": _versions(), "seed": 3, "embedding_dim": 768, "proj_dim": 512}
+    np.savez_compressed(os.path.join(GOLD, f"{tag}.npz"), meta=json.dumps(meta), **arrays)
+    print("wrote", tag)
+
+
 def main():
     os.makedirs(GOLD, exist_ok=True)
     torch.set_num_threads(8)
@@ -255,6 +276,7 @@ def main():
     golden_encoder(bc, "efficientnet-b5", 2, 80, 48, "enc_b5_80x48")
     golden_clip(bc, "clip_c1_contrastive", mvs=False)
     golden_clip(bc, "clip_c1_mvs", mvs=True)
+    golden_mlp_head(bc)
 
 
 if __name__ == "__main__":

@@ -150,3 +150,28 @@ def test_bf16_emulation_is_off_by_default_and_small_in_eval():
         m.emulate_bf16 = True
         b = m(x)
     assert not torch.equal(a, b) and rel_err(b, a) < 2e-2
+
+
+def _mlp_head_formula(head, x):
+    """projection.py:13-20 written out (what the kernel path implements)."""
+    p = head.projection(x)
+    return head.layer_norm(head.dropout(head.fc(torch.nn.functional.gelu(p))) + p)
+
+
+def test_mlp_head_formula_matches_the_reference_golden(golden_dir):
+    """The fixture was produced by the reference's own MLPProjectionHead (oracle/make_goldens.py::golden_mlp_head)."""
+    import numpy as np
+    from oracle import port
+    z = np.load(os.path.join(golden_dir, "mlp_head_768_512.npz"))
+    head = torch.nn.Module()
+    head.projection, head.gelu, head.fc = torch.nn.Linear(768, 512), torch.nn.GELU(), torch.nn.Linear(512, 512)
+    head.dropout, head.layer_norm = torch.nn.Dropout(0.1), torch.nn.LayerNorm(512)
+    port.fill_deterministic(head, 3)
+    head.eval()
+    x = torch.from_numpy(z["x"]).requires_grad_(True)
+    out = _mlp_head_formula(head, x)
+    (out * torch.from_numpy(z["probe"])).sum().backward()
+    assert torch.allclose(out, torch.from_numpy(z["out"]), atol=1e-5) and torch.allclose(x.grad, torch.from_numpy(z["dx"]), atol=1e-5)
+    for k, v in head.named_parameters():
+        g = v.grad[::8, ::8] if v.dim() == 2 else v.grad
+        assert torch.allclose(g, torch.from_numpy(z["grad." + k]), atol=1e-4, rtol=1e-4), k

@@ -202,3 +202,20 @@ def test_mlp_projection_head_on_kernels(training, monkeypatch):
     assert rel_err(xa.grad, xb.grad) < 3e-2
     for (k, a), (_, b) in zip(head.named_parameters(), ref.named_parameters()):
         assert rel_err(a.grad, b.grad) < 3e-2, k
+
+
+def test_mlp_projection_head_vs_reference_golden(golden_dir):
+    """Kernel MLP head vs the fixture produced by the reference's own MLPProjectionHead (eval mode; oracle/make_goldens.py)."""
+    from mammoclip_b200.model.modules import load_projection_head
+    from oracle import port
+    z = np.load(os.path.join(golden_dir, "mlp_head_768_512.npz"))
+    head = load_projection_head(768, {"name": "mlp", "proj_dim": 512, "dropout": 0.1})
+    port.fill_deterministic(head, 3)
+    head.cuda().eval()
+    x = torch.from_numpy(z["x"]).cuda().requires_grad_(True)
+    out = head(x)
+    (out * torch.from_numpy(z["probe"]).cuda()).sum().backward()
+    assert rel_err(out, torch.from_numpy(z["out"])) < 2e-2 and rel_err(x.grad, torch.from_numpy(z["dx"])) < 3e-2
+    for k, v in head.named_parameters():
+        g = v.grad[::8, ::8] if v.dim() == 2 else v.grad
+        assert rel_err(g, torch.from_numpy(z["grad." + k])) < 3e-2, k
