@@ -66,9 +66,13 @@ __device__ __forceinline__ float round_bf16(float x) { return __bfloat162float(_
 
 // sigmoid via one MUFU (tanh.approx): sigma(x) = 0.5*tanh(0.5x)+0.5 ; |err| ~ 2^-11, below bf16 storage
 __device__ __forceinline__ float fast_tanh(float x) {
+#ifdef MCLIP_PRECISE_ACT      // A/B builds only (scripts/build_variant.sh precise -DMCLIP_PRECISE_ACT): numerics attribution
+  return tanhf(x);
+#else
   float y;
   asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
+#endif
 }
 __device__ __forceinline__ float fast_sigmoid(float x) { return fmaf(0.5f, fast_tanh(0.5f * x), 0.5f); }
 __device__ __forceinline__ float swish_f(float x) { return x * fast_sigmoid(x); }

@@ -163,6 +163,40 @@ class _WeightCache:
         ops.weight_prep_run(self.table, len(self.entries))
 
 
+def _block_forward(net, i, x, pending, n, h, w, training, rowscale=None):
+    """One MBConvBlock (efficientnet_custom.py:91-132).  `x`: materialised block input [N,H,W,Cin] bf16, or None when
+    `pending` = (pre-BN tensor, BNState) of the stem whose BN+swish the depthwise loader applies.  Returns
+    (block output [N,Ho,Wo,Cout] bf16, saved state for _block_backward)."""
+    blk, wc = net._blocks[i], net._weights()
+    g = blk.geom
+    B = {"x_in": x, "h": h, "w": w}
+    if g.expand:
+        y0, st = ops.gemm_tn(x.view(n * h * w, g.cin), wc.bf16[("e", i)], want_stats=training)
+        y0 = y0.view(n, h, w, g.cexp)
+        bn0 = _bn_fin(st, n * h * w, blk._bn0, training)
+        B["y0"], B["bn0"] = y0, bn0
+        dw_in, dw_bn = y0, bn0
+    elif pending is not None:
+        dw_in, dw_bn = pending
+        B["from_stem"] = True
+    else:
+        dw_in, dw_bn = x, None
+    y1, st = ops.dwconv_forward(dw_in, blk._depthwise_conv.weight, g.k, g.s, g.pads, bn=dw_bn, want_stats=training)
+    ho, wo = y1.shape[1], y1.shape[2]
+    bn1 = _bn_fin(st, n * ho * wo, blk._bn1, training)
+    u, pool = ops.ew_forward(y1.view(n, ho * wo, g.cexp), bn=bn1, act=1, write=True, pool=True)
+    w1, w2 = blk._se_reduce.weight.view(g.cse, g.cexp), blk._se_expand.weight.view(g.cexp, g.cse)
+    pooled, z1, gate = ops.se_fc(pool, ho * wo, w1, blk._se_reduce.bias, w2, blk._se_expand.bias)
+    wg = ops.se_scale_weights(blk._project_conv.weight.view(g.cout, g.cexp), gate)
+    y2, st = ops.gemm_tn(u, wg, want_stats=training)                     # [N, ho*wo, cout], per-sample weights
+    del u, wg
+    bn2 = _bn_fin(st, n * ho * wo, blk._bn2, training)
+    rs = rowscale if g.skip else None
+    x_out, _ = ops.ew_forward(y2, bn=bn2, act=0, rowscale=rs, residual=x.view(n, h * w, g.cin) if g.skip else None)
+    B.update(y1=y1, bn1=bn1, pooled=pooled, z1=z1, gate=gate, y2=y2, bn2=bn2, rowscale=rs, ho=ho, wo=wo)
+    return x_out.view(n, ho, wo, g.cout), B
+
+
 def _forward(net, images, training, drop_rowscales, dropout_mult, want_raw):
     """Returns (features [N,Chead] fp32, saved state for backward, raw head activation or None)."""
     geom = net.geom
@@ -178,39 +212,14 @@ def _forward(net, images, training, drop_rowscales, dropout_mult, want_raw):
     pending = (y, bn)      # a pre-BN tensor whose BN+swish is applied by the consumer
     x = None               # materialised block input [N,H,W,C] bf16
     for i, blk in enumerate(net._blocks):
-        g = blk.geom
-        if g.expand and pending is not None:
+        if blk.geom.expand and pending is not None:
             # (never the case for B0-B7, whose first stage has expand_ratio 1) the expand GEMM needs a materialised input
             x, _ = ops.ew_forward(pending[0].view(n, h * w, -1), bn=pending[1], act=1)
             x, pending = x.view(n, h, w, -1), None
             S["stem_materialised"] = True
-        B = {"x_in": x, "h": h, "w": w}
-        if g.expand:
-            y0, st = ops.gemm_tn(x.view(n * h * w, g.cin), wc.bf16[("e", i)], want_stats=training)
-            y0 = y0.view(n, h, w, g.cexp)
-            bn0 = _bn_fin(st, n * h * w, blk._bn0, training)
-            B["y0"], B["bn0"] = y0, bn0
-            dw_in, dw_bn = y0, bn0
-        elif pending is not None:
-            dw_in, dw_bn = pending
-            B["from_stem"] = True
-        else:
-            dw_in, dw_bn = x, None
-        y1, st = ops.dwconv_forward(dw_in, blk._depthwise_conv.weight, g.k, g.s, g.pads, bn=dw_bn, want_stats=training)
-        ho, wo = y1.shape[1], y1.shape[2]
-        bn1 = _bn_fin(st, n * ho * wo, blk._bn1, training)
-        u, pool = ops.ew_forward(y1.view(n, ho * wo, g.cexp), bn=bn1, act=1, write=True, pool=True)
-        w1, w2 = blk._se_reduce.weight.view(g.cse, g.cexp), blk._se_expand.weight.view(g.cexp, g.cse)
-        pooled, z1, gate = ops.se_fc(pool, ho * wo, w1, blk._se_reduce.bias, w2, blk._se_expand.bias)
-        wg = ops.se_scale_weights(blk._project_conv.weight.view(g.cout, g.cexp), gate)
-        y2, st = ops.gemm_tn(u, wg, want_stats=training)                     # [N, ho*wo, cout], per-sample weights
-        del u, wg
-        bn2 = _bn_fin(st, n * ho * wo, blk._bn2, training)
-        rs = drop_rowscales.get(i) if (g.skip and drop_rowscales) else None
-        x_out, _ = ops.ew_forward(y2, bn=bn2, act=0, rowscale=rs, residual=x.view(n, h * w, g.cin) if g.skip else None)
-        B.update(y1=y1, bn1=bn1, pooled=pooled, z1=z1, gate=gate, y2=y2, bn2=bn2, rowscale=rs, ho=ho, wo=wo)
+        x, B = _block_forward(net, i, x, pending, n, h, w, training, drop_rowscales.get(i) if drop_rowscales else None)
         S["blocks"].append(B)
-        x, h, w, pending = x_out.view(n, ho, wo, g.cout), ho, wo, None
+        h, w, pending = B["ho"], B["wo"], None
     yh, st = ops.gemm_tn(x.view(n * h * w, x.shape[-1]), wc.bf16[("h",)], want_stats=training)
     yh = yh.view(n, h * w, geom.head_out)
     bnh = _bn_fin(st, n * h * w, net._bn1, training)
@@ -229,6 +238,72 @@ def _bn_backward(y3, bn, training, bnp: _BNParams, grads, prefix, act, du=None, 
     c1, c2 = ops.bn_bwd_finalize(part, bn.count, training, dg, db)
     grads[prefix + ".weight"], grads[prefix + ".bias"] = dg, db
     return ops.ew_backward(1, y3, bn, act, du=du, dvec=dvec, gate=gate, dpool=dpool, rowscale=rowscale, c1=c1, c2=c2)
+
+
+def _block_backward(net, i, B, dx, n, training, grads, G, S=None):
+    """Backward of one MBConvBlock.  dx: gradient w.r.t. the block output [N,Ho,Wo,Cout] bf16; returns the gradient w.r.t.
+    the block input (None for the block fed by the stem, whose BN/conv gradients are written here instead; S carries the stem state)."""
+    blk, wc, geom = net._blocks[i], net._weights(), net.geom
+    g, pre = blk.geom, f"_blocks.{i}."
+    h, w, ho, wo = B["h"], B["w"], B["ho"], B["wo"]
+    dxo = dx.view(n, ho * wo, g.cout)
+    dy2 = _bn_backward(B["y2"], B["bn2"], training, blk._bn2, grads, pre + "_bn2", 0, du=dxo, rowscale=B["rowscale"], G=G)
+    da2 = ops.gemm_tn(dy2.view(n * ho * wo, g.cout), wc.bf16_t[("p", i)]).view(n, ho * wo, g.cexp)
+    y1 = B["y1"].view(n, ho * wo, g.cexp)
+    a2, dgp = ops.ew_backward(2, y1, B["bn1"], 1, du=da2, gate=B["gate"])
+    gp = G(blk._project_conv.weight)
+    ops.gemm_wgrad(dy2.view(n * ho * wo, g.cout), a2.view(n * ho * wo, g.cexp), out=gp.view(g.cout, g.cexp))
+    grads[pre + "_project_conv.weight"] = gp
+    del a2, dy2
+    w1, w2 = blk._se_reduce.weight.view(g.cse, g.cexp), blk._se_expand.weight.view(g.cexp, g.cse)
+    dw1, db1, dw2, db2 = (G(t) for t in (blk._se_reduce.weight, blk._se_reduce.bias, blk._se_expand.weight, blk._se_expand.bias))
+    dpool = ops.se_fc_backward(dgp, ho * wo, w1, w2, B["pooled"], B["z1"], B["gate"], dw1, db1, dw2, db2)
+    grads[pre + "_se_reduce.weight"], grads[pre + "_se_reduce.bias"] = dw1, db1
+    grads[pre + "_se_expand.weight"], grads[pre + "_se_expand.bias"] = dw2, db2
+    # BN1 backward sums come out of the SE pass-1 partials (no separate reduction pass over dA2 / Y1)
+    bnp1 = ops.se_bn_combine(dgp, B["gate"], dpool)
+    dg1, db1_ = G(blk._bn1.weight), G(blk._bn1.bias)
+    c1, c2 = ops.bn_bwd_finalize(bnp1, B["bn1"].count, training, dg1, db1_)
+    grads[pre + "_bn1.weight"], grads[pre + "_bn1.bias"] = dg1, db1_
+    dy1 = ops.ew_backward(1, y1, B["bn1"], 1, du=da2, gate=B["gate"], dpool=dpool, c1=c1, c2=c2)
+    del da2
+    dy1 = dy1.view(n, ho, wo, g.cexp)
+    ddw = G(blk._depthwise_conv.weight)
+    grads[pre + "_depthwise_conv.weight"] = ddw
+    if g.expand:
+        y0, bn0 = B["y0"], B["bn0"]
+        dv0, bnp = ops.dwconv_backward(y0, blk._depthwise_conv.weight, g.k, g.s, g.pads, dy1, ddw, bn=bn0)
+        dg0, db0 = G(blk._bn0.weight), G(blk._bn0.bias)
+        c1, c2 = ops.bn_bwd_finalize(bnp, bn0.count, training, dg0, db0)
+        grads[pre + "_bn0.weight"], grads[pre + "_bn0.bias"] = dg0, db0
+        dy0 = ops.ew_backward(1, y0.view(n, h * w, g.cexp), bn0, 0, du=dv0.view(n, h * w, g.cexp), dv_given=True, c1=c1, c2=c2)
+        del dv0
+        dy0 = dy0.view(n * h * w, g.cexp)
+        x_in = B["x_in"].view(n * h * w, g.cin)
+        ge = G(blk._expand_conv.weight)
+        ops.gemm_wgrad(dy0, x_in, out=ge.view(g.cexp, g.cin))
+        grads[pre + "_expand_conv.weight"] = ge
+        dx = ops.gemm_tn(dy0, wc.bf16_t[("e", i)], residual=dx.view(n * h * w, g.cin) if g.skip else None).view(n, h, w, g.cin)
+        del dy0
+    elif B.get("from_stem"):
+        ys, bns = S["stem"]
+        dvs, bnp = ops.dwconv_backward(ys, blk._depthwise_conv.weight, g.k, g.s, g.pads, dy1, ddw, bn=bns)
+        dgs, dbs = G(net._bn0.weight), G(net._bn0.bias)
+        c1, c2 = ops.bn_bwd_finalize(bnp, bns.count, training, dgs, dbs)
+        grads["_bn0.weight"], grads["_bn0.bias"] = dgs, dbs
+        cs = geom.stem_out
+        dys = ops.ew_backward(1, ys.view(n, h * w, cs), bns, 0, du=dvs.view(n, h * w, cs), dv_given=True, c1=c1, c2=c2)
+        dws = G(net._conv_stem.weight)
+        ops.stem_wgrad(S["images"], dys.view(n, h, w, cs), geom.stem_pads, dws, patches=S["patches"])
+        grads["_conv_stem.weight"] = dws
+        dx = None
+    else:
+        dxd, _ = ops.dwconv_backward(B["x_in"], blk._depthwise_conv.weight, g.k, g.s, g.pads, dy1, ddw, bn=None)
+        if g.skip:
+            dxd, _ = ops.ew_forward(dxd.view(n, h * w, g.cin), residual=dx.view(n, h * w, g.cin))
+        dx = dxd.view(n, h, w, g.cin)
+    del dy1
+    return dx
 
 
 def _backward(net, S, dfeat, direct=False):
@@ -255,66 +330,7 @@ def _backward(net, S, dfeat, direct=False):
     dx = ops.gemm_tn(dyh2, wc.bf16_t[("h",)]).view(x_last.shape)
     del dyh, dyh2
     for i in reversed(range(len(net._blocks))):
-        blk, B = net._blocks[i], S["blocks"][i]
-        g, pre = blk.geom, f"_blocks.{i}."
-        h, w, ho, wo = B["h"], B["w"], B["ho"], B["wo"]
-        dxo = dx.view(n, ho * wo, g.cout)
-        dy2 = _bn_backward(B["y2"], B["bn2"], training, blk._bn2, grads, pre + "_bn2", 0, du=dxo, rowscale=B["rowscale"], G=G)
-        da2 = ops.gemm_tn(dy2.view(n * ho * wo, g.cout), wc.bf16_t[("p", i)]).view(n, ho * wo, g.cexp)
-        y1 = B["y1"].view(n, ho * wo, g.cexp)
-        a2, dgp = ops.ew_backward(2, y1, B["bn1"], 1, du=da2, gate=B["gate"])
-        gp = G(blk._project_conv.weight)
-        ops.gemm_wgrad(dy2.view(n * ho * wo, g.cout), a2.view(n * ho * wo, g.cexp), out=gp.view(g.cout, g.cexp))
-        grads[pre + "_project_conv.weight"] = gp
-        del a2, dy2
-        w1, w2 = blk._se_reduce.weight.view(g.cse, g.cexp), blk._se_expand.weight.view(g.cexp, g.cse)
-        dw1, db1, dw2, db2 = (G(t) for t in (blk._se_reduce.weight, blk._se_reduce.bias, blk._se_expand.weight, blk._se_expand.bias))
-        dpool = ops.se_fc_backward(dgp, ho * wo, w1, w2, B["pooled"], B["z1"], B["gate"], dw1, db1, dw2, db2)
-        grads[pre + "_se_reduce.weight"], grads[pre + "_se_reduce.bias"] = dw1, db1
-        grads[pre + "_se_expand.weight"], grads[pre + "_se_expand.bias"] = dw2, db2
-        # BN1 backward sums come out of the SE pass-1 partials (no separate reduction pass over dA2 / Y1)
-        bnp1 = ops.se_bn_combine(dgp, B["gate"], dpool)
-        dg1, db1_ = G(blk._bn1.weight), G(blk._bn1.bias)
-        c1, c2 = ops.bn_bwd_finalize(bnp1, B["bn1"].count, training, dg1, db1_)
-        grads[pre + "_bn1.weight"], grads[pre + "_bn1.bias"] = dg1, db1_
-        dy1 = ops.ew_backward(1, y1, B["bn1"], 1, du=da2, gate=B["gate"], dpool=dpool, c1=c1, c2=c2)
-        del da2
-        dy1 = dy1.view(n, ho, wo, g.cexp)
-        ddw = G(blk._depthwise_conv.weight)
-        grads[pre + "_depthwise_conv.weight"] = ddw
-        if g.expand:
-            y0, bn0 = B["y0"], B["bn0"]
-            dv0, bnp = ops.dwconv_backward(y0, blk._depthwise_conv.weight, g.k, g.s, g.pads, dy1, ddw, bn=bn0)
-            dg0, db0 = G(blk._bn0.weight), G(blk._bn0.bias)
-            c1, c2 = ops.bn_bwd_finalize(bnp, bn0.count, training, dg0, db0)
-            grads[pre + "_bn0.weight"], grads[pre + "_bn0.bias"] = dg0, db0
-            dy0 = ops.ew_backward(1, y0.view(n, h * w, g.cexp), bn0, 0, du=dv0.view(n, h * w, g.cexp), dv_given=True, c1=c1, c2=c2)
-            del dv0
-            dy0 = dy0.view(n * h * w, g.cexp)
-            x_in = B["x_in"].view(n * h * w, g.cin)
-            ge = G(blk._expand_conv.weight)
-            ops.gemm_wgrad(dy0, x_in, out=ge.view(g.cexp, g.cin))
-            grads[pre + "_expand_conv.weight"] = ge
-            dx = ops.gemm_tn(dy0, wc.bf16_t[("e", i)], residual=dx.view(n * h * w, g.cin) if g.skip else None).view(n, h, w, g.cin)
-            del dy0
-        elif B.get("from_stem"):
-            ys, bns = S["stem"]
-            dvs, bnp = ops.dwconv_backward(ys, blk._depthwise_conv.weight, g.k, g.s, g.pads, dy1, ddw, bn=bns)
-            dgs, dbs = G(net._bn0.weight), G(net._bn0.bias)
-            c1, c2 = ops.bn_bwd_finalize(bnp, bns.count, training, dgs, dbs)
-            grads["_bn0.weight"], grads["_bn0.bias"] = dgs, dbs
-            cs = geom.stem_out
-            dys = ops.ew_backward(1, ys.view(n, h * w, cs), bns, 0, du=dvs.view(n, h * w, cs), dv_given=True, c1=c1, c2=c2)
-            dws = G(net._conv_stem.weight)
-            ops.stem_wgrad(S["images"], dys.view(n, h, w, cs), geom.stem_pads, dws, patches=S["patches"])
-            grads["_conv_stem.weight"] = dws
-            dx = None
-        else:
-            dxd, _ = ops.dwconv_backward(B["x_in"], blk._depthwise_conv.weight, g.k, g.s, g.pads, dy1, ddw, bn=None)
-            if g.skip:
-                dxd, _ = ops.ew_forward(dxd.view(n, h * w, g.cin), residual=dx.view(n, h * w, g.cin))
-            dx = dxd.view(n, h, w, g.cin)
-        del dy1
+        dx = _block_backward(net, i, S["blocks"][i], dx, n, training, grads, G, S)
     if S.get("stem_materialised"):
         ys, bns = S["stem"]
         nn_, hs, ws, cs = ys.shape

@@ -19,7 +19,7 @@ def _build(layers, dropout=0.0):
     return ours.cuda(), ref.cuda()
 
 
-@pytest.mark.parametrize("layers,B,L", [(2, 4, 32), (12, 8, 64), (2, 3, 100)])
+@pytest.mark.parametrize("layers,B,L", [(2, 4, 32), (12, 8, 64), (2, 3, 100), (12, 4, 256), (2, 5, 256)])   # 256 = the reference's text_max_length (pre_train_b5_clip.yaml:27)
 def test_bert_forward_backward(layers, B, L):
     from oracle import port
     from transformers import BatchEncoding
@@ -46,7 +46,7 @@ def test_bert_forward_backward(layers, B, L):
 from bert_ref import bert_torch_ref as _bert_torch_ref  # noqa: E402
 
 
-@pytest.mark.parametrize("B,L", [(4, 32), (3, 100)])
+@pytest.mark.parametrize("B,L", [(4, 32), (3, 100), (3, 256)])
 def test_bert_train_mode_forward_backward_with_shared_dropout_masks(monkeypatch, B, L):
     """Train mode (p=0.1): kernel forward + kernel backward vs fp32 autograd of the same function with the SAME keep-masks
     (embedding / attention-probability / sub-layer dropout), every trainable parameter's gradient."""
@@ -121,7 +121,7 @@ def test_gelu_kernels():
     assert rel_err(ops.gelu_backward(dy, x), xr.grad) < 1e-2
 
 
-@pytest.mark.parametrize("B,L,drop", [(2, 64, False), (3, 100, True), (2, 160, True), (1, 9, False)])
+@pytest.mark.parametrize("B,L,drop", [(2, 64, False), (3, 100, True), (2, 160, True), (1, 9, False), (2, 256, True)])
 def test_attention_backward_kernel(B, L, drop):
     """d(Q,K,V) of softmax(QK^T/8 + padding mask) (o keep-mask) V vs fp32 autograd; L > 64 exercises the multi-block path."""
     import math
