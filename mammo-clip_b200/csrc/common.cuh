@@ -41,7 +41,8 @@ void mclip_set_error(const char* fmt, ...);
 
 int mclip_num_sms();   // cached SM count of the current device
 // cuTensorMapEncodeTiled through the runtime's driver entry point (no libcuda link dependency); bf16 tensors, dims[0] innermost,
-// strides in BYTES for dims 1..rank-1, zero fill out of bounds.  swizzle128 != 0 selects CU_TENSOR_MAP_SWIZZLE_128B.
+// strides in BYTES for dims 1..rank-1, zero fill out of bounds.  swizzle128: bit 0 selects CU_TENSOR_MAP_SWIZZLE_128B, bit 1 L2 promotion 128 B
+// instead of 256 B (boxes whose inner extent is one 128-byte line of a wider row).
 int mclip_tmap_encode_bf16(CUtensorMap* m, const void* ptr, int rank, const unsigned long long* dims, const unsigned long long* strides_bytes,
                            const unsigned* box, int swizzle128);
 

@@ -602,6 +602,7 @@ static int dw_blocks_per_sm(bool bwd) {
 
 extern "C" int mclip_dwconv_slots(const mclip_dwconv_args* a, int backward) {
   if (!a || a->c <= 0) return -1;
+  if (mclip_dws_covers(a, backward)) return mclip_dws_slots(a, backward);
   const bool b = backward != 0;
   int per_sm;
   if (a->k == 3 && a->stride == 1) per_sm = dw_blocks_per_sm<3, 1>(b);
@@ -630,6 +631,7 @@ extern "C" int mclip_dwconv_forward(const mclip_dwconv_args* a, void* stream_) {
   int rc = dw_fill(a, p);
   if (rc) return rc;
   MCLIP_REQUIRE(a->out, "mclip_dwconv_forward: null output");
+  if (mclip_dws_covers(a, 0)) return mclip_dws_forward(a, stream_);
   p.out = (bf16*)a->out; p.stats = a->stats;
   const int slots = mclip_dwconv_slots(a, 0);
   if (a->stats) MCLIP_REQUIRE(a->stat_slots == slots, "mclip_dwconv_forward: stat_slots=%d, expected %d", a->stat_slots, slots);

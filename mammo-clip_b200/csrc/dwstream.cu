@@ -1,0 +1,411 @@
+// Depthwise convolutions as ROW-STREAMING stencils (round 2; replaces the halo-tile kernels of conv.cu for the shapes it covers).
+//
+// Same contract as conv.cu (MBConvBlock._depthwise_conv, efficientnet_custom.py:66-73,109; static pads of
+// Conv2dStaticSamePadding, efficient_net_custom_utils.py:248-276; producer BN+swish applied on load, BN statistics of the
+// output, backward = dX (+swish'), dW, input-BN reduction terms), different execution model:
+//
+//   * a CTA owns a vertical strip (16 output columns x 64 channels) of one image and walks DOWN it.  TMA streams blocks of K
+//     input rows into a ring of shared-memory slots (mbarrier full/empty pairs, one elected producer thread), so every input
+//     row is fetched once per strip: no vertical halo re-reads, no per-tile pipeline bubble.
+//   * a warp owns 4 output columns x 64 channels (lane = 2 channels, packed fp32x2 math).  Per input row it loads the 4+K-1
+//     pixels it needs, applies BN+swish IN REGISTERS (fp32, one MUFU per element) and issues K*K*4 FFMA2 into K rolling
+//     accumulator rows (output row oy lives in accumulator slot (oy + const) mod K; the loop is unrolled K times so every
+//     role is static).  No transform pass over shared memory, no bf16 re-rounding of the activated input, no CTA barrier.
+//   * shared memory is addressed through 32-bit shared-window addresses (ld.shared), weights stay in registers.
+// Instruction mix per input row (k5): 8 LDS + 16 unpack + 8+8 FFMA2 (affine, swish) + 16 MUFU + 100 FFMA2.
+#include "common.cuh"
+#include "mclip_internal.h"
+#include <algorithm>
+#include <stdlib.h>
+#include <type_traits>
+
+typedef unsigned long long u64;
+
+#ifdef DWS_TIMING
+__device__ unsigned long long dws_timing[8];
+extern "C" int mclip_dws_timing(unsigned long long* out8, int reset) {
+  if (reset) { unsigned long long z[8] = {0}; cudaMemcpyToSymbol(dws_timing, z, sizeof(z)); return 0; }
+  cudaDeviceSynchronize();
+  cudaMemcpyFromSymbol(out8, dws_timing, 8 * sizeof(unsigned long long));
+  return 0;
+}
+#define DWS_T0() const long long _t0 = clock64()
+#define DWS_T1(i) _tacc[i] += clock64() - _t0
+#else
+#define DWS_T0()
+#define DWS_T1(i)
+#endif
+
+namespace {
+
+struct DwsDev {
+  int N, H, W, C, Ho, Wo, pl, pt;
+  int strips_x, segs, seg_rows, n_chunks, slots, items;      // items = N * strips_x * segs (per channel chunk)
+  const bf16* in; const float* scale; const float* shift; int act;
+  const float* w;
+  bf16* out; float* stats;
+};
+
+__device__ __forceinline__ float2 ffma2r(const float2& a, const float2& b, const float2& c) {
+  float2 d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(reinterpret_cast<u64&>(d)) : "l"(reinterpret_cast<const u64&>(a)), "l"(reinterpret_cast<const u64&>(b)),
+      "l"(reinterpret_cast<const u64&>(c)));
+  return d;
+}
+__device__ __forceinline__ void ffma2(float2& d, const float2& a, const float2& b) { d = ffma2r(a, b, d); }
+__device__ __forceinline__ float2 fmul2(const float2& a, const float2& b) {
+  float2 d;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(reinterpret_cast<u64&>(d)) : "l"(reinterpret_cast<const u64&>(a)), "l"(reinterpret_cast<const u64&>(b)));
+  return d;
+}
+// bf16x2 word -> two fp32: byte permute (ALU pipe) for the low half, mask for the high half; keeps the FMA pipe for FFMA2
+__device__ __forceinline__ float2 bf2_to_f2(uint32_t u) {
+  return make_float2(__uint_as_float(__byte_perm(u, 0u, 0x1044)), __uint_as_float(u & 0xffff0000u));
+}
+// predicated 32-bit global store without a branch (the compiler turns `if (p) *ptr = v` into a BSSY/BRA/BSYNC region per store)
+__device__ __forceinline__ void stg32_if(void* ptr, uint32_t v, bool pred) {
+  asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %2, 0;\n\t@q st.global.b32 [%0], %1;\n\t}" ::"l"(ptr), "r"(v), "r"((uint32_t)pred) : "memory");
+}
+// arrival counter of a ring slot: acq_rel at CTA scope, so the warp that observes the last arrival also observes that every
+// other warp has finished reading the slot (and may hand it back to TMA)
+__device__ __forceinline__ uint32_t atom_add_acqrel_smem(uint32_t* p, uint32_t v) {
+  uint32_t old;
+  asm volatile("atom.acq_rel.cta.shared::cta.add.u32 %0, [%1], %2;" : "=r"(old) : "r"(smem_u32(p)), "r"(v) : "memory");
+  return old;
+}
+__device__ __forceinline__ uint32_t lds32(uint32_t addr) {
+  uint32_t v;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
+  return v;
+}
+
+// -------------------------------------------------------------------------------------------------------------------
+// forward, stride 1
+// -------------------------------------------------------------------------------------------------------------------
+#ifndef DWS_K3_CTAS
+#define DWS_K3_CTAS 4
+#endif
+#ifndef DWS_K5_CTAS
+#define DWS_K5_CTAS 3
+#endif
+#ifndef DWS_K3_NSLOT
+#define DWS_K3_NSLOT 3
+#endif
+#ifndef DWS_K5_NSLOT
+#define DWS_K5_NSLOT 3
+#endif
+#ifndef DWS_K3_REP
+#define DWS_K3_REP 2
+#endif
+#ifndef DWS_K5_REP
+#define DWS_K5_REP 1
+#endif
+
+// Walks the (item, block) sequence of one CTA.  Kept in EVERY thread (all values are warp-uniform) so that the TMA issuer role
+// can rotate over the warps: no warp carries the producer's latency on its critical path every block.
+struct DwsIter {
+  int item, blk, nblk, n, x0, r0, rows;
+};
+
+template <int K, int NSLOT, int REP, bool ACT>
+__global__ void __launch_bounds__(128, (K == 3) ? DWS_K3_CTAS : DWS_K5_CTAS) mclip_dws_fwd_s1_kernel(const __grid_constant__ CUtensorMap tmIn, const DwsDev p) {
+  constexpr int SW = 4, NW = 4, TW = SW * NW, IW = TW + K - 1, PC = SW + K - 1, RB = K * REP;
+  constexpr uint32_t ROW_BYTES = IW * 128, SLOT_BYTES = RB * ROW_BYTES;
+  extern __shared__ __align__(1024) uint8_t dws_smem[];
+  __shared__ float red[NW][4][32];
+  __shared__ __align__(8) uint64_t full[NSLOT];
+  __shared__ uint32_t arrivals[NSLOT];               // monotonic: arrival number a of a slot is the last of its round iff a % NW == NW-1
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int chunk = blockIdx.x % p.n_chunks, slot = blockIdx.x / p.n_chunks;
+  const int c0 = chunk * 64, c = c0 + lane * 2;
+  const bool cvalid = c < p.C;
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tmIn);
+    for (int s = 0; s < NSLOT; ++s) { mbar_init(&full[s], 1); arrivals[s] = 0; }
+    fence_mbar_init();
+  }
+  __syncthreads();
+  const uint32_t ring = smem_u32(dws_smem);
+  const int my_items = p.items > slot ? (p.items - slot + p.slots - 1) / p.slots : 0;
+  const int per_img = p.strips_x * p.segs;
+
+  auto load_item = [&](DwsIter& it) {            // geometry of item `it.item` of this CTA (two divisions per item)
+    const int g = slot + it.item * p.slots;
+    it.n = g / per_img;
+    const int rem = g - it.n * per_img;
+    const int sy = rem / p.strips_x;
+    it.x0 = (rem - sy * p.strips_x) * TW;
+    it.r0 = sy * p.seg_rows;
+    it.rows = min(p.Ho, it.r0 + p.seg_rows) - it.r0;
+    it.nblk = (it.rows + K - 1 + RB - 1) / RB;    // steps = rows + K - 1 (the last output row needs K-1 more input rows)
+    it.blk = 0;
+  };
+  // ---- producer ----
+  // Every warp carries the iterator `pi` of the block that is NSLOT blocks ahead of the one it is consuming (warp-uniform
+  // integer work, once per block).  The warp whose arrival is the LAST on a slot refills that slot at once: nobody ever waits
+  // to issue, and the issue latency is on no warp's critical path as long as the ring has a block of slack.
+  DwsIter pi;
+  pi.item = 0;
+  auto advance = [&]() { if (++pi.blk == pi.nblk) { if (++pi.item < my_items) load_item(pi); } };
+  auto issue = [&](int s) {                          // one thread: block `pi` -> slot s
+    mbar_expect_tx(&full[s], SLOT_BYTES);
+    tma_load_4d(dws_smem + (size_t)s * SLOT_BYTES, &tmIn, &full[s], c0, pi.x0 - p.pl, pi.r0 - p.pt + pi.blk * RB, pi.n);
+  };
+  if (my_items > 0) {
+    load_item(pi);
+#pragma unroll 1
+    for (int i = 0; i < NSLOT; ++i) {
+      if (pi.item < my_items) {
+        if (threadIdx.x == 0) issue(i);
+        advance();
+      }
+    }
+  }
+
+  // ---- consumer state ----
+  float2 w[K * K];
+#pragma unroll
+  for (int t = 0; t < K * K; ++t) w[t] = cvalid ? make_float2(p.w[(size_t)c * K * K + t], p.w[(size_t)(c + 1) * K * K + t]) : make_float2(0.f, 0.f);
+  const float f = ACT ? 0.5f : 1.0f;                // swish(t) = h + h*tanh(h), h = t/2
+  float2 a2 = make_float2(f, f), b2 = make_float2(0.f, 0.f);
+  if (p.scale && cvalid) { a2 = make_float2(f * p.scale[c], f * p.scale[c + 1]); b2 = make_float2(f * p.shift[c], f * p.shift[c + 1]); }
+  float2 s_sum = make_float2(0.f, 0.f), s_sq = make_float2(0.f, 0.f);
+  const float2 one = make_float2(1.f, 1.f);
+  const int cw = p.C >> 1;
+  const int rstride = p.Wo * cw;                     // output row stride in 32-bit words
+  const unsigned rstride_b = (unsigned)rstride * 4u, pix_b = (unsigned)p.C * 2u;     // ... and row / pixel strides in bytes
+  DwsIter ci;
+  ci.item = 0;
+  int count = 0;                                     // blocks consumed so far (ring position)
+#ifdef DWS_TIMING
+  long long _tacc[4] = {0, 0, 0, 0};
+  const long long _tk = clock64();
+#endif
+#pragma unroll 1
+  for (; ci.item < my_items; ++ci.item) {
+    load_item(ci);
+    const int wx = ci.x0 + warp * SW;                // first output column of this warp
+    const bool wactive = wx < p.Wo;
+    // validity masks of the warp's PC input columns / SW output columns
+    uint32_t inmask = 0, outmask = 0;
+#pragma unroll
+    for (int ix = 0; ix < PC; ++ix) { const int gx = wx - p.pl + ix; inmask |= (gx >= 0 && gx < p.W) ? (1u << ix) : 0u; }
+#pragma unroll
+    for (int j = 0; j < SW; ++j) outmask |= (wx + j < p.Wo && cvalid) ? (1u << j) : 0u;
+    const bool edge = inmask != ((1u << PC) - 1u);
+    // this lane's word of output pixel (r0, wx); row oj of the item starts rstride words further per row
+    char* const obase = reinterpret_cast<char*>(p.out) + (((size_t)ci.n * p.Ho + ci.r0) * (size_t)rstride + (size_t)wx * cw + (c >> 1)) * 4;
+    const int iy0 = ci.r0 - p.pt;
+    // accumulator convention: at the start of a step the slot whose tap row is ky == 0 holds nothing (it is overwritten by the
+    // first tap, or zeroed when the input row is padding); the other slots hold partial sums
+    float2 acc[K][SW];
+#pragma unroll
+    for (int j = 0; j < K; ++j)
+#pragma unroll
+      for (int o = 0; o < SW; ++o) acc[j][o] = make_float2(0.f, 0.f);
+
+    // one input row (static r within the K-row group): FAST = row inside the image, no column masks, all SW outputs stored
+    auto step = [&](auto fast_c, auto r_c, uint32_t base, int j0) {
+      constexpr bool FAST = decltype(fast_c)::value;
+      constexpr int r = decltype(r_c)::value;
+      constexpr int KK = K;
+      if (FAST || (unsigned)(iy0 + j0 + r) < (unsigned)p.H) {
+        float2 x[PC];
+#pragma unroll
+        for (int ix = 0; ix < PC; ++ix) {
+          float2 h = ffma2r(bf2_to_f2(lds32(base + r * ROW_BYTES + ix * 128)), a2, b2);
+          if (ACT) h = ffma2r(h, make_float2(fast_tanh(h.x), fast_tanh(h.y)), h);
+          x[ix] = h;
+        }
+        if (!FAST && edge) {                       // ZeroPad2d acts on the activated tensor: columns outside the image are 0
+#pragma unroll
+          for (int ix = 0; ix < PC; ++ix)
+            if (!((inmask >> ix) & 1u)) x[ix] = make_float2(0.f, 0.f);
+        }
+#pragma unroll
+        for (int q = 0; q < K; ++q) {              // accumulator slot q holds the output row whose tap row is ky
+          const int ky = KK - 1 - ((q - r + KK) % KK);
+#pragma unroll
+          for (int kx = 0; kx < K; ++kx)
+#pragma unroll
+            for (int o = 0; o < SW; ++o) {
+              if (ky == 0 && kx == 0) acc[q][o] = fmul2(x[o], w[0]);
+              else ffma2(acc[q][o], x[o + kx], w[ky * K + kx]);
+            }
+        }
+      } else {
+        constexpr int qz = (r + KK - 1) % KK;      // the slot whose ky == 0 at this step
+#pragma unroll
+        for (int o = 0; o < SW; ++o) acc[qz][o] = make_float2(0.f, 0.f);
+      }
+      const int oj = j0 + r - (K - 1);             // slot r just received its last tap row
+      if (FAST || (unsigned)oj < (unsigned)ci.rows) {
+        char* op = obase + (size_t)((unsigned)oj * rstride_b);
+#pragma unroll
+        for (int o = 0; o < SW; ++o) {
+          // lanes past C hold zero weights, hence zero accumulators: only their stores need a predicate
+          const bool st = FAST ? cvalid : (((outmask >> o) & 1u) != 0);
+          stg32_if(op + (unsigned)o * pix_b, pack_bf16(acc[r][o].x, acc[r][o].y), st);
+          if (FAST || st) {
+            ffma2(s_sum, acc[r][o], one);          // statistics from the fp32 accumulators (bf16 rounding of the stored value is unbiased)
+            ffma2(s_sq, acc[r][o], acc[r][o]);
+          }
+        }
+      }
+    };
+    const bool warp_fast = !edge && wx + SW <= p.Wo;
+#pragma unroll 1
+    for (int blk = 0; blk < ci.nblk; ++blk, ++count) {
+      const int s = count % NSLOT;
+      { DWS_T0(); mbar_wait(&full[s], (uint32_t)(count / NSLOT) & 1u); DWS_T1(0); }
+#ifdef DWS_TIMING
+      const long long _tc = clock64();
+#endif
+#ifdef DWS_NOCOMPUTE
+      if (false) {
+#else
+      if (wactive) {
+#endif
+#pragma unroll 1
+        for (int rep = 0; rep < REP; ++rep) {
+          const uint32_t base = ring + (uint32_t)s * SLOT_BYTES + (uint32_t)(rep * K) * ROW_BYTES + (uint32_t)(warp * SW) * 128u + (uint32_t)lane * 4u;
+          const int j0 = blk * RB + rep * K;         // local step of row r = 0: input row iy0 + j0, completes output row j0 - (K-1)
+          // all K input rows inside the image and all K completing output rows inside the segment?
+          const bool fast = warp_fast && iy0 + j0 >= 0 && iy0 + j0 + K <= p.H && j0 >= K - 1 && j0 + 1 <= ci.rows;
+          if (fast) {
+            step(std::true_type{}, std::integral_constant<int, 0>{}, base, j0);
+            step(std::true_type{}, std::integral_constant<int, 1>{}, base, j0);
+            step(std::true_type{}, std::integral_constant<int, 2>{}, base, j0);
+            if constexpr (K == 5) {
+              step(std::true_type{}, std::integral_constant<int, 3>{}, base, j0);
+              step(std::true_type{}, std::integral_constant<int, 4>{}, base, j0);
+            }
+          } else {
+            step(std::false_type{}, std::integral_constant<int, 0>{}, base, j0);
+            step(std::false_type{}, std::integral_constant<int, 1>{}, base, j0);
+            step(std::false_type{}, std::integral_constant<int, 2>{}, base, j0);
+            if constexpr (K == 5) {
+              step(std::false_type{}, std::integral_constant<int, 3>{}, base, j0);
+              step(std::false_type{}, std::integral_constant<int, 4>{}, base, j0);
+            }
+          }
+        }
+      }
+      __syncwarp();
+#ifdef DWS_TIMING
+      _tacc[1] += clock64() - _tc; _tacc[3] += 1;
+#endif
+      { DWS_T0();
+      if (pi.item < my_items) {                      // block count + NSLOT exists: the last warp to leave slot s fetches it
+        if (lane == 0 && (atom_add_acqrel_smem(&arrivals[s], 1u) % NW) == NW - 1) {
+          fence_proxy_async_smem();                  // generic-proxy reads of the slot before the async-proxy (TMA) overwrite
+          issue(s);
+        }
+        advance();
+      }
+      DWS_T1(2); }
+    }
+  }
+#ifdef DWS_TIMING
+  if (lane == 0) {
+    for (int i = 0; i < 4; ++i) atomicAdd(&dws_timing[i], (unsigned long long)_tacc[i]);
+    atomicAdd(&dws_timing[4], (unsigned long long)(clock64() - _tk));
+    atomicAdd(&dws_timing[5], 1ull);
+  }
+#endif
+  if (p.stats) {
+    red[warp][0][lane] = s_sum.x; red[warp][1][lane] = s_sum.y; red[warp][2][lane] = s_sq.x; red[warp][3][lane] = s_sq.y;
+    __syncthreads();
+    if (warp == 0 && cvalid) {
+      float a = 0.f, b = 0.f, cc = 0.f, d = 0.f;
+#pragma unroll
+      for (int w2 = 0; w2 < NW; ++w2) { a += red[w2][0][lane]; b += red[w2][1][lane]; cc += red[w2][2][lane]; d += red[w2][3][lane]; }
+      float* stp = p.stats + (size_t)slot * 2 * p.C;
+      stp[c] = a; stp[c + 1] = b; stp[p.C + c] = cc; stp[p.C + c + 1] = d;
+    }
+  }
+}
+
+// 4-D tensor map over an NHWC bf16 tensor: dims {C, W, H, N}, box {64 channels, box_w, box_h, 1}, no swizzle.
+int dws_tmap(CUtensorMap* m, const void* ptr, int N, int H, int W, int C, int box_w, int box_h) {
+  const unsigned long long dims[4] = {(unsigned long long)C, (unsigned long long)W, (unsigned long long)H, (unsigned long long)N};
+  const unsigned long long strides[3] = {(unsigned long long)C * 2, (unsigned long long)W * C * 2, (unsigned long long)H * W * C * 2};
+  const unsigned box[4] = {64u, (unsigned)box_w, (unsigned)box_h, 1u};
+#ifndef DWS_L2PROMO
+#define DWS_L2PROMO 2
+#endif
+  return mclip_tmap_encode_bf16(m, ptr, 4, dims, strides, box, DWS_L2PROMO);
+}
+
+template <int K>
+struct FwdCfg {
+  static constexpr int NSLOT = (K == 3) ? DWS_K3_NSLOT : DWS_K5_NSLOT;
+  static constexpr int REP = (K == 3) ? DWS_K3_REP : DWS_K5_REP;
+  static constexpr int IW = 16 + K - 1;
+  static constexpr int SMEM = NSLOT * K * REP * IW * 128;
+};
+
+// work decomposition shared by mclip_dws_slots and the launchers
+void dws_plan(const mclip_dwconv_args* a, int ctas_per_sm, int rows_total, DwsDev& p) {
+  const int TW = 16;
+  p.n_chunks = ceil_div(a->c, 64);
+  p.strips_x = ceil_div(a->wo, TW);
+  int ctas = (mclip_num_sms() * ctas_per_sm) / p.n_chunks;
+  if (ctas < 1) ctas = 1;
+  // split the strip of `rows_total` rows into segments until every CTA gets >= ~6 items (segment overhead: K-1 rows)
+  const long long cols = (long long)a->n * p.strips_x;
+  int segs = 1;
+  while (cols * segs < 6LL * ctas && rows_total / (segs * 2) >= 24) segs *= 2;
+  p.seg_rows = ceil_div(rows_total, segs);
+  p.segs = ceil_div(rows_total, p.seg_rows);
+  p.items = (int)(cols * p.segs);
+  p.slots = std::min(ctas, p.items);
+}
+
+template <int K>
+int dws_launch_fwd_s1(const mclip_dwconv_args* a, DwsDev& p, cudaStream_t stream) {
+  constexpr int NSLOT = FwdCfg<K>::NSLOT;
+  CUtensorMap tm;
+  int rc = dws_tmap(&tm, p.in, p.N, p.H, p.W, p.C, FwdCfg<K>::IW, K * FwdCfg<K>::REP);
+  if (rc) return rc;
+  auto kern = p.act ? mclip_dws_fwd_s1_kernel<K, NSLOT, FwdCfg<K>::REP, true> : mclip_dws_fwd_s1_kernel<K, NSLOT, FwdCfg<K>::REP, false>;
+  static bool attr[2] = {false, false};
+  if (!attr[p.act]) { MCLIP_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, FwdCfg<K>::SMEM)); attr[p.act] = true; }
+  kern<<<p.n_chunks * p.slots, 128, FwdCfg<K>::SMEM, stream>>>(tm, p);
+  MCLIP_CHECK_LAUNCH();
+  return MCLIP_OK;
+}
+
+void dws_fill(const mclip_dwconv_args* a, DwsDev& p) {
+  memset(&p, 0, sizeof(p));
+  p.N = a->n; p.H = a->h; p.W = a->w; p.C = a->c; p.Ho = a->ho; p.Wo = a->wo; p.pl = a->pad_left; p.pt = a->pad_top;
+  p.in = (const bf16*)a->in; p.scale = a->in_scale; p.shift = a->in_shift; p.act = a->in_scale ? a->in_act : 0; p.w = a->weight;
+}
+
+}  // namespace
+
+// Which shapes the streaming kernels cover (the rest stays on conv.cu): stride 1 forward for now.
+bool mclip_dws_covers(const mclip_dwconv_args* a, int backward) {
+  static int enabled = -1;
+  if (enabled < 0) { const char* e = getenv("MCLIP_DW_STREAM"); enabled = e ? atoi(e) : 1; }
+  if (!enabled) return false;
+  if (backward) return false;
+  return a->stride == 1 && (a->k == 3 || a->k == 5);
+}
+
+int mclip_dws_slots(const mclip_dwconv_args* a, int backward) {
+  DwsDev p;
+  dws_fill(a, p);
+  dws_plan(a, a->k == 3 ? DWS_K3_CTAS : DWS_K5_CTAS, a->ho, p);
+  return p.slots;
+}
+
+int mclip_dws_forward(const mclip_dwconv_args* a, void* stream_) {
+  DwsDev p;
+  dws_fill(a, p);
+  dws_plan(a, a->k == 3 ? DWS_K3_CTAS : DWS_K5_CTAS, a->ho, p);
+  p.out = (bf16*)a->out; p.stats = a->stats;
+  if (a->stats) MCLIP_REQUIRE(a->stat_slots == p.slots, "mclip_dwconv_forward: stat_slots=%d, expected %d", a->stat_slots, p.slots);
+  if (a->k == 3) return dws_launch_fwd_s1<3>(a, p, (cudaStream_t)stream_);
+  return dws_launch_fwd_s1<5>(a, p, (cudaStream_t)stream_);
+}

@@ -59,7 +59,8 @@ int mclip_tmap_encode_bf16(CUtensorMap* m, const void* ptr, int rank, const unsi
     if (st[i] % 16) { mclip_set_error("TMA stride %llu is not a multiple of 16 bytes", strides_bytes[i]); return MCLIP_ERR_INVALID; }
   }
   CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(ptr), d, st, b, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                   swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   (swizzle128 & 1) ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
+                   (swizzle128 & 2) ? CU_TENSOR_MAP_L2_PROMOTION_L2_128B : CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) { mclip_set_error("cuTensorMapEncodeTiled failed (%d), rank %d", (int)r, rank); return MCLIP_ERR_CUDA; }
   return MCLIP_OK;

@@ -2,3 +2,9 @@
 #pragma once
 #include "../../include/mclip.h"
 #define MCLIP_ABI_VERSION 3
+
+// row-streaming depthwise kernels (dwstream.cu); conv.cu dispatches to them for the shapes they cover
+bool mclip_dws_covers(const mclip_dwconv_args* a, int backward);
+int mclip_dws_slots(const mclip_dwconv_args* a, int backward);
+int mclip_dws_forward(const mclip_dwconv_args* a, void* stream);
+int mclip_dws_backward(const mclip_dwconv_args* a, void* stream);

@@ -36,7 +36,7 @@ def _dw_ref(x, w, k, s, pads, bn):
     xf = x.float().permute(0, 3, 1, 2)
     if bn is not None:
         v = xf * bn.scale.view(1, -1, 1, 1) + bn.shift.view(1, -1, 1, 1)
-        xf = (v * torch.sigmoid(v)).to(torch.bfloat16).float()       # the kernel stages the activated tile as bf16
+        xf = v * torch.sigmoid(v)                                   # BN + swish in fp32 registers (stride 2 still stages a bf16 tile)
     xf = xf.detach().requires_grad_(True)
     y = F.conv2d(F.pad(xf, pads), w, stride=s, groups=w.shape[0])
     return xf, y
@@ -54,9 +54,12 @@ def test_dwconv_forward_backward(n, h, w, c, k, s, pads, with_bn):
     yr = yref.permute(0, 2, 3, 1)
     assert y.shape == yr.shape
     assert rel_err(y.float(), yr) < 8e-3
+    # BatchNorm partials: sums of the fp32 accumulators (the bf16 rounding of the stored tensor is unbiased), i.e. the fp32
+    # reference's own statistics; against the stored bf16 values they agree to the rounding noise of the sum
     st = stats.double().sum(0)
-    yd = y.double().reshape(-1, c)
-    assert rel_err(st[0], yd.sum(0)) < 1e-4 and rel_err(st[1], (yd * yd).sum(0)) < 1e-4
+    yd, yrd = y.double().reshape(-1, c), yr.detach().double().reshape(-1, c)
+    assert rel_err(st[0], yrd.sum(0)) < 3e-3 and rel_err(st[1], (yrd * yrd).sum(0)) < 3e-3
+    assert rel_err(st[0], yd.sum(0)) < 5e-3 and rel_err(st[1], (yd * yd).sum(0)) < 5e-3
     # backward
     dy = _rand(y.shape, 4)
     dwt = torch.empty_like(wt)
