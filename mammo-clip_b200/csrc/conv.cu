@@ -647,6 +647,7 @@ extern "C" int mclip_dwconv_backward(const mclip_dwconv_args* a, void* stream_) 
   int rc = dw_fill(a, p);
   if (rc) return rc;
   MCLIP_REQUIRE(a->dy && a->dx && a->dweight && a->dw_partials, "mclip_dwconv_backward: null operand");
+  if (mclip_dws_covers(a, 1)) return mclip_dws_backward(a, stream_);
   const int slots = mclip_dwconv_slots(a, 1);
   MCLIP_REQUIRE(a->stat_slots == slots, "mclip_dwconv_backward: stat_slots=%d, expected %d", a->stat_slots, slots);
   p.dy = (const bf16*)a->dy; p.dx = (bf16*)a->dx; p.dw_part = a->dw_partials;

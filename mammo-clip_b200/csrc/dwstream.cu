@@ -44,6 +44,8 @@ struct DwsDev {
   const bf16* in; const float* scale; const float* shift; int act;
   const float* w;
   bf16* out; float* stats;
+  // backward
+  const bf16* dy; bf16* dx; float* dw_part; float* bn_part; const float* mean; const float* invstd;
 };
 
 __device__ __forceinline__ float2 ffma2r(const float2& a, const float2& b, const float2& c) {
@@ -326,6 +328,282 @@ __global__ void __launch_bounds__(128, (K == 3) ? DWS_K3_CTAS : DWS_K5_CTAS) mcl
   }
 }
 
+
+// -------------------------------------------------------------------------------------------------------------------
+// backward, stride 1 (H == Ho, W == Wo): one pass over (Y_in, dY) produces dX (times swish'), dW partials and the input
+// BatchNorm's reduction terms.  A CTA = 4 column strips x 2 ROLES (8 warps): for every strip one warp accumulates the weight
+// gradient (K*K register accumulators for the whole kernel, a rolling window of K dY rows, the activated input row) and one
+// warp computes the data gradient (the forward's rolling-accumulator scheme on dY with the flipped kernel, then swish' and the
+// BN sums on the completed row).  Splitting the roles halves the register state per warp (25 weights OR 25 dW accumulators for
+// k5) and lets both streams share one ring: slot = K*REP rows of Y_in + the K*REP rows of dY shifted by pad_top.
+// -------------------------------------------------------------------------------------------------------------------
+#ifndef DWS_BWD_NSLOT
+#define DWS_BWD_NSLOT 3
+#endif
+template <int K, int NSLOT, int REP, bool BN>
+__global__ void __launch_bounds__(256, 2) mclip_dws_bwd_s1_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constant__ CUtensorMap tmDy, const DwsDev p) {
+  constexpr int SW = 4, NS = 4, NW = 8, TW = SW * NS, IW = TW + K - 1, PC = SW + K - 1, RB = K * REP, KK = K;
+  constexpr uint32_t ROW_BYTES = IW * 128, PART_BYTES = RB * ROW_BYTES, SLOT_BYTES = 2 * PART_BYTES;
+  extern __shared__ __align__(1024) uint8_t dws_smem[];
+  __shared__ float red[NS][4][32];
+  __shared__ __align__(8) uint64_t full[NSLOT];
+  __shared__ uint32_t arrivals[NSLOT];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int strip = warp & 3;
+  const bool wrole = warp < NS;                      // warps 0-3: weight gradient, warps 4-7: data gradient
+  const int chunk = blockIdx.x % p.n_chunks, slot = blockIdx.x / p.n_chunks;
+  const int c0 = chunk * 64, c = c0 + lane * 2;
+  const bool cvalid = c < p.C;
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tmIn); tma_prefetch_desc(&tmDy);
+    for (int s = 0; s < NSLOT; ++s) { mbar_init(&full[s], 1); arrivals[s] = 0; }
+    fence_mbar_init();
+  }
+  __syncthreads();
+  const uint32_t ring = smem_u32(dws_smem);
+  const int my_items = p.items > slot ? (p.items - slot + p.slots - 1) / p.slots : 0;
+  const int per_img = p.strips_x * p.segs;
+
+  auto load_item = [&](DwsIter& it) {
+    const int g = slot + it.item * p.slots;
+    it.n = g / per_img;
+    const int rem = g - it.n * per_img;
+    const int sy = rem / p.strips_x;
+    it.x0 = (rem - sy * p.strips_x) * TW;
+    it.r0 = sy * p.seg_rows;
+    it.rows = min(p.H, it.r0 + p.seg_rows) - it.r0;
+    // steps t = r0-(K-1) .. r1+K-2-pt : the data gradient of row r0 starts K-1 dY rows early, the weight gradient of dY row
+    // r1-1 ends at input row r1-1-pt+K-1
+    it.nblk = (it.rows + 2 * K - 2 - p.pt + RB - 1) / RB;
+    it.blk = 0;
+  };
+  DwsIter pi;
+  pi.item = 0;
+  auto advance = [&]() { if (++pi.blk == pi.nblk) { if (++pi.item < my_items) load_item(pi); } };
+  auto issue = [&](int s) {
+    const int t = pi.r0 - (K - 1) + pi.blk * RB;
+    uint8_t* dst = dws_smem + (size_t)s * SLOT_BYTES;
+    mbar_expect_tx(&full[s], SLOT_BYTES);
+    tma_load_4d(dst, &tmIn, &full[s], c0, pi.x0 - p.pl, t, pi.n);
+    tma_load_4d(dst + PART_BYTES, &tmDy, &full[s], c0, pi.x0 + p.pl - (K - 1), t + p.pt, pi.n);
+  };
+  if (my_items > 0) {
+    load_item(pi);
+#pragma unroll 1
+    for (int i = 0; i < NSLOT; ++i) {
+      if (pi.item < my_items) {
+        if (threadIdx.x == 0) issue(i);
+        advance();
+      }
+    }
+  }
+
+  // ---- per-role register state ----
+  // wgrad role: wv = dW accumulators; dgrad role: wv = the weights (wv[ky*K+kx] = w[ky][kx], the flip is in the tap indexing)
+  float2 wv[K * K];
+#pragma unroll
+  for (int t = 0; t < K * K; ++t)
+    wv[t] = (!wrole && cvalid) ? make_float2(p.w[(size_t)c * K * K + t], p.w[(size_t)(c + 1) * K * K + t]) : make_float2(0.f, 0.f);
+  const float f = BN ? 0.5f : 1.0f;                  // BN <=> the input is a pre-BN tensor followed by swish
+  float2 a2 = make_float2(f, f), b2 = make_float2(0.f, 0.f), mu_is = make_float2(1.f, 1.f), nmis = make_float2(0.f, 0.f);
+  if (BN && cvalid) {
+    a2 = make_float2(f * p.scale[c], f * p.scale[c + 1]); b2 = make_float2(f * p.shift[c], f * p.shift[c + 1]);
+    mu_is = make_float2(p.invstd[c], p.invstd[c + 1]);
+    nmis = make_float2(-p.mean[c] * mu_is.x, -p.mean[c + 1] * mu_is.y);
+  }
+  float2 bs = make_float2(0.f, 0.f), bq = make_float2(0.f, 0.f);
+  const float2 one = make_float2(1.f, 1.f), half2 = make_float2(0.5f, 0.5f), two2 = make_float2(2.f, 2.f), neg1 = make_float2(-1.f, -1.f);
+  const int cw = p.C >> 1;
+  const unsigned rstride_b = (unsigned)(p.W * cw) * 4u, pix_b = (unsigned)p.C * 2u;
+  DwsIter ci;
+  ci.item = 0;
+  int count = 0;
+#pragma unroll 1
+  for (; ci.item < my_items; ++ci.item) {
+    load_item(ci);
+    const int wx = ci.x0 + strip * SW;
+    const bool wactive = wx < p.W;
+    uint32_t inmask = 0, outmask = 0;
+#pragma unroll
+    for (int ix = 0; ix < PC; ++ix) { const int gx = wx - p.pl + ix; inmask |= (gx >= 0 && gx < p.W) ? (1u << ix) : 0u; }
+#pragma unroll
+    for (int j = 0; j < SW; ++j) outmask |= (wx + j < p.W && cvalid) ? (1u << j) : 0u;
+    const bool edge = inmask != ((1u << PC) - 1u);
+    const bool warp_fast = wrole ? !edge : (wx + SW <= p.W);
+    char* const obase = reinterpret_cast<char*>(p.dx) + (((size_t)ci.n * p.H) * (size_t)(p.W * cw) + (size_t)wx * cw + (c >> 1)) * 4;
+    const int t0 = ci.r0 - (K - 1), r1 = ci.r0 + ci.rows;
+    // dgrad role: acc[q] = partial data gradient of the input row completing (K + q - r) % K steps ahead
+    // wgrad role: acc[q] = dY row (4 pixels) of the step congruent to q: the rolling window of the last K dY rows
+    float2 acc[K][SW];
+#pragma unroll
+    for (int j = 0; j < K; ++j)
+#pragma unroll
+      for (int o = 0; o < SW; ++o) acc[j][o] = make_float2(0.f, 0.f);
+
+    auto wstep = [&](auto fast_c, auto r_c, uint32_t ybase, uint32_t gbase, int t) {       // weight-gradient role, input row t
+      constexpr bool FAST = decltype(fast_c)::value;
+      constexpr int r = decltype(r_c)::value;
+      // newest dY row t+pt enters the window (only rows of this segment count: every (dY row, tap) pair is summed once)
+      const int oy = t + p.pt;
+      if (FAST || (oy >= ci.r0 && oy < r1)) {
+#pragma unroll
+        for (int o = 0; o < SW; ++o) acc[r][o] = bf2_to_f2(lds32(gbase + r * ROW_BYTES + (K - 1 + o) * 128 - p.pl * 128));
+      } else {
+#pragma unroll
+        for (int o = 0; o < SW; ++o) acc[r][o] = make_float2(0.f, 0.f);
+      }
+      if (FAST || (unsigned)t < (unsigned)p.H) {
+        float2 x[PC];
+#pragma unroll
+        for (int ix = 0; ix < PC; ++ix) {
+          float2 h = ffma2r(bf2_to_f2(lds32(ybase + r * ROW_BYTES + ix * 128)), a2, b2);
+          if (BN) h = ffma2r(h, make_float2(fast_tanh(h.x), fast_tanh(h.y)), h);
+          x[ix] = h;
+        }
+        if (!FAST && edge) {
+#pragma unroll
+          for (int ix = 0; ix < PC; ++ix)
+            if (!((inmask >> ix) & 1u)) x[ix] = make_float2(0.f, 0.f);
+        }
+#pragma unroll
+        for (int ky = 0; ky < K; ++ky) {             // dY row t+pt-ky sits in window slot (r - ky) mod K
+          constexpr int dummy = 0; (void)dummy;
+          const int q = (r - ky + KK) % KK;
+#pragma unroll
+          for (int kx = 0; kx < K; ++kx)
+#pragma unroll
+            for (int o = 0; o < SW; ++o) ffma2(wv[ky * K + kx], acc[q][o], x[o + kx]);
+        }
+      }
+    };
+    auto dstep = [&](auto fast_c, auto r_c, uint32_t ybase, uint32_t gbase, int t) {       // data-gradient role, dY row t+pt
+      constexpr bool FAST = decltype(fast_c)::value;
+      constexpr int r = decltype(r_c)::value;
+      float2 x[PC];                                    // dY[t+pt][wx + pl - (K-1) + j]; TMA zero-fills rows/columns outside dY
+#pragma unroll
+      for (int j = 0; j < PC; ++j) x[j] = bf2_to_f2(lds32(gbase + r * ROW_BYTES + j * 128));
+#pragma unroll
+      for (int q = 0; q < K; ++q) {
+        const int ky = (q - r + KK) % KK;              // slot q completes ky steps ahead: input row t+ky takes tap row ky
+#pragma unroll
+        for (int kx = 0; kx < K; ++kx)
+#pragma unroll
+          for (int o = 0; o < SW; ++o) {
+            if (ky == K - 1 && kx == 0) acc[q][o] = fmul2(x[o + K - 1], wv[ky * K]);
+            else ffma2(acc[q][o], x[o + K - 1 - kx], wv[ky * K + kx]);
+          }
+      }
+      if (FAST || (t >= ci.r0 && t < r1)) {            // input row t is complete (slot r)
+        char* op = obase + (size_t)((unsigned)t * rstride_b);
+#pragma unroll
+        for (int o = 0; o < SW; ++o) {
+          const bool st = FAST ? cvalid : (((outmask >> o) & 1u) != 0);
+          float2 d = acc[r][o];
+          if (BN) {
+            // dv = dA * swish'(v), v = a*y+b; swish'(v) = s + s(1-s)v with s = sigma(v) = 0.5 + 0.5 tanh(v/2)
+            const float2 yv = bf2_to_f2(lds32(ybase + r * ROW_BYTES + (o * 128) + p.pl * 128));
+            const float2 hv = ffma2r(yv, a2, b2);                                          // v / 2
+            const float2 sg = ffma2r(make_float2(fast_tanh(hv.x), fast_tanh(hv.y)), half2, half2);
+            const float2 om = ffma2r(sg, neg1, one);                                       // 1 - s
+            const float2 qq = ffma2r(fmul2(hv, om), two2, one);                            // 1 + v (1 - s)
+            d = fmul2(d, fmul2(sg, qq));
+            if (!FAST && !st) d = make_float2(0.f, 0.f);
+            ffma2(bs, d, one);                         // BN-backward sums from the fp32 values (the stored bf16 rounding is unbiased)
+            ffma2(bq, d, ffma2r(yv, mu_is, nmis));     // yhat = (y - mean) * invstd
+          }
+          stg32_if(op + (unsigned)o * pix_b, pack_bf16(d.x, d.y), st);
+        }
+      }
+    };
+#pragma unroll 1
+    for (int blk = 0; blk < ci.nblk; ++blk, ++count) {
+      const int s = count % NSLOT;
+      mbar_wait(&full[s], (uint32_t)(count / NSLOT) & 1u);
+      if (wactive) {
+#pragma unroll 1
+        for (int rep = 0; rep < REP; ++rep) {
+          const uint32_t sbase = ring + (uint32_t)s * SLOT_BYTES + (uint32_t)(rep * K) * ROW_BYTES + (uint32_t)lane * 4u;
+          const uint32_t ybase = sbase + (uint32_t)(strip * SW) * 128u, gbase = ybase + PART_BYTES;
+          const int t = t0 + blk * RB + rep * K;       // input row of step r = 0 of this group
+          if (wrole) {
+            const bool fast = warp_fast && t >= 0 && t + K <= p.H && t + p.pt >= ci.r0 && t + p.pt + K <= r1;
+            if (fast) {
+              wstep(std::true_type{}, std::integral_constant<int, 0>{}, ybase, gbase, t);
+              wstep(std::true_type{}, std::integral_constant<int, 1>{}, ybase, gbase, t + 1);
+              wstep(std::true_type{}, std::integral_constant<int, 2>{}, ybase, gbase, t + 2);
+              if constexpr (K == 5) {
+                wstep(std::true_type{}, std::integral_constant<int, 3>{}, ybase, gbase, t + 3);
+                wstep(std::true_type{}, std::integral_constant<int, 4>{}, ybase, gbase, t + 4);
+              }
+            } else {
+              wstep(std::false_type{}, std::integral_constant<int, 0>{}, ybase, gbase, t);
+              wstep(std::false_type{}, std::integral_constant<int, 1>{}, ybase, gbase, t + 1);
+              wstep(std::false_type{}, std::integral_constant<int, 2>{}, ybase, gbase, t + 2);
+              if constexpr (K == 5) {
+                wstep(std::false_type{}, std::integral_constant<int, 3>{}, ybase, gbase, t + 3);
+                wstep(std::false_type{}, std::integral_constant<int, 4>{}, ybase, gbase, t + 4);
+              }
+            }
+          } else {
+            const bool fast = warp_fast && t >= ci.r0 && t + K <= r1;
+            if (fast) {
+              dstep(std::true_type{}, std::integral_constant<int, 0>{}, ybase, gbase, t);
+              dstep(std::true_type{}, std::integral_constant<int, 1>{}, ybase, gbase, t + 1);
+              dstep(std::true_type{}, std::integral_constant<int, 2>{}, ybase, gbase, t + 2);
+              if constexpr (K == 5) {
+                dstep(std::true_type{}, std::integral_constant<int, 3>{}, ybase, gbase, t + 3);
+                dstep(std::true_type{}, std::integral_constant<int, 4>{}, ybase, gbase, t + 4);
+              }
+            } else {
+              dstep(std::false_type{}, std::integral_constant<int, 0>{}, ybase, gbase, t);
+              dstep(std::false_type{}, std::integral_constant<int, 1>{}, ybase, gbase, t + 1);
+              dstep(std::false_type{}, std::integral_constant<int, 2>{}, ybase, gbase, t + 2);
+              if constexpr (K == 5) {
+                dstep(std::false_type{}, std::integral_constant<int, 3>{}, ybase, gbase, t + 3);
+                dstep(std::false_type{}, std::integral_constant<int, 4>{}, ybase, gbase, t + 4);
+              }
+            }
+          }
+        }
+      }
+      __syncwarp();
+      if (pi.item < my_items) {
+        if (lane == 0 && (atom_add_acqrel_smem(&arrivals[s], 1u) % NW) == NW - 1) {
+          fence_proxy_async_smem();
+          issue(s);
+        }
+        advance();
+      }
+    }
+  }
+  // ---- flush: dW partials (wgrad warps) through the ring memory, BN partials (dgrad warps) ----
+  __syncthreads();                                     // every TMA load has been consumed
+  float* wred = reinterpret_cast<float*>(dws_smem);    // [NS][K*K][64]
+  if (wrole) {
+#pragma unroll
+    for (int q = 0; q < K * K; ++q) *reinterpret_cast<float2*>(wred + ((size_t)strip * K * K + q) * 64 + lane * 2) = wv[q];
+  } else {
+    red[strip][0][lane] = bs.x; red[strip][1][lane] = bs.y; red[strip][2][lane] = bq.x; red[strip][3][lane] = bq.y;
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < K * K * 64; i += 256) {
+    const int t = i / 64, ch = i % 64;
+    if (c0 + ch < p.C) {
+      float s2 = 0.f;
+#pragma unroll
+      for (int w2 = 0; w2 < NS; ++w2) s2 += wred[((size_t)w2 * K * K + t) * 64 + ch];
+      p.dw_part[((size_t)slot * K * K + t) * p.C + c0 + ch] = s2;
+    }
+  }
+  if (BN && p.bn_part && warp == 0 && cvalid) {
+    float a = 0.f, b = 0.f, cc = 0.f, d = 0.f;
+#pragma unroll
+    for (int w2 = 0; w2 < NS; ++w2) { a += red[w2][0][lane]; b += red[w2][1][lane]; cc += red[w2][2][lane]; d += red[w2][3][lane]; }
+    float* st = p.bn_part + (size_t)slot * 2 * p.C;
+    st[c] = a; st[c + 1] = b; st[p.C + c] = cc; st[p.C + c + 1] = d;
+  }
+}
+
 // 4-D tensor map over an NHWC bf16 tensor: dims {C, W, H, N}, box {64 channels, box_w, box_h, 1}, no swizzle.
 int dws_tmap(CUtensorMap* m, const void* ptr, int N, int H, int W, int C, int box_w, int box_h) {
   const unsigned long long dims[4] = {(unsigned long long)C, (unsigned long long)W, (unsigned long long)H, (unsigned long long)N};
@@ -376,6 +654,30 @@ int dws_launch_fwd_s1(const mclip_dwconv_args* a, DwsDev& p, cudaStream_t stream
   return MCLIP_OK;
 }
 
+template <int K>
+struct BwdCfg {
+  static constexpr int NSLOT = DWS_BWD_NSLOT;
+  static constexpr int REP = (K == 3) ? 2 : 1;
+  static constexpr int IW = 16 + K - 1;
+  static constexpr int RING = NSLOT * 2 * K * REP * IW * 128;
+  static constexpr int SMEM = RING > 4 * K * K * 64 * 4 ? RING : 4 * K * K * 64 * 4;
+};
+
+template <int K>
+int dws_launch_bwd_s1(const mclip_dwconv_args* a, DwsDev& p, cudaStream_t stream) {
+  CUtensorMap tmIn, tmDy;
+  int rc = dws_tmap(&tmIn, p.in, p.N, p.H, p.W, p.C, BwdCfg<K>::IW, K * BwdCfg<K>::REP);
+  if (rc) return rc;
+  if ((rc = dws_tmap(&tmDy, p.dy, p.N, p.Ho, p.Wo, p.C, BwdCfg<K>::IW, K * BwdCfg<K>::REP))) return rc;
+  const bool bn = p.scale != nullptr;
+  auto kern = bn ? mclip_dws_bwd_s1_kernel<K, BwdCfg<K>::NSLOT, BwdCfg<K>::REP, true> : mclip_dws_bwd_s1_kernel<K, BwdCfg<K>::NSLOT, BwdCfg<K>::REP, false>;
+  static bool attr[2] = {false, false};
+  if (!attr[bn]) { MCLIP_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, BwdCfg<K>::SMEM)); attr[bn] = true; }
+  kern<<<p.n_chunks * p.slots, 256, BwdCfg<K>::SMEM, stream>>>(tmIn, tmDy, p);
+  MCLIP_CHECK_LAUNCH();
+  return MCLIP_OK;
+}
+
 void dws_fill(const mclip_dwconv_args* a, DwsDev& p) {
   memset(&p, 0, sizeof(p));
   p.N = a->n; p.H = a->h; p.W = a->w; p.C = a->c; p.Ho = a->ho; p.Wo = a->wo; p.pl = a->pad_left; p.pt = a->pad_top;
@@ -387,17 +689,47 @@ void dws_fill(const mclip_dwconv_args* a, DwsDev& p) {
 // Which shapes the streaming kernels cover (the rest stays on conv.cu): stride 1 forward for now.
 bool mclip_dws_covers(const mclip_dwconv_args* a, int backward) {
   static int enabled = -1;
-  if (enabled < 0) { const char* e = getenv("MCLIP_DW_STREAM"); enabled = e ? atoi(e) : 1; }
+  if (enabled < 0) { const char* e = getenv("MCLIP_DW_STREAM"); enabled = e ? atoi(e) : 3; }      // bit 0: forward, bit 1: backward
   if (!enabled) return false;
-  if (backward) return false;
-  return a->stride == 1 && (a->k == 3 || a->k == 5);
+  if (a->stride != 1 || (a->k != 3 && a->k != 5)) return false;
+  if (backward) return (enabled & 2) != 0 && a->ho == a->h && a->wo == a->w && (a->in_scale == nullptr || a->in_act == 1);
+  return true;
 }
 
 int mclip_dws_slots(const mclip_dwconv_args* a, int backward) {
   DwsDev p;
   dws_fill(a, p);
-  dws_plan(a, a->k == 3 ? DWS_K3_CTAS : DWS_K5_CTAS, a->ho, p);
+  if (backward) dws_plan(a, 2, a->h, p);
+  else dws_plan(a, a->k == 3 ? DWS_K3_CTAS : DWS_K5_CTAS, a->ho, p);
   return p.slots;
+}
+
+// dW[c, t] = sum_slots part[slot][t][c]      (fixed order)
+__global__ void mclip_dws_wgrad_reduce_kernel(const float* __restrict__ part, float* __restrict__ dw, int slots, int KK, int C, int accumulate) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= KK * C) return;
+  const int t = i / C, c = i % C;
+  float s = 0.f;
+  for (int k = 0; k < slots; ++k) s += part[((size_t)k * KK + t) * C + c];
+  float* o = dw + (size_t)c * KK + t;
+  *o = accumulate ? *o + s : s;
+}
+
+int mclip_dws_backward(const mclip_dwconv_args* a, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  DwsDev p;
+  dws_fill(a, p);
+  dws_plan(a, 2, a->h, p);
+  MCLIP_REQUIRE(a->stat_slots == p.slots, "mclip_dwconv_backward: stat_slots=%d, expected %d", a->stat_slots, p.slots);
+  p.dy = (const bf16*)a->dy; p.dx = (bf16*)a->dx; p.dw_part = a->dw_partials;
+  p.bn_part = a->in_scale ? a->bn_partials : nullptr; p.mean = a->in_mean; p.invstd = a->in_invstd;
+  if (p.bn_part) MCLIP_REQUIRE(p.mean && p.invstd, "mclip_dwconv_backward: input BN statistics missing");
+  int rc = a->k == 3 ? dws_launch_bwd_s1<3>(a, p, stream) : dws_launch_bwd_s1<5>(a, p, stream);
+  if (rc) return rc;
+  const int KK = a->k * a->k;
+  mclip_dws_wgrad_reduce_kernel<<<ceil_div(KK * a->c, 256), 256, 0, stream>>>(a->dw_partials, a->dweight, p.slots, KK, a->c, a->accumulate);
+  MCLIP_CHECK_LAUNCH();
+  return MCLIP_OK;
 }
 
 int mclip_dws_forward(const mclip_dwconv_args* a, void* stream_) {

@@ -74,11 +74,13 @@ def test_dwconv_forward_backward(n, h, w, c, k, s, pads, with_bn):
         sg = torch.sigmoid(v)
         dv = dA * (sg * (1 + v * (1 - sg)))
         assert rel_err(dx.float(), dv) < 1e-2, "dv"
-        yh = (x.float() - bn.mean) * bn.invstd
+        # BN-backward partials: sums of the fp32 gradient (stride 1) / of the stored bf16 values (stride 2); both within the
+        # rounding noise of the sum of each other and of the fp32 reference
+        yh = ((x.float() - bn.mean) * bn.invstd).double().reshape(-1, c)
         p = bnp.double().sum(0)
-        dvq = dx.double().reshape(-1, c)
-        assert rel_err(p[0], dvq.sum(0)) < 1e-3
-        assert rel_err(p[1], (dvq * yh.double().reshape(-1, c)).sum(0)) < 1e-3
+        dvq, dvr = dx.double().reshape(-1, c), dv.double().reshape(-1, c)
+        assert rel_err(p[0], dvr.sum(0)) < 3e-3 and rel_err(p[1], (dvr * yh).sum(0)) < 3e-3
+        assert rel_err(p[0], dvq.sum(0)) < 5e-3 and rel_err(p[1], (dvq * yh).sum(0)) < 5e-3
 
 
 @pytest.mark.parametrize("n,h,w,c,pads,nhwc", [(2, 64, 48, 32, (0, 1, 0, 1), True), (3, 31, 45, 48, (0, 1, 0, 1), False), (1, 96, 64, 40, (1, 1, 1, 1), True)])
