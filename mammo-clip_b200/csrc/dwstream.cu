@@ -109,9 +109,24 @@ struct DwsIter {
   int item, blk, nblk, n, x0, r0, rows;
 };
 
-template <int K, int NSLOT, int REP, bool ACT>
-__global__ void __launch_bounds__(128, (K == 3) ? DWS_K3_CTAS : DWS_K5_CTAS) mclip_dws_fwd_s1_kernel(const __grid_constant__ CUtensorMap tmIn, const DwsDev p) {
-  constexpr int SW = 4, NW = 4, TW = SW * NW, IW = TW + K - 1, PC = SW + K - 1, RB = K * REP;
+// compile-time configuration of the forward kernel for (kernel size, stride)
+template <int K, int S>
+struct FwdCfg {
+  static constexpr int SW = 4, NW = 4, TW = SW * NW;
+  static constexpr int NA = (K + S - 1) / S;         // live accumulator rows: output row oy lives in slot oy % NA
+  static constexpr int G = S * NA;                   // input rows per fully unrolled group (all slot roles static)
+  static constexpr int REP = (S == 1 && K == 3) ? DWS_K3_REP : (S == 1 ? DWS_K5_REP : 1);
+  static constexpr int RB = G * REP;                 // input rows per ring slot
+  static constexpr int IW = (TW - 1) * S + K, PC = (SW - 1) * S + K;
+  static constexpr int NSLOT = (S == 1) ? (K == 3 ? DWS_K3_NSLOT : DWS_K5_NSLOT) : (K == 3 ? 3 : 2);
+  static constexpr int CTAS = (S == 1) ? (K == 3 ? DWS_K3_CTAS : DWS_K5_CTAS) : (K == 3 ? 4 : 3);
+  static constexpr int SMEM = NSLOT * RB * IW * 128;
+};
+
+template <int K, int S, bool ACT>
+__global__ void __launch_bounds__(128, FwdCfg<K, S>::CTAS) mclip_dws_fwd_kernel(const __grid_constant__ CUtensorMap tmIn, const DwsDev p) {
+  using Cfg = FwdCfg<K, S>;
+  constexpr int SW = Cfg::SW, NW = Cfg::NW, TW = Cfg::TW, IW = Cfg::IW, PC = Cfg::PC, RB = Cfg::RB, NA = Cfg::NA, G = Cfg::G, REP = Cfg::REP, NSLOT = Cfg::NSLOT;
   constexpr uint32_t ROW_BYTES = IW * 128, SLOT_BYTES = RB * ROW_BYTES;
   extern __shared__ __align__(1024) uint8_t dws_smem[];
   __shared__ float red[NW][4][32];
@@ -139,7 +154,7 @@ __global__ void __launch_bounds__(128, (K == 3) ? DWS_K3_CTAS : DWS_K5_CTAS) mcl
     it.x0 = (rem - sy * p.strips_x) * TW;
     it.r0 = sy * p.seg_rows;
     it.rows = min(p.Ho, it.r0 + p.seg_rows) - it.r0;
-    it.nblk = (it.rows + K - 1 + RB - 1) / RB;    // steps = rows + K - 1 (the last output row needs K-1 more input rows)
+    it.nblk = (S * (it.rows - 1) + K + RB - 1) / RB;      // local steps j = 0 .. S*(rows-1)+K-1 : input row S*r0 - pt + j
     it.blk = 0;
   };
   // ---- producer ----
@@ -151,7 +166,7 @@ __global__ void __launch_bounds__(128, (K == 3) ? DWS_K3_CTAS : DWS_K5_CTAS) mcl
   auto advance = [&]() { if (++pi.blk == pi.nblk) { if (++pi.item < my_items) load_item(pi); } };
   auto issue = [&](int s) {                          // one thread: block `pi` -> slot s
     mbar_expect_tx(&full[s], SLOT_BYTES);
-    tma_load_4d(dws_smem + (size_t)s * SLOT_BYTES, &tmIn, &full[s], c0, pi.x0 - p.pl, pi.r0 - p.pt + pi.blk * RB, pi.n);
+    tma_load_4d(dws_smem + (size_t)s * SLOT_BYTES, &tmIn, &full[s], c0, S * pi.x0 - p.pl, S * pi.r0 - p.pt + pi.blk * RB, pi.n);
   };
   if (my_items > 0) {
     load_item(pi);
@@ -191,31 +206,31 @@ __global__ void __launch_bounds__(128, (K == 3) ? DWS_K3_CTAS : DWS_K5_CTAS) mcl
     // validity masks of the warp's PC input columns / SW output columns
     uint32_t inmask = 0, outmask = 0;
 #pragma unroll
-    for (int ix = 0; ix < PC; ++ix) { const int gx = wx - p.pl + ix; inmask |= (gx >= 0 && gx < p.W) ? (1u << ix) : 0u; }
+    for (int ix = 0; ix < PC; ++ix) { const int gx = S * wx - p.pl + ix; inmask |= (gx >= 0 && gx < p.W) ? (1u << ix) : 0u; }
 #pragma unroll
     for (int j = 0; j < SW; ++j) outmask |= (wx + j < p.Wo && cvalid) ? (1u << j) : 0u;
     const bool edge = inmask != ((1u << PC) - 1u);
     // this lane's word of output pixel (r0, wx); row oj of the item starts rstride words further per row
     char* const obase = reinterpret_cast<char*>(p.out) + (((size_t)ci.n * p.Ho + ci.r0) * (size_t)rstride + (size_t)wx * cw + (c >> 1)) * 4;
-    const int iy0 = ci.r0 - p.pt;
-    // accumulator convention: at the start of a step the slot whose tap row is ky == 0 holds nothing (it is overwritten by the
-    // first tap, or zeroed when the input row is padding); the other slots hold partial sums
-    float2 acc[K][SW];
+    const int iy0 = S * ci.r0 - p.pt;                // input row of local step 0
+    // Local step j = input row iy0 + j feeds, with tap row ky, the output row (j - ky) / S of the item (when S divides j - ky);
+    // that output row lives in accumulator slot ((j - ky) / S) % NA, is initialised by its ky == 0 tap and complete after its
+    // ky == K-1 tap.  Groups of G = S*NA steps start at multiples of G, so every role below is a compile-time constant.
+    float2 acc[NA][SW];
 #pragma unroll
-    for (int j = 0; j < K; ++j)
+    for (int j = 0; j < NA; ++j)
 #pragma unroll
       for (int o = 0; o < SW; ++o) acc[j][o] = make_float2(0.f, 0.f);
 
-    // one input row (static r within the K-row group): FAST = row inside the image, no column masks, all SW outputs stored
-    auto step = [&](auto fast_c, auto r_c, uint32_t base, int j0) {
+    // one input row (static position s within the group): FAST = row inside the image, no column masks, all SW outputs stored
+    auto step = [&](auto fast_c, auto s_c, uint32_t base, int j0) {
       constexpr bool FAST = decltype(fast_c)::value;
-      constexpr int r = decltype(r_c)::value;
-      constexpr int KK = K;
-      if (FAST || (unsigned)(iy0 + j0 + r) < (unsigned)p.H) {
+      constexpr int s = decltype(s_c)::value;
+      if (FAST || (unsigned)(iy0 + j0 + s) < (unsigned)p.H) {
         float2 x[PC];
 #pragma unroll
         for (int ix = 0; ix < PC; ++ix) {
-          float2 h = ffma2r(bf2_to_f2(lds32(base + r * ROW_BYTES + ix * 128)), a2, b2);
+          float2 h = ffma2r(bf2_to_f2(lds32(base + s * ROW_BYTES + ix * 128)), a2, b2);
           if (ACT) h = ffma2r(h, make_float2(fast_tanh(h.x), fast_tanh(h.y)), h);
           x[ix] = h;
         }
@@ -225,32 +240,37 @@ __global__ void __launch_bounds__(128, (K == 3) ? DWS_K3_CTAS : DWS_K5_CTAS) mcl
             if (!((inmask >> ix) & 1u)) x[ix] = make_float2(0.f, 0.f);
         }
 #pragma unroll
-        for (int q = 0; q < K; ++q) {              // accumulator slot q holds the output row whose tap row is ky
-          const int ky = KK - 1 - ((q - r + KK) % KK);
+        for (int ky = 0; ky < K; ++ky) {
+          if ((s - ky + K * S) % S != 0) continue;             // this input row is not on output row (j-ky)/S's tap row ky
+          constexpr int dummy = 0; (void)dummy;
+          const int q = (((s - ky + K * S) / S - K) % NA + NA) % NA;       // floor((s-ky)/S) mod NA
 #pragma unroll
           for (int kx = 0; kx < K; ++kx)
 #pragma unroll
             for (int o = 0; o < SW; ++o) {
-              if (ky == 0 && kx == 0) acc[q][o] = fmul2(x[o], w[0]);
-              else ffma2(acc[q][o], x[o + kx], w[ky * K + kx]);
+              if (ky == 0 && kx == 0) acc[q][o] = fmul2(x[S * o], w[0]);
+              else ffma2(acc[q][o], x[S * o + kx], w[ky * K + kx]);
             }
         }
-      } else {
-        constexpr int qz = (r + KK - 1) % KK;      // the slot whose ky == 0 at this step
+      } else if (s % S == 0) {                     // padding row: the slot that this step would have initialised starts at zero
+        constexpr int qz = (s / S) % NA;
 #pragma unroll
         for (int o = 0; o < SW; ++o) acc[qz][o] = make_float2(0.f, 0.f);
       }
-      const int oj = j0 + r - (K - 1);             // slot r just received its last tap row
-      if (FAST || (unsigned)oj < (unsigned)ci.rows) {
-        char* op = obase + (size_t)((unsigned)oj * rstride_b);
+      if ((s - (K - 1) + K * S) % S == 0) {        // an output row received its last tap row
+        constexpr int qc = (((s - (K - 1) + K * S) / S - K) % NA + NA) % NA;
+        const int oj = (j0 + s - (K - 1)) / S;     // exact: S divides j0 (multiple of G) and s-(K-1)
+        if (FAST || (j0 + s >= K - 1 && oj < ci.rows)) {
+          char* op = obase + (size_t)((unsigned)oj * rstride_b);
 #pragma unroll
-        for (int o = 0; o < SW; ++o) {
-          // lanes past C hold zero weights, hence zero accumulators: only their stores need a predicate
-          const bool st = FAST ? cvalid : (((outmask >> o) & 1u) != 0);
-          stg32_if(op + (unsigned)o * pix_b, pack_bf16(acc[r][o].x, acc[r][o].y), st);
-          if (FAST || st) {
-            ffma2(s_sum, acc[r][o], one);          // statistics from the fp32 accumulators (bf16 rounding of the stored value is unbiased)
-            ffma2(s_sq, acc[r][o], acc[r][o]);
+          for (int o = 0; o < SW; ++o) {
+            // lanes past C hold zero weights, hence zero accumulators: only their stores need a predicate
+            const bool st = FAST ? cvalid : (((outmask >> o) & 1u) != 0);
+            stg32_if(op + (unsigned)o * pix_b, pack_bf16(acc[qc][o].x, acc[qc][o].y), st);
+            if (FAST || st) {
+              ffma2(s_sum, acc[qc][o], one);       // statistics from the fp32 accumulators (bf16 rounding of the stored value is unbiased)
+              ffma2(s_sq, acc[qc][o], acc[qc][o]);
+            }
           }
         }
       }
@@ -258,8 +278,8 @@ __global__ void __launch_bounds__(128, (K == 3) ? DWS_K3_CTAS : DWS_K5_CTAS) mcl
     const bool warp_fast = !edge && wx + SW <= p.Wo;
 #pragma unroll 1
     for (int blk = 0; blk < ci.nblk; ++blk, ++count) {
-      const int s = count % NSLOT;
-      { DWS_T0(); mbar_wait(&full[s], (uint32_t)(count / NSLOT) & 1u); DWS_T1(0); }
+      const int sl = count % NSLOT;
+      { DWS_T0(); mbar_wait(&full[sl], (uint32_t)(count / NSLOT) & 1u); DWS_T1(0); }
 #ifdef DWS_TIMING
       const long long _tc = clock64();
 #endif
@@ -270,26 +290,25 @@ __global__ void __launch_bounds__(128, (K == 3) ? DWS_K3_CTAS : DWS_K5_CTAS) mcl
 #endif
 #pragma unroll 1
         for (int rep = 0; rep < REP; ++rep) {
-          const uint32_t base = ring + (uint32_t)s * SLOT_BYTES + (uint32_t)(rep * K) * ROW_BYTES + (uint32_t)(warp * SW) * 128u + (uint32_t)lane * 4u;
-          const int j0 = blk * RB + rep * K;         // local step of row r = 0: input row iy0 + j0, completes output row j0 - (K-1)
-          // all K input rows inside the image and all K completing output rows inside the segment?
-          const bool fast = warp_fast && iy0 + j0 >= 0 && iy0 + j0 + K <= p.H && j0 >= K - 1 && j0 + 1 <= ci.rows;
+          const uint32_t base = ring + (uint32_t)sl * SLOT_BYTES + (uint32_t)(rep * G) * ROW_BYTES + (uint32_t)(warp * SW * S) * 128u + (uint32_t)lane * 4u;
+          const int j0 = blk * RB + rep * G;         // local step of position s = 0
+          // all G input rows inside the image and every output row completing in this group inside the segment?
+          // (first completion: step >= K-1; last completing output: (j0 + G - 1 - (K-1)) / S rounded down to a completion step)
+          const bool fast = warp_fast && iy0 + j0 >= 0 && iy0 + j0 + G <= p.H && j0 >= K - 1 && (j0 + G - 1 - (K - 1)) / S < ci.rows;
           if (fast) {
             step(std::true_type{}, std::integral_constant<int, 0>{}, base, j0);
             step(std::true_type{}, std::integral_constant<int, 1>{}, base, j0);
             step(std::true_type{}, std::integral_constant<int, 2>{}, base, j0);
-            if constexpr (K == 5) {
-              step(std::true_type{}, std::integral_constant<int, 3>{}, base, j0);
-              step(std::true_type{}, std::integral_constant<int, 4>{}, base, j0);
-            }
+            if constexpr (G > 3) step(std::true_type{}, std::integral_constant<int, 3>{}, base, j0);
+            if constexpr (G > 4) step(std::true_type{}, std::integral_constant<int, 4>{}, base, j0);
+            if constexpr (G > 5) step(std::true_type{}, std::integral_constant<int, 5>{}, base, j0);
           } else {
             step(std::false_type{}, std::integral_constant<int, 0>{}, base, j0);
             step(std::false_type{}, std::integral_constant<int, 1>{}, base, j0);
             step(std::false_type{}, std::integral_constant<int, 2>{}, base, j0);
-            if constexpr (K == 5) {
-              step(std::false_type{}, std::integral_constant<int, 3>{}, base, j0);
-              step(std::false_type{}, std::integral_constant<int, 4>{}, base, j0);
-            }
+            if constexpr (G > 3) step(std::false_type{}, std::integral_constant<int, 3>{}, base, j0);
+            if constexpr (G > 4) step(std::false_type{}, std::integral_constant<int, 4>{}, base, j0);
+            if constexpr (G > 5) step(std::false_type{}, std::integral_constant<int, 5>{}, base, j0);
           }
         }
       }
@@ -298,10 +317,10 @@ __global__ void __launch_bounds__(128, (K == 3) ? DWS_K3_CTAS : DWS_K5_CTAS) mcl
       _tacc[1] += clock64() - _tc; _tacc[3] += 1;
 #endif
       { DWS_T0();
-      if (pi.item < my_items) {                      // block count + NSLOT exists: the last warp to leave slot s fetches it
-        if (lane == 0 && (atom_add_acqrel_smem(&arrivals[s], 1u) % NW) == NW - 1) {
+      if (pi.item < my_items) {                      // block count + NSLOT exists: the last warp to leave slot sl fetches it
+        if (lane == 0 && (atom_add_acqrel_smem(&arrivals[sl], 1u) % NW) == NW - 1) {
           fence_proxy_async_smem();                  // generic-proxy reads of the slot before the async-proxy (TMA) overwrite
-          issue(s);
+          issue(sl);
         }
         advance();
       }
@@ -327,7 +346,6 @@ __global__ void __launch_bounds__(128, (K == 3) ? DWS_K3_CTAS : DWS_K5_CTAS) mcl
     }
   }
 }
-
 
 // -------------------------------------------------------------------------------------------------------------------
 // backward, stride 1 (H == Ho, W == Wo): one pass over (Y_in, dY) produces dX (times swish'), dW partials and the input
@@ -615,14 +633,6 @@ int dws_tmap(CUtensorMap* m, const void* ptr, int N, int H, int W, int C, int bo
   return mclip_tmap_encode_bf16(m, ptr, 4, dims, strides, box, DWS_L2PROMO);
 }
 
-template <int K>
-struct FwdCfg {
-  static constexpr int NSLOT = (K == 3) ? DWS_K3_NSLOT : DWS_K5_NSLOT;
-  static constexpr int REP = (K == 3) ? DWS_K3_REP : DWS_K5_REP;
-  static constexpr int IW = 16 + K - 1;
-  static constexpr int SMEM = NSLOT * K * REP * IW * 128;
-};
-
 // work decomposition shared by mclip_dws_slots and the launchers
 void dws_plan(const mclip_dwconv_args* a, int ctas_per_sm, int rows_total, DwsDev& p) {
   const int TW = 16;
@@ -640,18 +650,23 @@ void dws_plan(const mclip_dwconv_args* a, int ctas_per_sm, int rows_total, DwsDe
   p.slots = std::min(ctas, p.items);
 }
 
-template <int K>
-int dws_launch_fwd_s1(const mclip_dwconv_args* a, DwsDev& p, cudaStream_t stream) {
-  constexpr int NSLOT = FwdCfg<K>::NSLOT;
+template <int K, int S>
+int dws_launch_fwd(const mclip_dwconv_args* a, DwsDev& p, cudaStream_t stream) {
+  using Cfg = FwdCfg<K, S>;
   CUtensorMap tm;
-  int rc = dws_tmap(&tm, p.in, p.N, p.H, p.W, p.C, FwdCfg<K>::IW, K * FwdCfg<K>::REP);
+  int rc = dws_tmap(&tm, p.in, p.N, p.H, p.W, p.C, Cfg::IW, Cfg::RB);
   if (rc) return rc;
-  auto kern = p.act ? mclip_dws_fwd_s1_kernel<K, NSLOT, FwdCfg<K>::REP, true> : mclip_dws_fwd_s1_kernel<K, NSLOT, FwdCfg<K>::REP, false>;
+  auto kern = p.act ? mclip_dws_fwd_kernel<K, S, true> : mclip_dws_fwd_kernel<K, S, false>;
   static bool attr[2] = {false, false};
-  if (!attr[p.act]) { MCLIP_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, FwdCfg<K>::SMEM)); attr[p.act] = true; }
-  kern<<<p.n_chunks * p.slots, 128, FwdCfg<K>::SMEM, stream>>>(tm, p);
+  if (!attr[p.act]) { MCLIP_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM)); attr[p.act] = true; }
+  kern<<<p.n_chunks * p.slots, 128, Cfg::SMEM, stream>>>(tm, p);
   MCLIP_CHECK_LAUNCH();
   return MCLIP_OK;
+}
+
+static int dws_fwd_ctas(const mclip_dwconv_args* a) {
+  if (a->stride == 1) return a->k == 3 ? FwdCfg<3, 1>::CTAS : FwdCfg<5, 1>::CTAS;
+  return a->k == 3 ? FwdCfg<3, 2>::CTAS : FwdCfg<5, 2>::CTAS;
 }
 
 template <int K>
@@ -689,18 +704,18 @@ void dws_fill(const mclip_dwconv_args* a, DwsDev& p) {
 // Which shapes the streaming kernels cover (the rest stays on conv.cu): stride 1 forward for now.
 bool mclip_dws_covers(const mclip_dwconv_args* a, int backward) {
   static int enabled = -1;
-  if (enabled < 0) { const char* e = getenv("MCLIP_DW_STREAM"); enabled = e ? atoi(e) : 3; }      // bit 0: forward, bit 1: backward
+  if (enabled < 0) { const char* e = getenv("MCLIP_DW_STREAM"); enabled = e ? atoi(e) : 7; }      // bit 0: forward, bit 1: backward (stride 1), bit 2: stride-2 forward
   if (!enabled) return false;
-  if (a->stride != 1 || (a->k != 3 && a->k != 5)) return false;
-  if (backward) return (enabled & 2) != 0 && a->ho == a->h && a->wo == a->w && (a->in_scale == nullptr || a->in_act == 1);
-  return true;
+  if ((a->stride != 1 && a->stride != 2) || (a->k != 3 && a->k != 5)) return false;
+  if (backward) return (enabled & 2) != 0 && a->stride == 1 && a->ho == a->h && a->wo == a->w && (a->in_scale == nullptr || a->in_act == 1);
+  return (enabled & 1) != 0 && (a->stride == 1 || (enabled & 4) != 0);
 }
 
 int mclip_dws_slots(const mclip_dwconv_args* a, int backward) {
   DwsDev p;
   dws_fill(a, p);
   if (backward) dws_plan(a, 2, a->h, p);
-  else dws_plan(a, a->k == 3 ? DWS_K3_CTAS : DWS_K5_CTAS, a->ho, p);
+  else dws_plan(a, dws_fwd_ctas(a), a->ho, p);
   return p.slots;
 }
 
@@ -735,9 +750,10 @@ int mclip_dws_backward(const mclip_dwconv_args* a, void* stream_) {
 int mclip_dws_forward(const mclip_dwconv_args* a, void* stream_) {
   DwsDev p;
   dws_fill(a, p);
-  dws_plan(a, a->k == 3 ? DWS_K3_CTAS : DWS_K5_CTAS, a->ho, p);
+  dws_plan(a, dws_fwd_ctas(a), a->ho, p);
   p.out = (bf16*)a->out; p.stats = a->stats;
   if (a->stats) MCLIP_REQUIRE(a->stat_slots == p.slots, "mclip_dwconv_forward: stat_slots=%d, expected %d", a->stat_slots, p.slots);
-  if (a->k == 3) return dws_launch_fwd_s1<3>(a, p, (cudaStream_t)stream_);
-  return dws_launch_fwd_s1<5>(a, p, (cudaStream_t)stream_);
+  cudaStream_t st = (cudaStream_t)stream_;
+  if (a->stride == 1) return a->k == 3 ? dws_launch_fwd<3, 1>(a, p, st) : dws_launch_fwd<5, 1>(a, p, st);
+  return a->k == 3 ? dws_launch_fwd<3, 2>(a, p, st) : dws_launch_fwd<5, 2>(a, p, st);
 }
