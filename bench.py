@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Benchmark of the Mammo-CLIP contrastive pre-training step (BASELINE.json metric: image-text pairs/sec).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c3|c2|c1]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference|oracle-gpu] [--workload c3|c2|c1|c3-mvs|loss-sweep]
 
 One step = forward (EfficientNet + BERT + projection heads + L2-norm) + fused InfoNCE (+ NVLink gather) + backward +
 gradient all-reduce (N>1) + AdamW, on synthetic data of the named shape with seeded random-init weights.
@@ -128,7 +128,25 @@ def cpu_reference_run(workload, steps, warmup, sample_batch, report_sample=True)
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
     torch.manual_seed(0)
-    model = port.OracleBreastClip(enc_name, num_hidden_layers=layers)
+    kind, loss_fn = "port", (lambda out: port.contrastive_loss(**out, is_train=True, label_smoothing=0.0))
+    model = None
+    try:                                             # the UNMODIFIED reference, where /root/reference exists (build container)
+        from oracle import ref_loader, make_goldens
+        if ref_loader.available():
+            ref_loader.load_reference()
+            from breastclip.loss import build_loss as ref_build_loss
+            from breastclip.model import build_model as ref_build_model
+            cfg, loss_cfg = _model_cfg(enc_cfg, layers)
+            cfg["text_encoder"] = dict(cfg["text_encoder"], name=make_goldens._bert_dir(layers, 0.1))
+            cfg["text_encoder"].pop("config")
+            model = ref_build_model(cfg, loss_cfg, make_goldens._Tok())
+            ref_loss = ref_build_loss(loss_cfg)
+            kind, loss_fn = "reference", (lambda out: ref_loss(**out, is_train=True)["total"])
+    except Exception as e:                           # any stub / import trouble: the pinned port
+        print(f"[bench] reference import failed ({type(e).__name__}: {e}); timing the oracle port", file=sys.stderr)
+        model = None
+    if model is None:
+        model = port.OracleBreastClip(enc_name, num_hidden_layers=layers)
     model.train()
     opt = torch.optim.AdamW(model.parameters(), lr=5e-5, weight_decay=1e-4)
     b = min(sample_batch, batch)
@@ -137,34 +155,50 @@ def cpu_reference_run(workload, steps, warmup, sample_batch, report_sample=True)
     for i in range(warmup + steps):
         t0 = time.perf_counter()
         opt.zero_grad(set_to_none=True)
-        out = model(data)
-        loss = port.contrastive_loss(**out, is_train=True, label_smoothing=0.0)
+        out = model(data, "cpu") if kind == "reference" else model(data)
+        loss = loss_fn(out)
         loss.backward()
         opt.step()
         if i >= warmup:
             times.append(time.perf_counter() - t0)
     sec = sum(times) / len(times)
-    return {"value": b / sec, "unit": "pairs/s", "cores": cores, "kind": "port",
+    return {"value": b / sec, "unit": "pairs/s", "cores": cores, "kind": kind,
             "sample": f"{len(times)} step(s) of {b} pair(s) of {workload} ({enc_name}, {h}x{w}, L={L}, BERT {layers} layers), fwd+loss+bwd+AdamW, fp32, {sec:.2f} s/step"}, sec
 
 
 def run_oracle_gpu(args):
-    """Informational (not a driver arm): the oracle port — the reference's module wiring on PyTorch/cuDNN/cuBLAS — on
-    cuda:0 under bf16 autocast, channels_last, eager (and torch.compile if --compile), at the largest batch that fits
-    (the reference's eager graph needs ~4.4 GB of saved activations per EN-B5 image, SURVEY finding 2)."""
+    """Reference GPU arm (SURVEY 8d "Reference GPU baseline"): the oracle port -- the reference's module wiring on
+    PyTorch/cuDNN/cuBLAS/NCCL -- under bf16 autocast, channels_last, fused AdamW, DDP(find_unused_parameters=True) when
+    launched through torchrun (trainer_ddp.py:134,293-300), eager or torch.compile (--compile).  The reference's eager
+    graph keeps ~4.4 GB of activations per EN-B5 image, so B = 64 does not fit 180 GB: the arm halves the batch until a
+    step fits (or takes --batch) and says so (`same_config`); --checkpoint recomputes every MBConv block in the backward
+    (torch.utils.checkpoint) so that the metric's batch fits.  Same JSON contract as the main arm."""
     import torch
+    import torch.distributed as dist
     from transformers import BatchEncoding
     from oracle import port
     enc_cfg, enc_name, layers, batch, h, w, L = WORKLOADS[args.workload]
-    b = args.batch or min(batch, 16)
+    rank, world, local = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
     torch.backends.cudnn.benchmark = True
     torch.manual_seed(0)
-    model = port.OracleBreastClip(enc_name, num_hidden_layers=layers).cuda().train().to(memory_format=torch.channels_last)
-    fwd = torch.compile(model) if args.compile else model
+    model = port.OracleBreastClip(enc_name, num_hidden_layers=layers).to(dev).train().to(memory_format=torch.channels_last)
+    if args.checkpoint:
+        from torch.utils.checkpoint import checkpoint
+        for blk in model.image_encoder._blocks:
+            blk.forward = (lambda *a, _f=blk.forward, **k: checkpoint(_f, *a, use_reentrant=False, **k))
+    net = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local], find_unused_parameters=True) if world > 1 else model
+    fwd = torch.compile(net) if args.compile else net
     opt = torch.optim.AdamW(model.parameters(), lr=5e-5, weight_decay=1e-4, fused=True)
-    data = {"images": port.synth_images(b, h, w, seed=1234, device="cuda"), "text_tokens": BatchEncoding(port.synth_tokens(b, L, seed=4321, device="cuda"))}
 
-    def step():
+    def make(b):
+        return {"images": port.synth_images(b, h, w, seed=1234 + rank, device=dev), "text_tokens": BatchEncoding(port.synth_tokens(b, L, seed=4321 + rank, device=dev))}
+
+    def step(data):
         opt.zero_grad(set_to_none=True)
         with torch.autocast("cuda", dtype=torch.bfloat16):
             out = fwd(data)
@@ -172,19 +206,46 @@ def run_oracle_gpu(args):
         loss.backward()
         opt.step()
 
-    for _ in range(max(args.warmup, 3)):
-        step()
-    torch.cuda.synchronize()
-    a, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    a.record()
-    for _ in range(args.steps):
-        step()
-    e.record()
-    torch.cuda.synchronize()
-    ms = a.elapsed_time(e) / args.steps
-    print(json.dumps({"impl": "oracle-gpu", "note": "informational: reference wiring on torch %s (cuDNN/cuBLAS), bf16 autocast, channels_last, %s" % (
-        torch.__version__, "torch.compile" if args.compile else "eager"), "value": b / (ms * 1e-3), "unit": "pairs/s", "ms_per_step": ms, "batch": b,
-        "workload": args.workload, "peak_mem_gb": torch.cuda.max_memory_allocated() / 1e9}))
+    b = args.batch or batch
+    while True:                                      # largest batch (halving) whose step fits; all ranks take the same decision
+        try:
+            data = make(b)
+            for _ in range(max(args.warmup, 3)):
+                step(data)
+            torch.cuda.synchronize()
+            ok = 1
+        except torch.OutOfMemoryError:
+            ok = 0
+        flag = torch.tensor([ok], device=dev)
+        if world > 1:
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        if flag.item():
+            break
+        data = None
+        opt.zero_grad(set_to_none=True)
+        torch.cuda.empty_cache()
+        if b == 1:
+            raise SystemExit("oracle-gpu: not even one pair fits")
+        b //= 2
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    ms = _timed_events(lambda: step(data), args.steps, barrier, dev, world) / args.steps
+    if rank == 0:
+        print(json.dumps({"impl": "oracle-gpu", "metric": "image-text pairs/sec", "value": b * world / (ms * 1e-3), "unit": "pairs/s", "n_gpus": world,
+                          "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                          "dtype": "bf16", "data": "synthetic",
+                          "config": {"workload": f"{args.workload}: {enc_name} + BERT-{layers}L, {h}x{w}, L={L}: reference wiring (oracle port) on torch {torch.__version__} "
+                                                 f"cuDNN/cuBLAS{'/NCCL DDP' if world > 1 else ''}, bf16 autocast, channels_last, fused AdamW, "
+                                                 f"{'torch.compile' if args.compile else 'eager'}{', per-MBConv activation checkpointing' if args.checkpoint else ''}",
+                                     "batch_per_gpu": b, "metric_batch_per_gpu": batch, "same_config": b == batch, "parallelism": f"ddp{world}"},
+                          "peak_mem_gb": round(torch.cuda.max_memory_allocated() / 1e9, 1),
+                          "note": "informational reference-GPU arm (the driver's --impl reference arm is the CPU path); not a product path"}))
+    if world > 1:
+        dist.destroy_process_group()
 
 
 def run_reference(args):
@@ -199,10 +260,146 @@ def run_reference(args):
     line = {"impl": "reference", "metric": "image-text pairs/sec", "value": base["value"], "unit": "pairs/s", "n_gpus": args.gpus, "steps": steps,
             "warmup": warm, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic", "config": {"workload": f"{args.workload}: {enc_name} + BERT-{layers}L, {h}x{w}, L={L}, contrastive step on host cores",
-                                           "sample_pairs_per_step": sample},
+                                           "sample_pairs_per_step": sample,
+                                           "note": f"pairs/s extrapolated from {sample} pair(s) per step (the CPU path needs ~11 GB and ~2 s per EN-B5 pair); "
+                                                   f"the metric config has {batch} pairs per step"},
             "cpu_baseline": base, "e2e": {"value": base["value"], "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------------------------------
+def p2p_parity(dev, rank, world, mvs=False):
+    """Start-up check at N > 1 (every driver-run scaling point): the fused NVLink gather + InfoNCE kernel against plain
+    torch.distributed all_gather (forward) / reduce_scatter (backward) -- the semantics of the reference's
+    DistAutogradAllGatherFunction (util/dist_autograd.py:4-26) under breast_clip_contrastive.py:28-59 -- on seeded
+    embeddings: loss, every embedding gradient and d(logit_scale).  Returns the worst relative error over ranks."""
+    import torch
+    import torch.distributed as dist
+    import torch.nn.functional as F
+    from mammoclip_b200.loss import build_loss
+
+    class _Gather(torch.autograd.Function):
+        @staticmethod
+        def forward(ctx, x):
+            out = [torch.zeros_like(x) for _ in range(world)]
+            dist.all_gather(out, x.contiguous())
+            return torch.cat(out, 0)
+
+        @staticmethod
+        def backward(ctx, g):
+            mine = torch.zeros(g.shape[0] // world, g.shape[1], device=g.device, dtype=g.dtype)
+            dist.reduce_scatter(mine, [t.contiguous() for t in g.chunk(world, 0)], dist.ReduceOp.SUM)
+            return mine
+
+    eps, B, D = 0.1, 64, 512
+    lf = build_loss({"breast_clip_contrastive": {"label_smoothing": eps, "i2i_weight": 1.0, "t2t_weight": 0.5, "loss_ratio": 1.0}})
+    worst = 0.0
+    for step in range(3):                      # several calls: epoch counters / double buffering of the gather buffers
+        g = torch.Generator(device=dev).manual_seed(1000 * step + rank)
+        embs = [F.normalize(torch.randn(B, D, generator=g, device=dev), dim=1) for _ in range(2)]
+        ours = [e.clone().requires_grad_(True) for e in embs]
+        ref = [e.clone().requires_grad_(True) for e in embs]
+        s1 = torch.tensor(14.2857, device=dev, requires_grad=True)
+        s2 = torch.tensor(14.2857, device=dev, requires_grad=True)
+        lab = torch.arange(B, device=dev)
+        lo = lf(image_embeddings=ours[0], text_embeddings=ours[1], labels=lab, logit_scale=s1, is_train=True)["total"]
+        lo.backward()
+        all_i, all_t = _Gather.apply(ref[0]), _Gather.apply(ref[1])
+        labels = lab + rank * B
+        lr = 0.75 * F.cross_entropy(s2 * ref[0] @ all_t.T, labels, label_smoothing=eps) + 0.25 * F.cross_entropy(s2 * ref[1] @ all_i.T, labels, label_smoothing=eps)
+        lr.backward()
+        errs = [abs(lo.item() - lr.item()) / abs(lr.item()), abs(s1.grad.item() - s2.grad.item()) / (abs(s2.grad.item()) + 1e-6)]
+        errs += [((a.grad - b.grad).abs().max() / b.grad.abs().max()).item() for a, b in zip(ours, ref)]
+        worst = max(worst, max(errs))
+    t = torch.tensor([worst], device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return t.item()
+
+
+def _timed_events(fn, n, barrier, dev, world):
+    import torch
+    import torch.distributed as dist
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    a.record()
+    for _ in range(n):
+        fn()
+    b.record()
+    barrier()
+    ms = torch.tensor([a.elapsed_time(b)], device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    return ms.item()
+
+
+def run_loss_sweep(args):
+    """BASELINE config 5: the fused gather + InfoNCE kernel over the global-batch sweep 64..512 pairs per GPU, next to NCCL
+    all_gather + reduce_scatter + the torch loss on the same embeddings.  Bytes received per rank and call: (W-1)*2*B*512*4.
+    One JSON line; `value` = fused calls per second at B = 64 per GPU."""
+    import torch
+    import torch.distributed as dist
+    import torch.nn.functional as F
+    from mammoclip_b200.loss import build_loss
+    from mammoclip_b200.util import GlobalEnv
+    rank, world, local = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    GlobalEnv.reset()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    parity = p2p_parity(dev, rank, world) if world > 1 else None
+    lf = build_loss({"breast_clip_contrastive": {"label_smoothing": 0.0, "i2i_weight": 0.0, "t2t_weight": 0.0, "loss_ratio": 1.0}})
+    rows = []
+    for B in (64, 128, 256, 512):
+        embs = [F.normalize(torch.randn(B, 512, device=dev), dim=1).requires_grad_(True) for _ in range(2)]
+        s = torch.tensor(14.2857, device=dev, requires_grad=True)
+        lab = torch.arange(B, device=dev)
+
+        def fused():
+            lf(image_embeddings=embs[0], text_embeddings=embs[1], labels=lab, logit_scale=s, is_train=True)["total"].backward()
+
+        def nccl():
+            if world > 1:
+                gi = [torch.empty_like(embs[0]) for _ in range(world)]; gt = [torch.empty_like(embs[1]) for _ in range(world)]
+                dist.all_gather(gi, embs[0].detach()); dist.all_gather(gt, embs[1].detach())
+                all_i, all_t = torch.cat(gi).requires_grad_(True), torch.cat(gt).requires_grad_(True)
+            else:
+                all_i, all_t = embs[0], embs[1]
+            labels = lab + rank * B
+            loss = 0.75 * F.cross_entropy(s * embs[0] @ all_t.T, labels) + 0.25 * F.cross_entropy(s * embs[1] @ all_i.T, labels)
+            loss.backward()
+            if world > 1:
+                for full in (all_i, all_t):
+                    mine = torch.empty_like(embs[0])
+                    dist.reduce_scatter(mine, list(full.grad.chunk(world, 0)), dist.ReduceOp.SUM)
+
+        res = {}
+        for name, fn in (("fused", fused), ("nccl_torch", nccl)):
+            for _ in range(max(args.warmup, 3)):
+                fn()
+            res[name] = _timed_events(fn, args.steps, barrier, dev, world) / args.steps * 1e3      # us per fwd+bwd call
+        recv = (world - 1) * 2 * B * 512 * 4
+        rows.append({"pairs_per_gpu": B, "global_batch": B * world, "fused_us": round(res["fused"], 1), "nccl_torch_us": round(res["nccl_torch"], 1),
+                     "recv_bytes_per_rank": recv, "achieved_gbs": round(recv / (res["fused"] * 1e-6) / 1e9, 2) if world > 1 else None,
+                     "frac_of_770": round(recv / (res["fused"] * 1e-6) / 770e9, 4) if world > 1 else None})
+    if rank == 0:
+        print(json.dumps({"metric": "fused gather+InfoNCE calls/sec (fwd+bwd, B=64/GPU)", "value": 1e6 / rows[0]["fused_us"], "unit": "calls/s", "n_gpus": world,
+                          "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": rows[0]["fused_us"] / 1e3, "higher_is_better": True, "scaling": "weak",
+                          "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                          "config": {"workload": "loss-sweep: L2-normalised [B,512] fp32 embeddings per GPU, contrastive loss fwd+bwd incl. the gather (BASELINE config 5)",
+                                     "note": "time per call includes the host launch; achieved_gbs = bytes received per rank / call time (whole call, not only the transfer)"},
+                          "p2p_parity": None if parity is None else {"status": "ok" if parity < 1e-3 else "FAILED", "worst_rel_err": parity},
+                          "sweep": rows}))
+    if world > 1:
+        dist.destroy_process_group()
 
 
 # ------------------------------------------------------------------------------------------------------------------
@@ -226,6 +423,9 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=dev)
     GlobalEnv.reset()
     _lib.check(_lib.lib().mclip_device_check(), "mclip_device_check")
+    parity = p2p_parity(dev, rank, world) if world > 1 else None
+    if parity is not None and not parity < 1e-3:
+        raise SystemExit(f"fused P2P loss disagrees with all_gather/reduce_scatter: worst rel err {parity}")
 
     enc_cfg, enc_name, layers, batch, h, w, L = WORKLOADS[args.workload]
     if args.batch:
@@ -242,14 +442,26 @@ def run_ours(args):
     img_h, tok_h = _synth_host(batch, h, w, L, rank)
     img_d = img_h.to(dev, non_blocking=True).permute(0, 3, 1, 2)
     tok_d = BatchEncoding({k: v.to(dev, non_blocking=True) for k, v in tok_h.items()})
-    h2d_bytes = img_h.numel() * 4 + sum(v.numel() * 8 for v in tok_h.values())
+    # end-to-end leg = the input edge: the loader's grey-level image as ONE uint8 channel in pinned host memory;
+    # per-image min-max + mean/std normalisation and the 1 -> 3 channel replication happen inside the stem's im2col kernel
+    # (bit-identical to the reference-shaped 3 x fp32 tensor, tests/test_gpu_conv.py).  --e2e-fp32 times the old 3 x fp32 copy.
+    g8 = torch.Generator().manual_seed(4321 + rank)
+    img8_h = torch.randint(0, 256, (batch, 1, h, w), generator=g8, dtype=torch.uint8).pin_memory()
+    e2e_img_h = img_h if args.e2e_fp32 else img8_h
+    h2d_bytes = e2e_img_h.numel() * e2e_img_h.element_size() + sum(v.numel() * 8 for v in tok_h.values())
+
+    ar_events = []
 
     def step(images, tokens):
         opt.zero_grad()
         out = model({"images": images, "text_tokens": tokens}, dev)
         loss = loss_fn(**out, is_train=True)["total"]
-        loss.backward()
-        scale = opt.all_reduce_grads(world)
+        loss.backward()                                  # finished gradient buckets are all-reduced on a side stream meanwhile
+        if world > 1 and ar_events is not None:
+            e0 = torch.cuda.Event(enable_timing=True); e0.record()
+        scale = opt.all_reduce_grads(world)              # remaining ranges + wait: the EXPOSED part of the collective
+        if world > 1 and ar_events is not None:
+            e1 = torch.cuda.Event(enable_timing=True); e1.record(); ar_events.append((e0, e1))
         opt.step(grad_scale=scale)
         return loss
 
@@ -261,7 +473,7 @@ def run_ours(args):
     def h2d_async():
         copy_stream.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(copy_stream):
-            images = img_h.to(dev, non_blocking=True)
+            images = e2e_img_h.to(dev, non_blocking=True)
             tokens = {k: v.to(dev, non_blocking=True) for k, v in tok_h.items()}
         pending["batch"] = (images, tokens)
 
@@ -274,7 +486,8 @@ def run_ours(args):
             t.record_stream(torch.cuda.current_stream())
         if prefetch_next:
             h2d_async()
-        return step(images.permute(0, 3, 1, 2), BatchEncoding(tokens)).item()          # device -> host read of the loss
+        images = images.permute(0, 3, 1, 2) if args.e2e_fp32 else images
+        return step(images, BatchEncoding(tokens)).item()          # device -> host read of the loss
 
     def barrier():
         if world > 1:
@@ -282,17 +495,7 @@ def run_ours(args):
         torch.cuda.synchronize()
 
     def timed(fn, n):
-        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        barrier()
-        a.record()
-        for _ in range(n):
-            fn()
-        b.record()
-        barrier()
-        ms = torch.tensor([a.elapsed_time(b)], device=dev)
-        if world > 1:
-            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-        return ms.item()
+        return _timed_events(fn, n, barrier, dev, world)
 
     # ---- warm-up, then a calibration step that event-times every kernel class to find the dominant one ----
     for _ in range(max(args.warmup, 3)):
@@ -325,8 +528,11 @@ def run_ours(args):
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
+    del ar_events[:]
     ms_total = timed(lambda: step(img_d, tok_d), args.steps)
     clocks = sampler.stop() if rank == 0 else None
+    ar_exposed_ms = sum(a.elapsed_time(b) for a, b in ar_events) / max(len(ar_events), 1) if world > 1 else 0.0
+    ar_stats = getattr(opt, "comm_stats", (0, 0))
     launches = _lib.PROF.launches()
     dom = _lib.PROF.summary().get(dominant, (0, 0.0, 0))
     _lib.PROF.enable([])
@@ -357,17 +563,24 @@ def run_ours(args):
         "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
         "config": {"workload": f"{args.workload}: {enc_name} + BERT-{layers}L (random init), batch {batch}/GPU, {h}x{w} 3-ch fp32 images, {L}-token text, "
                                f"single-view InfoNCE, fwd+loss+bwd+grad-allreduce+AdamW, train mode (drop-connect/dropout on)",
+                   "e2e_input": "3 x fp32 [B,3,H,W] pinned host images" if args.e2e_fp32 else
+                                "input edge: 1 x uint8 [B,1,H,W] pinned host images, normalised + replicated to 3 channels inside the stem kernel",
                    "l2": "inputs larger than L2 (images %.0f MB/step, activations GBs); no explicit flush" % (img_h.numel() * 4 / 1e6),
                    "parallelism": f"dp{world}"},
         "clocks": clocks,
         "e2e": {"value": pairs / (ms_e2e / e2e_steps * 1e-3), "unit": "pairs/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4,
                 "steps": e2e_steps},
         "gpu_launches": launches,
+        "p2p_parity": None if parity is None else {"status": "ok", "worst_rel_err": parity, "what": "fused NVLink gather+InfoNCE vs torch all_gather/reduce_scatter (loss, dE, dscale), 3 calls, B=64/GPU"},
+        "grad_allreduce": None if world == 1 else {"collective": "ncclAllReduce(sum) over fp32 gradient buckets on a side stream, overlapped with the backward",
+                                                   "calls_per_step": ar_stats[0], "bytes_per_step": ar_stats[1], "exposed_ms_per_step": round(ar_exposed_ms, 3)},
         "roofline": {"bound": "hbm", "kernel": dominant, "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
                      "traffic": (_traffic(dominant) or {}).get("bytes_per_launch") if args.workload == "c3" else None,
                      "traffic_note": (_traffic(dominant) or {}).get("note"),
                      "algorithmic_bytes_per_launch": dom[2] / max(dom[0], 1), "launches": dom[0], "avg_launch_ms": dom[1] / max(dom[0], 1), "peak_source": peak_src,
                      "step_share_ms": share,
+                     "classes": {k: {"ms": round(v[1], 3), "algorithmic_gbs": round(v[2] / 1e9 / (v[1] * 1e-3), 1) if v[1] > 0 else None,
+                                     "frac_of_hbm": round(v[2] / 1e9 / (v[1] * 1e-3) / hbm_peak, 3) if v[1] > 0 else None} for k, v in calib.items()},
                      "whole_step": {"algorithmic_gb_per_pair": bytes_pair / 1e9, "achieved_gbs": value / world * bytes_pair / 1e9,
                                     "frac_of_hbm": value / world * bytes_pair / 1e9 / hbm_peak,
                                     "tensor_tflops": value / world * flops_pair / 1e12, "frac_of_bf16": value / world * flops_pair / 1e12 / tf_peak}},
@@ -386,13 +599,17 @@ def main():
     ap.add_argument("--steps", type=int, default=8)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference", "oracle-gpu"])
+    ap.add_argument("--e2e-fp32", action="store_true", help="end-to-end leg copies the reference-shaped 3 x fp32 images instead of the uint8 input edge")
     ap.add_argument("--compile", action="store_true", help="oracle-gpu only: wrap the model in torch.compile")
-    ap.add_argument("--workload", default="c3", choices=list(WORKLOADS))
+    ap.add_argument("--checkpoint", action="store_true", help="oracle-gpu only: recompute every MBConv block in the backward so that the metric batch fits")
+    ap.add_argument("--workload", default="c3", choices=list(WORKLOADS) + ["loss-sweep", "c3-mvs"])
     ap.add_argument("--batch", type=int, default=0, help="debug only: override the per-GPU batch of the workload")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--ncu-range", action="store_true", help="run warm-up, then ONE step inside cudaProfilerStart/Stop and exit (ncu launch list)")
     args = ap.parse_args()
-    if args.impl == "reference":
+    if args.workload == "loss-sweep":
+        run_loss_sweep(args)
+    elif args.impl == "reference":
         run_reference(args)
     elif args.impl == "oracle-gpu":
         run_oracle_gpu(args)

@@ -51,6 +51,10 @@ typedef struct mclip_loss_args {
   uint32_t* const* peer_flags;                 /* device table [W]: every rank's arrival counters (u32[W]) */
   const uint32_t* my_flags;                    /* this rank's arrival counters */
   long long epoch;                             /* 1,2,3,... identical on all ranks, +1 per call on this buffer set */
+  /* ABI 4: a peer that never arrives no longer traps the context.  After peer_timeout_s seconds (0: MCLIP_PEER_TIMEOUT_S or
+   * 600 s, the order of NCCL's watchdog) the kernel stores 1 + <missing rank> in *status (device int, may be NULL), writes NaN
+   * to out[0] and finishes; the host raises from the status word (mammoclip_b200.ops checks it on the next call). */
+  int* status; double peer_timeout_s;
 } mclip_loss_args;
 long long mclip_loss_workspace_bytes(int world, int batch, int dim, int n_pairs);
 int mclip_loss_grid(int world, int batch, int n_pairs);
@@ -137,10 +141,21 @@ int mclip_dwconv_backward(const mclip_dwconv_args* args, void* stream);
 typedef struct mclip_stem_args {
   int n, h, w, ho, wo;
   int pad_left, pad_right, pad_top, pad_bottom;
-  const float* in; long long stride_n, stride_c, stride_h, stride_w;
+  const void* in; long long stride_n, stride_c, stride_h, stride_w;   /* element strides; stride_c ignored when in_channels == 1 */
   void* out;                      /* bf16 [n*ho*wo, 32] */
+  /* input edge (ABI 4): the data pipeline's grey-level image is a single channel replicated three times
+   * (datasets/imagetext.py:121 `convert('RGB')`).  in_channels == 1 reads ONE channel and writes it to the three tap groups,
+   * bit-identical to the 3-identical-channel input.  in_dtype: 0 fp32, 1 fp16, 2 bf16, 3 uint8.  With uint8 and norm_lut != NULL
+   * the per-image normalisation of imagetext.py:129-134 is applied on load through a per-image 256-entry table (bf16
+   * [n][256], from mclip_image_norm_lut_u8) that holds, for every grey level u, the reference's own fp32 result
+   * ((u - min) / range - mean) / std rounded to the bf16 the patch stores anyway. */
+  int in_channels, in_dtype;
+  const void* norm_lut;
 } mclip_stem_args;
 int mclip_stem_im2col(const mclip_stem_args* args, void* stream);
+/* uint8 [n, hw] image batch -> per-image {min, max - min} as fp32 [n][2] (imagetext.py:130-131) and the normalisation table
+ * lut[n][u] = bf16(((u - min) / (max - min) - mean) / std) in the reference's fp32 operation order (IEEE division). */
+int mclip_image_norm_lut_u8(const void* in, int n, long long hw, float mean, float std, float* minmax, void* lut, void* stream);
 
 /* ---- BatchNorm / swish / squeeze-excite / pooling passes ---------------------------------------------------------
  * Producer kernels (GEMM, depthwise, stem) emit per-channel (sum, sum sq) partials; mclip_bn_finalize turns them

@@ -32,6 +32,7 @@ class LossArgs(C.Structure):
         ("peer_flags", C.c_void_p),
         ("my_flags", C.c_void_p),
         ("epoch", C.c_longlong),
+        ("status", C.c_void_p), ("peer_timeout_s", C.c_double),
     ]
 
 
@@ -168,6 +169,7 @@ class StemArgs(C.Structure):
         ("pad_left", C.c_int), ("pad_right", C.c_int), ("pad_top", C.c_int), ("pad_bottom", C.c_int),
         ("in_", C.c_void_p), ("stride_n", C.c_longlong), ("stride_c", C.c_longlong), ("stride_h", C.c_longlong), ("stride_w", C.c_longlong),
         ("out", C.c_void_p),
+        ("in_channels", C.c_int), ("in_dtype", C.c_int), ("norm_lut", C.c_void_p),
     ]
 
 

@@ -12,6 +12,7 @@
 // weights in registers, input tile staged in shared memory after the BN+swish transform.
 #include "common.cuh"
 #include "mclip_internal.h"
+#include <cuda_fp16.h>
 #include <algorithm>
 using std::max;
 
@@ -671,8 +672,18 @@ extern "C" int mclip_dwconv_backward(const mclip_dwconv_args* a, void* stream_) 
 // 32 (K padded for the MMA), t = ci*9 + ky*3 + kx like the OIHW weight.  Forward = mclip_gemm_tn(patches, W[c,32]) with
 // the BN-statistics epilogue; weight gradient = mclip_gemm_wgrad(dY, patches).  (bf16 patches = what autocast feeds the conv.)
 // =====================================================================================================
-__global__ void __launch_bounds__(256) mclip_stem_im2col_kernel(const float* __restrict__ in, long long sn, long long sc, long long sh, long long sw,
-                                                                bf16* __restrict__ out, int N, int H, int W, int Ho, int Wo, int pl, int pt) {
+template <typename T> __device__ __forceinline__ float stem_ld(const T* p);
+template <> __device__ __forceinline__ float stem_ld<float>(const float* p) { return __ldg(p); }
+template <> __device__ __forceinline__ float stem_ld<__half>(const __half* p) { return __half2float(__ldg(p)); }
+template <> __device__ __forceinline__ float stem_ld<bf16>(const bf16* p) { return __bfloat162float(__ldg(p)); }
+template <> __device__ __forceinline__ float stem_ld<uint8_t>(const uint8_t* p) { return (float)__ldg(p); }
+
+// CIN == 3: the trainer's [N,3,H,W] tensor; CIN == 1: one channel, replicated into the three tap groups (bit-identical to
+// three identical channels).  NORM (uint8 input): ((u - min) / range - mean) / std per image, the reference's op order.
+template <typename T, int CIN, bool NORM>
+__global__ void __launch_bounds__(256) mclip_stem_im2col_kernel(const T* __restrict__ in, long long sn, long long sc, long long sh, long long sw,
+                                                                bf16* __restrict__ out, int N, int H, int W, int Ho, int Wo, int pl, int pt,
+                                                                const bf16* __restrict__ lut) {
   const long long npix = (long long)N * Ho * Wo;
   for (long long px = (long long)blockIdx.x * blockDim.x + threadIdx.x; px < npix; px += (long long)gridDim.x * blockDim.x) {
     const int ox = (int)(px % Wo);
@@ -681,7 +692,7 @@ __global__ void __launch_bounds__(256) mclip_stem_im2col_kernel(const float* __r
     float v[32];
 #pragma unroll
     for (int t = 0; t < 32; ++t) v[t] = 0.f;
-    const float* base = in + n * sn;
+    const T* base = in + n * sn;
 #pragma unroll
     for (int ky = 0; ky < 3; ++ky) {
       const int y = oy * 2 - pt + ky;
@@ -690,9 +701,16 @@ __global__ void __launch_bounds__(256) mclip_stem_im2col_kernel(const float* __r
       for (int kx = 0; kx < 3; ++kx) {
         const int x = ox * 2 - pl + kx;
         if ((unsigned)x >= (unsigned)W) continue;
-        const float* ip = base + y * sh + x * sw;
+        const T* ip = base + y * sh + x * sw;
+        if (CIN == 3) {
 #pragma unroll
-        for (int ci = 0; ci < 3; ++ci) v[ci * 9 + ky * 3 + kx] = __ldg(ip + ci * sc);
+          for (int ci = 0; ci < 3; ++ci) v[ci * 9 + ky * 3 + kx] = stem_ld<T>(ip + ci * sc);
+        } else {
+          float t;
+          if (NORM) t = __bfloat162float(lut[n * 256 + (int)__ldg(reinterpret_cast<const uint8_t*>(ip))]);      // 512-byte table per image: L1 hits
+          else t = stem_ld<T>(ip);
+          v[ky * 3 + kx] = t; v[9 + ky * 3 + kx] = t; v[18 + ky * 3 + kx] = t;
+        }
       }
     }
     bf16* op = out + (size_t)px * 32;
@@ -701,15 +719,68 @@ __global__ void __launch_bounds__(256) mclip_stem_im2col_kernel(const float* __r
   }
 }
 
+// per-image min / (max - min) of a uint8 image: one CTA per image, 16-byte loads
+__global__ void __launch_bounds__(1024) mclip_image_minmax_u8_kernel(const uint8_t* __restrict__ in, long long hw, float* __restrict__ out,
+                                                                     bf16* __restrict__ lut, float nmean, float nstd) {
+  __shared__ int smin[32], smax[32];
+  __shared__ float s_mn, s_rng;
+  const uint8_t* p = in + (size_t)blockIdx.x * hw;
+  int mn = 255, mx = 0;
+  const long long nvec = (((uintptr_t)p & 15) == 0) ? hw / 16 : 0;
+  for (long long i = threadIdx.x; i < nvec; i += blockDim.x) {
+    const uint4 q = __ldg(reinterpret_cast<const uint4*>(p) + i);
+    const uint32_t w4[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+#pragma unroll
+      for (int b = 0; b < 4; ++b) { const int u = (w4[k] >> (8 * b)) & 255; mn = min(mn, u); mx = max(mx, u); }
+  }
+  for (long long i = nvec * 16 + threadIdx.x; i < hw; i += blockDim.x) { const int u = p[i]; mn = min(mn, u); mx = max(mx, u); }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) { mn = min(mn, __shfl_xor_sync(0xffffffffu, mn, o)); mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o)); }
+  if ((threadIdx.x & 31) == 0) { smin[threadIdx.x >> 5] = mn; smax[threadIdx.x >> 5] = mx; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) { mn = min(mn, smin[w]); mx = max(mx, smax[w]); }
+    out[2 * blockIdx.x] = (float)mn;
+    out[2 * blockIdx.x + 1] = (float)(mx - mn);       // image -= image.min(); image /= image.max()   (imagetext.py:130-131)
+    s_mn = (float)mn; s_rng = (float)(mx - mn);
+  }
+  __syncthreads();
+  if (lut && threadIdx.x < 256)                       // ((u - min) / range - mean) / std in fp32 (IEEE division), then the patch's bf16
+    lut[blockIdx.x * 256 + threadIdx.x] = __float2bfloat16_rn(__fdiv_rn(__fsub_rn(__fdiv_rn(__fsub_rn((float)threadIdx.x, s_mn), s_rng), nmean), nstd));
+}
+
+extern "C" int mclip_image_norm_lut_u8(const void* in, int n, long long hw, float mean, float std, float* minmax, void* lut, void* stream) {
+  MCLIP_REQUIRE(in && minmax && n > 0 && hw > 0 && (!lut || std != 0.f), "mclip_image_norm_lut_u8: bad arguments");
+  mclip_image_minmax_u8_kernel<<<n, 1024, 0, (cudaStream_t)stream>>>((const uint8_t*)in, hw, minmax, (bf16*)lut, mean, std);
+  MCLIP_CHECK_LAUNCH();
+  return MCLIP_OK;
+}
+
 extern "C" int mclip_stem_im2col(const mclip_stem_args* a, void* stream_) {
   MCLIP_REQUIRE(a && a->in && a->out, "mclip_stem_im2col: null operand");
   MCLIP_REQUIRE(a->ho == (a->h + a->pad_top + a->pad_bottom - 3) / 2 + 1 && a->wo == (a->w + a->pad_left + a->pad_right - 3) / 2 + 1,
                 "mclip_stem_im2col: output size inconsistent with the static padding");
+  MCLIP_REQUIRE(a->in_channels == 0 || a->in_channels == 1 || a->in_channels == 3, "mclip_stem_im2col: in_channels=%d", a->in_channels);
+  MCLIP_REQUIRE(a->in_dtype >= 0 && a->in_dtype <= 3, "mclip_stem_im2col: in_dtype=%d", a->in_dtype);
+  const int cin = a->in_channels == 1 ? 1 : 3;
+  MCLIP_REQUIRE(cin == 1 || a->in_dtype == 0, "mclip_stem_im2col: the 3-channel input is fp32 (the reference trainer's tensor)");
+  MCLIP_REQUIRE(!a->norm_lut || (cin == 1 && a->in_dtype == 3), "mclip_stem_im2col: normalisation on load needs a 1-channel uint8 input");
   const long long npix = (long long)a->n * a->ho * a->wo;
   long long grid = (npix + 255) / 256;
   if (grid > (long long)mclip_num_sms() * 16) grid = (long long)mclip_num_sms() * 16;
-  mclip_stem_im2col_kernel<<<(int)grid, 256, 0, (cudaStream_t)stream_>>>(a->in, a->stride_n, a->stride_c, a->stride_h, a->stride_w, (bf16*)a->out, a->n,
-                                                                          a->h, a->w, a->ho, a->wo, a->pad_left, a->pad_top);
+  cudaStream_t st = (cudaStream_t)stream_;
+#define STEM_LAUNCH(T, CIN, NORM)                                                                                                              \
+  mclip_stem_im2col_kernel<T, CIN, NORM><<<(int)grid, 256, 0, st>>>((const T*)a->in, a->stride_n, a->stride_c, a->stride_h, a->stride_w, (bf16*)a->out, \
+                                                                    a->n, a->h, a->w, a->ho, a->wo, a->pad_left, a->pad_top, (const bf16*)a->norm_lut)
+  if (cin == 3) STEM_LAUNCH(float, 3, false);
+  else if (a->in_dtype == 0) STEM_LAUNCH(float, 1, false);
+  else if (a->in_dtype == 1) STEM_LAUNCH(__half, 1, false);
+  else if (a->in_dtype == 2) STEM_LAUNCH(bf16, 1, false);
+  else if (a->norm_lut) STEM_LAUNCH(uint8_t, 1, true);
+  else STEM_LAUNCH(uint8_t, 1, false);
+#undef STEM_LAUNCH
   MCLIP_CHECK_LAUNCH();
   return MCLIP_OK;
 }

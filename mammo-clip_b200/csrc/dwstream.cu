@@ -358,17 +358,17 @@ __global__ void __launch_bounds__(128, FwdCfg<K, S>::CTAS) mclip_dws_fwd_kernel(
 #ifndef DWS_BWD_NSLOT
 #define DWS_BWD_NSLOT 3
 #endif
-template <int K, int NSLOT, int REP, bool BN>
-__global__ void __launch_bounds__(256, 2) mclip_dws_bwd_s1_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constant__ CUtensorMap tmDy, const DwsDev p) {
-  constexpr int SW = 4, NS = 4, NW = 8, TW = SW * NS, IW = TW + K - 1, PC = SW + K - 1, RB = K * REP, KK = K;
+template <int K, int NSLOT, int REP, bool BN, int NS>
+__global__ void __launch_bounds__(NS * 64, NS == 4 ? 2 : 3) mclip_dws_bwd_s1_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constant__ CUtensorMap tmDy, const DwsDev p) {
+  constexpr int SW = 4, NW = 2 * NS, TW = SW * NS, IW = TW + K - 1, PC = SW + K - 1, RB = K * REP, KK = K;
   constexpr uint32_t ROW_BYTES = IW * 128, PART_BYTES = RB * ROW_BYTES, SLOT_BYTES = 2 * PART_BYTES;
   extern __shared__ __align__(1024) uint8_t dws_smem[];
   __shared__ float red[NS][4][32];
   __shared__ __align__(8) uint64_t full[NSLOT];
   __shared__ uint32_t arrivals[NSLOT];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int strip = warp & 3;
-  const bool wrole = warp < NS;                      // warps 0-3: weight gradient, warps 4-7: data gradient
+  const int strip = warp % NS;
+  const bool wrole = warp < NS;                      // first NS warps: weight gradient, last NS warps: data gradient
   const int chunk = blockIdx.x % p.n_chunks, slot = blockIdx.x / p.n_chunks;
   const int c0 = chunk * 64, c = c0 + lane * 2;
   const bool cvalid = c < p.C;
@@ -604,6 +604,290 @@ __global__ void __launch_bounds__(256, 2) mclip_dws_bwd_s1_kernel(const __grid_c
     red[strip][0][lane] = bs.x; red[strip][1][lane] = bs.y; red[strip][2][lane] = bq.x; red[strip][3][lane] = bq.y;
   }
   __syncthreads();
+  for (int i = threadIdx.x; i < K * K * 64; i += NS * 64) {
+    const int t = i / 64, ch = i % 64;
+    if (c0 + ch < p.C) {
+      float s2 = 0.f;
+#pragma unroll
+      for (int w2 = 0; w2 < NS; ++w2) s2 += wred[((size_t)w2 * K * K + t) * 64 + ch];
+      p.dw_part[((size_t)slot * K * K + t) * p.C + c0 + ch] = s2;
+    }
+  }
+  if (BN && p.bn_part && warp == 0 && cvalid) {
+    float a = 0.f, b = 0.f, cc = 0.f, d = 0.f;
+#pragma unroll
+    for (int w2 = 0; w2 < NS; ++w2) { a += red[w2][0][lane]; b += red[w2][1][lane]; cc += red[w2][2][lane]; d += red[w2][3][lane]; }
+    float* st = p.bn_part + (size_t)slot * 2 * p.C;
+    st[c] = a; st[c + 1] = b; st[p.C + c] = cc; st[p.C + c + 1] = d;
+  }
+}
+
+
+// -------------------------------------------------------------------------------------------------------------------
+// backward, stride 2.  Same two roles as stride 1, but the data gradient is a GATHER: input pixel (v, x) receives
+//   dA = sum over ky = (v+pt) mod 2 (+2,+4), kx = (x+pl) mod 2 (+2,+4) of dY[(v+pt-ky)/2][(x+pl-kx)/2] * w[ky][kx]
+// so the dgrad warp keeps a register window of the last NA = (K+1)/2 dY rows (4 + NA-1 pixels each) and produces the 8 input
+// pixels of one row per step (then swish', store, BN sums).  Ownership is shifted by the pads so that every parity is a
+// compile-time constant: a warp owns input columns 2*wx - pl + i (i < 8), an item owns input rows 2*r0 - pt + j (j < 2*rows);
+// local step jj = j + 2(NA-1) >= 0 (the dgrad window needs NA-1 earlier dY rows), groups of G = 2*NA steps.
+// Ring slot = G input rows of Y_in (33/35 px wide) + NA rows of dY (17/18 px wide).
+// -------------------------------------------------------------------------------------------------------------------
+template <int K, bool BN>
+__global__ void __launch_bounds__(256, 2) mclip_dws_bwd_s2_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constant__ CUtensorMap tmDy, const DwsDev p) {
+  constexpr int SW = 4, NS = 4, NW = 8, TW = SW * NS, NA = (K + 1) / 2, G = 2 * NA, RB = G, NSLOT = 3;
+  constexpr int IW = (TW - 1) * 2 + K, PC = (SW - 1) * 2 + K, IWG = TW + NA - 1, PCG = SW + NA - 1, OWN = 2 * SW;
+  constexpr uint32_t ROWY = IW * 128, ROWG = IWG * 128, PARTY = RB * ROWY, SLOT_BYTES = PARTY + NA * ROWG;
+  constexpr int JMIN = -2 * (NA - 1);
+  extern __shared__ __align__(1024) uint8_t dws_smem[];
+  __shared__ float red[NS][4][32];
+  __shared__ __align__(8) uint64_t full[NSLOT];
+  __shared__ uint32_t arrivals[NSLOT];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int strip = warp & 3;
+  const bool wrole = warp < NS;
+  const int chunk = blockIdx.x % p.n_chunks, slot = blockIdx.x / p.n_chunks;
+  const int c0 = chunk * 64, c = c0 + lane * 2;
+  const bool cvalid = c < p.C;
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tmIn); tma_prefetch_desc(&tmDy);
+    for (int s = 0; s < NSLOT; ++s) { mbar_init(&full[s], 1); arrivals[s] = 0; }
+    fence_mbar_init();
+  }
+  __syncthreads();
+  const uint32_t ring = smem_u32(dws_smem);
+  const int my_items = p.items > slot ? (p.items - slot + p.slots - 1) / p.slots : 0;
+  const int per_img = p.strips_x * p.segs;
+  const int rows_total = p.seg_rows * p.segs;      // >= max(Ho, ceil((H+pt)/2)): the row-pair grid (host plan)
+
+  auto load_item = [&](DwsIter& it) {
+    const int g = slot + it.item * p.slots;
+    it.n = g / per_img;
+    const int rem = g - it.n * per_img;
+    const int sy = rem / p.strips_x;
+    it.x0 = (rem - sy * p.strips_x) * TW;
+    it.r0 = sy * p.seg_rows;
+    it.rows = min(rows_total, it.r0 + p.seg_rows) - it.r0;
+    it.nblk = (2 * (it.rows - 1) + K + 2 * (NA - 1) + RB - 1) / RB;
+    it.blk = 0;
+  };
+  DwsIter pi;
+  pi.item = 0;
+  auto advance = [&]() { if (++pi.blk == pi.nblk) { if (++pi.item < my_items) load_item(pi); } };
+  auto issue = [&](int s) {
+    uint8_t* dst = dws_smem + (size_t)s * SLOT_BYTES;
+    mbar_expect_tx(&full[s], SLOT_BYTES);
+    tma_load_4d(dst, &tmIn, &full[s], c0, 2 * pi.x0 - p.pl, 2 * pi.r0 - p.pt + JMIN + pi.blk * RB, pi.n);
+    tma_load_4d(dst + PARTY, &tmDy, &full[s], c0, pi.x0 - (NA - 1), pi.r0 - (NA - 1) + pi.blk * NA, pi.n);
+  };
+  if (my_items > 0) {
+    load_item(pi);
+#pragma unroll 1
+    for (int i = 0; i < NSLOT; ++i) {
+      if (pi.item < my_items) {
+        if (threadIdx.x == 0) issue(i);
+        advance();
+      }
+    }
+  }
+
+  float2 wv[K * K];                                    // wgrad role: dW accumulators; dgrad role: the weights
+#pragma unroll
+  for (int t = 0; t < K * K; ++t)
+    wv[t] = (!wrole && cvalid) ? make_float2(p.w[(size_t)c * K * K + t], p.w[(size_t)(c + 1) * K * K + t]) : make_float2(0.f, 0.f);
+  const float f = BN ? 0.5f : 1.0f;
+  float2 a2 = make_float2(f, f), b2 = make_float2(0.f, 0.f), mu_is = make_float2(1.f, 1.f), nmis = make_float2(0.f, 0.f);
+  if (BN && cvalid) {
+    a2 = make_float2(f * p.scale[c], f * p.scale[c + 1]); b2 = make_float2(f * p.shift[c], f * p.shift[c + 1]);
+    mu_is = make_float2(p.invstd[c], p.invstd[c + 1]);
+    nmis = make_float2(-p.mean[c] * mu_is.x, -p.mean[c + 1] * mu_is.y);
+  }
+  float2 bs = make_float2(0.f, 0.f), bq = make_float2(0.f, 0.f);
+  const float2 one = make_float2(1.f, 1.f), half2 = make_float2(0.5f, 0.5f), two2 = make_float2(2.f, 2.f), neg1 = make_float2(-1.f, -1.f);
+  const int cw = p.C >> 1;
+  const unsigned rstride_b = (unsigned)(p.W * cw) * 4u, pix_b = (unsigned)p.C * 2u;
+  DwsIter ci;
+  ci.item = 0;
+  int count = 0;
+#pragma unroll 1
+  for (; ci.item < my_items; ++ci.item) {
+    load_item(ci);
+    const int wx = ci.x0 + strip * SW;               // first dY column of this warp's strip
+    const int xo = 2 * wx - p.pl;                    // first owned input column (may be negative)
+    const bool wactive = xo < p.W;
+    uint32_t inmask = 0, ownmask = 0;
+#pragma unroll
+    for (int ix = 0; ix < PC; ++ix) { const int gx = xo + ix; inmask |= (gx >= 0 && gx < p.W) ? (1u << ix) : 0u; }
+#pragma unroll
+    for (int i = 0; i < OWN; ++i) { const int gx = xo + i; ownmask |= (gx >= 0 && gx < p.W && cvalid) ? (1u << i) : 0u; }
+    const bool edge = inmask != ((1u << PC) - 1u);
+    const bool warp_fast = wrole ? !edge : (xo >= 0 && xo + OWN <= p.W);
+    const int v0 = 2 * ci.r0 - p.pt;                 // input row of local step j = 0
+    // dx word of (row v0, column xo) for this lane; rows / columns advance by rstride_b / pix_b
+    char* const obase = reinterpret_cast<char*>(p.dx) + ((long long)ci.n * p.H * (long long)(p.W * cw) + (long long)(c >> 1)) * 4 +
+                        (long long)v0 * (long long)rstride_b + (long long)xo * (long long)pix_b;
+    // window of the last NA dY rows: the dgrad role keeps PCG pixels per row, the wgrad role SW (zero outside its segment)
+    float2 win[NA][PCG];
+#pragma unroll
+    for (int a = 0; a < NA; ++a)
+#pragma unroll
+      for (int b = 0; b < PCG; ++b) win[a][b] = make_float2(0.f, 0.f);
+
+    // slot of dY row (j - ky) / 2 with j = jj + JMIN, jj = s (mod G):  ((s - ky)/2 - (NA-1)) mod NA
+    auto wstep = [&](auto fast_c, auto s_c, uint32_t ybase, uint32_t gbase, int j) {
+      constexpr bool FAST = decltype(fast_c)::value;
+      constexpr int s = decltype(s_c)::value;
+      if (s % 2 == 0) {                              // dY row j/2 enters the window
+        constexpr int qn = ((s / 2 - (NA - 1)) % NA + NA) % NA;
+        const int orel = (j - (s % 2)) / 2;
+        if (FAST || (j >= 0 && orel < ci.rows && ci.r0 + orel < p.Ho)) {
+#pragma unroll
+          for (int o = 0; o < SW; ++o) win[qn][o] = bf2_to_f2(lds32(gbase + (s / 2) * ROWG + (NA - 1 + o) * 128));
+        } else {
+#pragma unroll
+          for (int o = 0; o < SW; ++o) win[qn][o] = make_float2(0.f, 0.f);
+        }
+      }
+      if (FAST || (unsigned)(v0 + j) < (unsigned)p.H) {
+        float2 x[PC];
+#pragma unroll
+        for (int ix = 0; ix < PC; ++ix) {
+          float2 h = ffma2r(bf2_to_f2(lds32(ybase + s * ROWY + ix * 128)), a2, b2);
+          if (BN) h = ffma2r(h, make_float2(fast_tanh(h.x), fast_tanh(h.y)), h);
+          x[ix] = h;
+        }
+        if (!FAST && edge) {
+#pragma unroll
+          for (int ix = 0; ix < PC; ++ix)
+            if (!((inmask >> ix) & 1u)) x[ix] = make_float2(0.f, 0.f);
+        }
+#pragma unroll
+        for (int ky = s % 2; ky < K; ky += 2) {
+          constexpr int dummy = 0; (void)dummy;
+          const int q = (((s - ky) / 2 - (NA - 1)) % NA + 2 * NA) % NA;
+#pragma unroll
+          for (int kx = 0; kx < K; ++kx)
+#pragma unroll
+            for (int o = 0; o < SW; ++o) ffma2(wv[ky * K + kx], win[q][o], x[2 * o + kx]);
+        }
+      }
+    };
+    auto dstep = [&](auto fast_c, auto s_c, uint32_t ybase, uint32_t gbase, int j) {
+      constexpr bool FAST = decltype(fast_c)::value;
+      constexpr int s = decltype(s_c)::value;
+      if (s % 2 == 0) {                              // dY row j/2 enters the window (TMA zero-fills outside dY)
+        constexpr int qn = ((s / 2 - (NA - 1)) % NA + NA) % NA;
+#pragma unroll
+        for (int b = 0; b < PCG; ++b) win[qn][b] = bf2_to_f2(lds32(gbase + (s / 2) * ROWG + b * 128));
+      }
+      // owned input row v0 + j (owned: 0 <= j < 2*rows)
+      if (FAST || (j >= 0 && j < 2 * ci.rows && (unsigned)(v0 + j) < (unsigned)p.H)) {
+        float2 acc[OWN];
+#pragma unroll
+        for (int i = 0; i < OWN; ++i) {
+          bool first = true;
+#pragma unroll
+          for (int ky = s % 2; ky < K; ky += 2) {
+            const int q = (((s - ky) / 2 - (NA - 1)) % NA + 2 * NA) % NA;
+#pragma unroll
+            for (int kx = i % 2; kx < K; kx += 2) {
+              const int b = (i - kx) / 2 + (NA - 1);   // exact: i - kx is even
+              if (first) { acc[i] = fmul2(win[q][b], wv[ky * K + kx]); first = false; }
+              else ffma2(acc[i], win[q][b], wv[ky * K + kx]);
+            }
+          }
+        }
+        char* op = obase + (long long)j * (long long)rstride_b;
+#pragma unroll
+        for (int i = 0; i < OWN; ++i) {
+          const bool st = FAST ? cvalid : (((ownmask >> i) & 1u) != 0);
+          float2 d = acc[i];
+          if (BN) {
+            const float2 yv = bf2_to_f2(lds32(ybase + s * ROWY + i * 128));
+            const float2 hv = ffma2r(yv, a2, b2);
+            const float2 sg = ffma2r(make_float2(fast_tanh(hv.x), fast_tanh(hv.y)), half2, half2);
+            const float2 om = ffma2r(sg, neg1, one);
+            const float2 qq = ffma2r(fmul2(hv, om), two2, one);
+            d = fmul2(d, fmul2(sg, qq));
+            if (!FAST && !st) d = make_float2(0.f, 0.f);
+            ffma2(bs, d, one);
+            ffma2(bq, d, ffma2r(yv, mu_is, nmis));
+          }
+          stg32_if(op + (unsigned)i * pix_b, pack_bf16(d.x, d.y), st);
+        }
+      }
+    };
+#pragma unroll 1
+    for (int blk = 0; blk < ci.nblk; ++blk, ++count) {
+      const int sl = count % NSLOT;
+      mbar_wait(&full[sl], (uint32_t)(count / NSLOT) & 1u);
+      if (wactive) {
+        const uint32_t sbase = ring + (uint32_t)sl * SLOT_BYTES + (uint32_t)lane * 4u;
+        const uint32_t ybase = sbase + (uint32_t)(strip * OWN) * 128u, gbase = sbase + PARTY + (uint32_t)(strip * SW) * 128u;
+        const int j = JMIN + blk * RB;               // local step j of group position s = 0
+        if (wrole) {
+          // fast: every A row inside the image, every dY row entering the window owned by this segment and inside dY
+          const bool fast = warp_fast && v0 + j >= 0 && v0 + j + G <= p.H && j >= 0 && (j + G - 2) / 2 < ci.rows && ci.r0 + (j + G - 2) / 2 < p.Ho;
+          if (fast) {
+            wstep(std::true_type{}, std::integral_constant<int, 0>{}, ybase, gbase, j);
+            wstep(std::true_type{}, std::integral_constant<int, 1>{}, ybase, gbase, j + 1);
+            wstep(std::true_type{}, std::integral_constant<int, 2>{}, ybase, gbase, j + 2);
+            wstep(std::true_type{}, std::integral_constant<int, 3>{}, ybase, gbase, j + 3);
+            if constexpr (G > 4) {
+              wstep(std::true_type{}, std::integral_constant<int, 4>{}, ybase, gbase, j + 4);
+              wstep(std::true_type{}, std::integral_constant<int, 5>{}, ybase, gbase, j + 5);
+            }
+          } else {
+            wstep(std::false_type{}, std::integral_constant<int, 0>{}, ybase, gbase, j);
+            wstep(std::false_type{}, std::integral_constant<int, 1>{}, ybase, gbase, j + 1);
+            wstep(std::false_type{}, std::integral_constant<int, 2>{}, ybase, gbase, j + 2);
+            wstep(std::false_type{}, std::integral_constant<int, 3>{}, ybase, gbase, j + 3);
+            if constexpr (G > 4) {
+              wstep(std::false_type{}, std::integral_constant<int, 4>{}, ybase, gbase, j + 4);
+              wstep(std::false_type{}, std::integral_constant<int, 5>{}, ybase, gbase, j + 5);
+            }
+          }
+        } else {
+          const bool fast = warp_fast && j >= 0 && j + G <= 2 * ci.rows && v0 + j >= 0 && v0 + j + G <= p.H;
+          if (fast) {
+            dstep(std::true_type{}, std::integral_constant<int, 0>{}, ybase, gbase, j);
+            dstep(std::true_type{}, std::integral_constant<int, 1>{}, ybase, gbase, j + 1);
+            dstep(std::true_type{}, std::integral_constant<int, 2>{}, ybase, gbase, j + 2);
+            dstep(std::true_type{}, std::integral_constant<int, 3>{}, ybase, gbase, j + 3);
+            if constexpr (G > 4) {
+              dstep(std::true_type{}, std::integral_constant<int, 4>{}, ybase, gbase, j + 4);
+              dstep(std::true_type{}, std::integral_constant<int, 5>{}, ybase, gbase, j + 5);
+            }
+          } else {
+            dstep(std::false_type{}, std::integral_constant<int, 0>{}, ybase, gbase, j);
+            dstep(std::false_type{}, std::integral_constant<int, 1>{}, ybase, gbase, j + 1);
+            dstep(std::false_type{}, std::integral_constant<int, 2>{}, ybase, gbase, j + 2);
+            dstep(std::false_type{}, std::integral_constant<int, 3>{}, ybase, gbase, j + 3);
+            if constexpr (G > 4) {
+              dstep(std::false_type{}, std::integral_constant<int, 4>{}, ybase, gbase, j + 4);
+              dstep(std::false_type{}, std::integral_constant<int, 5>{}, ybase, gbase, j + 5);
+            }
+          }
+        }
+      }
+      __syncwarp();
+      if (pi.item < my_items) {
+        if (lane == 0 && (atom_add_acqrel_smem(&arrivals[sl], 1u) % NW) == NW - 1) {
+          fence_proxy_async_smem();
+          issue(sl);
+        }
+        advance();
+      }
+    }
+  }
+  __syncthreads();
+  float* wred = reinterpret_cast<float*>(dws_smem);
+  if (wrole) {
+#pragma unroll
+    for (int q = 0; q < K * K; ++q) *reinterpret_cast<float2*>(wred + ((size_t)strip * K * K + q) * 64 + lane * 2) = wv[q];
+  } else {
+    red[strip][0][lane] = bs.x; red[strip][1][lane] = bs.y; red[strip][2][lane] = bq.x; red[strip][3][lane] = bq.y;
+  }
+  __syncthreads();
   for (int i = threadIdx.x; i < K * K * 64; i += 256) {
     const int t = i / 64, ch = i % 64;
     if (c0 + ch < p.C) {
@@ -634,8 +918,7 @@ int dws_tmap(CUtensorMap* m, const void* ptr, int N, int H, int W, int C, int bo
 }
 
 // work decomposition shared by mclip_dws_slots and the launchers
-void dws_plan(const mclip_dwconv_args* a, int ctas_per_sm, int rows_total, DwsDev& p) {
-  const int TW = 16;
+void dws_plan(const mclip_dwconv_args* a, int ctas_per_sm, int rows_total, DwsDev& p, int TW = 16) {
   p.n_chunks = ceil_div(a->c, 64);
   p.strips_x = ceil_div(a->wo, TW);
   int ctas = (mclip_num_sms() * ctas_per_sm) / p.n_chunks;
@@ -669,13 +952,18 @@ static int dws_fwd_ctas(const mclip_dwconv_args* a) {
   return a->k == 3 ? FwdCfg<3, 2>::CTAS : FwdCfg<5, 2>::CTAS;
 }
 
+#ifndef DWS_BWD_K5_NS
+#define DWS_BWD_K5_NS 4
+#endif
 template <int K>
 struct BwdCfg {
   static constexpr int NSLOT = DWS_BWD_NSLOT;
   static constexpr int REP = (K == 3) ? 2 : 1;
-  static constexpr int IW = 16 + K - 1;
+  static constexpr int NS = (K == 3) ? 4 : DWS_BWD_K5_NS;      // column strips per CTA (k5: 2 -> 128 threads, 3 CTAs/SM at 168 registers, no spills)
+  static constexpr int CTAS = NS == 4 ? 2 : 3;
+  static constexpr int TW = 4 * NS, IW = TW + K - 1;
   static constexpr int RING = NSLOT * 2 * K * REP * IW * 128;
-  static constexpr int SMEM = RING > 4 * K * K * 64 * 4 ? RING : 4 * K * K * 64 * 4;
+  static constexpr int SMEM = RING > NS * K * K * 64 * 4 ? RING : NS * K * K * 64 * 4;
 };
 
 template <int K>
@@ -685,12 +973,48 @@ int dws_launch_bwd_s1(const mclip_dwconv_args* a, DwsDev& p, cudaStream_t stream
   if (rc) return rc;
   if ((rc = dws_tmap(&tmDy, p.dy, p.N, p.Ho, p.Wo, p.C, BwdCfg<K>::IW, K * BwdCfg<K>::REP))) return rc;
   const bool bn = p.scale != nullptr;
-  auto kern = bn ? mclip_dws_bwd_s1_kernel<K, BwdCfg<K>::NSLOT, BwdCfg<K>::REP, true> : mclip_dws_bwd_s1_kernel<K, BwdCfg<K>::NSLOT, BwdCfg<K>::REP, false>;
+  auto kern = bn ? mclip_dws_bwd_s1_kernel<K, BwdCfg<K>::NSLOT, BwdCfg<K>::REP, true, BwdCfg<K>::NS> : mclip_dws_bwd_s1_kernel<K, BwdCfg<K>::NSLOT, BwdCfg<K>::REP, false, BwdCfg<K>::NS>;
   static bool attr[2] = {false, false};
   if (!attr[bn]) { MCLIP_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, BwdCfg<K>::SMEM)); attr[bn] = true; }
-  kern<<<p.n_chunks * p.slots, 256, BwdCfg<K>::SMEM, stream>>>(tmIn, tmDy, p);
+  kern<<<p.n_chunks * p.slots, BwdCfg<K>::NS * 64, BwdCfg<K>::SMEM, stream>>>(tmIn, tmDy, p);
   MCLIP_CHECK_LAUNCH();
   return MCLIP_OK;
+}
+
+template <int K>
+struct Bwd2Cfg {
+  static constexpr int NA = (K + 1) / 2, G = 2 * NA, IW = 30 + K, IWG = 16 + NA - 1;
+  static constexpr int RING = 3 * (G * IW + NA * IWG) * 128;
+  static constexpr int SMEM = RING > 4 * K * K * 64 * 4 ? RING : 4 * K * K * 64 * 4;
+};
+
+template <int K>
+int dws_launch_bwd_s2(const mclip_dwconv_args* a, DwsDev& p, cudaStream_t stream) {
+  using Cfg = Bwd2Cfg<K>;
+  CUtensorMap tmIn, tmDy;
+  int rc = dws_tmap(&tmIn, p.in, p.N, p.H, p.W, p.C, Cfg::IW, Cfg::G);
+  if (rc) return rc;
+  if ((rc = dws_tmap(&tmDy, p.dy, p.N, p.Ho, p.Wo, p.C, Cfg::IWG, Cfg::NA))) return rc;
+  const bool bn = p.scale != nullptr;
+  auto kern = bn ? mclip_dws_bwd_s2_kernel<K, true> : mclip_dws_bwd_s2_kernel<K, false>;
+  static bool attr[2] = {false, false};
+  if (!attr[bn]) { MCLIP_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM)); attr[bn] = true; }
+  kern<<<p.n_chunks * p.slots, 256, Cfg::SMEM, stream>>>(tmIn, tmDy, p);
+  MCLIP_CHECK_LAUNCH();
+  return MCLIP_OK;
+}
+
+static void dws_plan_bwd1(const mclip_dwconv_args* a, DwsDev& p) {
+  if (a->k == 3) dws_plan(a, BwdCfg<3>::CTAS, a->h, p, BwdCfg<3>::TW);
+  else dws_plan(a, BwdCfg<5>::CTAS, a->h, p, BwdCfg<5>::TW);
+}
+
+// stride-2 backward: the grid of (dY row, dY column) PAIRS must also cover every input pixel, with ownership shifted by the pads
+static void dws_plan_bwd2(const mclip_dwconv_args* a, DwsDev& p) {
+  const int rows = std::max(a->ho, ceil_div(a->h + a->pad_top, 2)), cols = std::max(a->wo, ceil_div(a->w + a->pad_left, 2));
+  mclip_dwconv_args t = *a;
+  t.wo = cols;
+  dws_plan(&t, 2, rows, p);
 }
 
 void dws_fill(const mclip_dwconv_args* a, DwsDev& p) {
@@ -704,17 +1028,19 @@ void dws_fill(const mclip_dwconv_args* a, DwsDev& p) {
 // Which shapes the streaming kernels cover (the rest stays on conv.cu): stride 1 forward for now.
 bool mclip_dws_covers(const mclip_dwconv_args* a, int backward) {
   static int enabled = -1;
-  if (enabled < 0) { const char* e = getenv("MCLIP_DW_STREAM"); enabled = e ? atoi(e) : 7; }      // bit 0: forward, bit 1: backward (stride 1), bit 2: stride-2 forward
+  if (enabled < 0) { const char* e = getenv("MCLIP_DW_STREAM"); enabled = e ? atoi(e) : 15; }     // bit 0: forward, bit 1: backward (stride 1), bit 2: stride-2 forward, bit 3: stride-2 backward
   if (!enabled) return false;
   if ((a->stride != 1 && a->stride != 2) || (a->k != 3 && a->k != 5)) return false;
-  if (backward) return (enabled & 2) != 0 && a->stride == 1 && a->ho == a->h && a->wo == a->w && (a->in_scale == nullptr || a->in_act == 1);
+  if (backward && a->stride == 2) return (enabled & 8) != 0 && (a->in_scale == nullptr || a->in_act == 1);
+  if (backward) return (enabled & 2) != 0 && a->ho == a->h && a->wo == a->w && (a->in_scale == nullptr || a->in_act == 1);
   return (enabled & 1) != 0 && (a->stride == 1 || (enabled & 4) != 0);
 }
 
 int mclip_dws_slots(const mclip_dwconv_args* a, int backward) {
   DwsDev p;
   dws_fill(a, p);
-  if (backward) dws_plan(a, 2, a->h, p);
+  if (backward && a->stride == 2) dws_plan_bwd2(a, p);
+  else if (backward) dws_plan_bwd1(a, p);
   else dws_plan(a, dws_fwd_ctas(a), a->ho, p);
   return p.slots;
 }
@@ -734,12 +1060,14 @@ int mclip_dws_backward(const mclip_dwconv_args* a, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   DwsDev p;
   dws_fill(a, p);
-  dws_plan(a, 2, a->h, p);
+  if (a->stride == 2) dws_plan_bwd2(a, p); else dws_plan_bwd1(a, p);
   MCLIP_REQUIRE(a->stat_slots == p.slots, "mclip_dwconv_backward: stat_slots=%d, expected %d", a->stat_slots, p.slots);
   p.dy = (const bf16*)a->dy; p.dx = (bf16*)a->dx; p.dw_part = a->dw_partials;
   p.bn_part = a->in_scale ? a->bn_partials : nullptr; p.mean = a->in_mean; p.invstd = a->in_invstd;
   if (p.bn_part) MCLIP_REQUIRE(p.mean && p.invstd, "mclip_dwconv_backward: input BN statistics missing");
-  int rc = a->k == 3 ? dws_launch_bwd_s1<3>(a, p, stream) : dws_launch_bwd_s1<5>(a, p, stream);
+  int rc;
+  if (a->stride == 2) rc = a->k == 3 ? dws_launch_bwd_s2<3>(a, p, stream) : dws_launch_bwd_s2<5>(a, p, stream);
+  else rc = a->k == 3 ? dws_launch_bwd_s1<3>(a, p, stream) : dws_launch_bwd_s1<5>(a, p, stream);
   if (rc) return rc;
   const int KK = a->k * a->k;
   mclip_dws_wgrad_reduce_kernel<<<ceil_div(KK * a->c, 256), 256, 0, stream>>>(a->dw_partials, a->dweight, p.slots, KK, a->c, a->accumulate);

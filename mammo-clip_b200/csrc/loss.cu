@@ -25,6 +25,7 @@
 //   3  deterministic fixed-order reduction of the partials into dE_k, loss, per-pair components, d scale.
 #include "common.cuh"
 #include "mclip_internal.h"
+#include <stdlib.h>
 #include <cooperative_groups.h>
 #include <math.h>
 namespace cg = cooperative_groups;
@@ -56,6 +57,8 @@ struct LossDev {
   // outputs
   float* dE[MCLIP_LOSS_MAX_TENSORS];   // [B,D] each
   float* out;        // [2 + 2P]: loss, dscale, then per pair (row CE mean, col CE mean)
+  int* status;       // device int or nullptr: 1 + rank of a peer that never arrived
+  long long timeout_cycles;
 };
 
 __device__ __forceinline__ unsigned int ld_acquire_sys(const unsigned int* p) {
@@ -76,10 +79,12 @@ __device__ __forceinline__ void wait_sources(const LossDev& p, int r0, int r1) {
       if (s == p.rank) continue;   // own slab is written by this very grid before the phase barrier
       long long t0 = clock64();
       while ((int)(ld_acquire_sys(p.my_flags + s) - p.flag_target) < 0) {
-        if (clock64() - t0 > 40000000000LL) {   // ~20 s at 2 GHz: a peer never arrived
-          printf("mclip loss: rank %d timed out waiting for the embeddings of rank %d\n", p.rank, s);
-          __trap();
+        if (clock64() - t0 > p.timeout_cycles) {   // a peer never arrived: report and finish (no trap: the context survives)
+          if (p.status && atomicCAS(p.status, 0, 1 + s) == 0)
+            printf("mclip loss: rank %d timed out waiting for the embeddings of rank %d\n", p.rank, s);
+          break;
         }
+        __nanosleep(200);
       }
     }
   }
@@ -340,7 +345,7 @@ __global__ void __launch_bounds__(LOSS_THREADS) mclip_loss_kernel(const LossDev 
           float w = side == 0 ? p.w_row[pr] : p.w_col[pr];
           p.out[2 + 2 * pr + side] = (w != 0.f) ? a / w : 0.f;   // the unweighted CE mean of this direction
         }
-      p.out[0] = loss;
+      p.out[0] = (p.status && *reinterpret_cast<volatile int*>(p.status) != 0) ? __int_as_float(0x7fc00000) : loss;
       p.out[1] = ds;
     }
   }
@@ -429,6 +434,16 @@ extern "C" int mclip_contrastive_loss(const mclip_loss_args* a, void* stream_) {
   p.gpart = (float*)ws;    ws += (size_t)p.P * 2 * p.nJ64 * p.B * p.D * 4;
   p.spart = (float*)ws;
   p.out = a->out;
+  p.status = a->status;
+  {
+    double secs = a->peer_timeout_s;
+    if (secs <= 0.0) { const char* e = getenv("MCLIP_PEER_TIMEOUT_S"); secs = e ? atof(e) : 600.0; }
+    if (secs <= 0.0) secs = 600.0;
+    int khz = 0, dev = 0;
+    cudaGetDevice(&dev);
+    if (cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, dev) != cudaSuccess || khz <= 0) khz = 2000000;
+    p.timeout_cycles = (long long)(secs * (double)khz * 1e3);
+  }
   void* kargs[] = {(void*)&p};
   MCLIP_CHECK_CUDA(cudaLaunchCooperativeKernel((void*)mclip_loss_kernel, dim3(grid), dim3(LOSS_THREADS), kargs, 0, stream));
   return MCLIP_OK;

@@ -27,7 +27,8 @@ class _FusedInfoNCE(torch.autograd.Function):
     @staticmethod
     def backward(ctx, dloss, _dout):
         gs = [(g * dloss).to(dt) for g, dt in zip(ctx.grads, ctx.dtypes)]
-        return (None, None, (ctx.dscale * dloss).reshape(ctx.scale_shape), *gs)
+        dscale = (ctx.dscale * dloss).reshape(ctx.scale_shape) if ctx.needs_input_grad[2] else None
+        return (None, None, dscale, *gs)
 
 
 class _FusedLossBase(nn.Module):
@@ -50,6 +51,10 @@ class _FusedLossBase(nn.Module):
     def _run(self, pairs, logit_scale, embeds):
         if not torch.is_tensor(logit_scale):
             logit_scale = torch.tensor(float(logit_scale), device=embeds[0].device)
+        elif logit_scale.device != embeds[0].device:
+            # model config without `temperature`: clip.py keeps logit_scale as a CPU 0-dim constant, like the reference (:39-41),
+            # whose `logit_scale * emb` accepts it; it carries no gradient
+            logit_scale = logit_scale.detach().to(embeds[0].device)
         loss, comps = _FusedInfoNCE.apply(self, pairs, logit_scale, *embeds)
         self.last_components = comps
         return loss

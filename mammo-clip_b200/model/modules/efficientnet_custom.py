@@ -204,7 +204,11 @@ def _forward(net, images, training, drop_rowscales, dropout_mult, want_raw):
     wc = net._weights()
     wc.refresh()
     S = {"images": images, "training": training, "blocks": []}
-    y, st, patches = ops.stem_forward(images, net._conv_stem.weight, geom.stem_pads, want_stats=training, w_bf16=wc.bf16[("s",)], return_patches=True)
+    lut = None
+    if images.dtype == torch.uint8:           # input edge: raw grey levels, per-image min-max + mean/std applied on load
+        _, lut = ops.image_norm_lut_u8(images, net.input_mean, net.input_std)
+    y, st, patches = ops.stem_forward(images, net._conv_stem.weight, geom.stem_pads, want_stats=training, w_bf16=wc.bf16[("s",)], return_patches=True,
+                                      norm_lut=lut)
     S["patches"] = patches
     h, w = y.shape[1], y.shape[2]
     bn = _bn_fin(st, n * h * w, net._bn0, training)
@@ -329,8 +333,15 @@ def _backward(net, S, dfeat, direct=False):
     grads["_conv_head.weight"] = gh
     dx = ops.gemm_tn(dyh2, wc.bf16_t[("h",)]).view(x_last.shape)
     del dyh, dyh2
+    # data parallel: finished gradient ranges are all-reduced on a side stream while the backward goes on (optim.FlatAdamW)
+    opt = getattr(net, "_flat_optimizer", None) if direct else None
+    early = opt is not None and opt.single_use(net)
+    if early:
+        opt.reduce_params([net._conv_head.weight, net._bn1.weight, net._bn1.bias])
     for i in reversed(range(len(net._blocks))):
         dx = _block_backward(net, i, S["blocks"][i], dx, n, training, grads, G, S)
+        if early:
+            opt.reduce_params(list(net._blocks[i].parameters()))
     if S.get("stem_materialised"):
         ys, bns = S["stem"]
         nn_, hs, ws, cs = ys.shape
@@ -338,6 +349,8 @@ def _backward(net, S, dfeat, direct=False):
         dws = G(net._conv_stem.weight)
         ops.stem_wgrad(S["images"], dys.view(nn_, hs, ws, cs), geom.stem_pads, dws, patches=S["patches"])
         grads["_conv_stem.weight"] = dws
+    if early:
+        opt.reduce_params([net._conv_stem.weight, net._bn0.weight, net._bn0.bias], flush=True)
     return grads
 
 
@@ -385,6 +398,9 @@ class EfficientNet(nn.Module):
         self.out_dim = g.head_out
         self.stochastic = stochastic      # False: drop-connect / dropout off in train mode (parity runs)
         self._wcache = None
+        # input edge: a [B,1,H,W] uint8 batch is normalised on load like datasets/imagetext.py:129-134 with the
+        # mean / std of the shipped configs (configs/pre_train_b5_clip.yaml:23-24)
+        self.input_mean, self.input_std = 0.3089279, 0.25053555408335154
 
     @classmethod
     def from_name(cls, model_name, in_channels=3, **override_params):
@@ -392,14 +408,58 @@ class EfficientNet(nn.Module):
             raise ValueError("the B200 stem kernel is specialised for 3 input channels")
         return cls(model_name)
 
+    # file names of the ImageNet checkpoints the reference downloads (efficient_net_custom_utils.py:556-579), as torch.hub caches them
+    _PRETRAINED = {"efficientnet-b0": "efficientnet-b0-355c32eb.pth", "efficientnet-b1": "efficientnet-b1-f1951068.pth",
+                   "efficientnet-b2": "efficientnet-b2-8bb594d6.pth", "efficientnet-b3": "efficientnet-b3-5fb5a3c3.pth",
+                   "efficientnet-b4": "efficientnet-b4-6ed6700e.pth", "efficientnet-b5": "efficientnet-b5-b6417697.pth",
+                   "efficientnet-b6": "efficientnet-b6-c76e70fd.pth", "efficientnet-b7": "efficientnet-b7-dcc49843.pth"}
+
+    @classmethod
+    def _find_pretrained(cls, model_name, weights_path, advprop):
+        """weights_path argument > $MCLIP_EFFICIENTNET_WEIGHTS (file, or directory holding the reference's file names) > the
+        torch.hub checkpoint cache the reference itself fills (model_zoo.load_url, efficient_net_custom_utils.py:602)."""
+        import os
+        if isinstance(weights_path, str):
+            return weights_path
+        fname = ("adv-" if advprop else "") + cls._PRETRAINED[model_name]
+        cands = []
+        env = os.environ.get("MCLIP_EFFICIENTNET_WEIGHTS")
+        if env:
+            cands += [env] if os.path.isfile(env) else [os.path.join(env, fname)]
+        try:
+            cands.append(os.path.join(torch.hub.get_dir(), "checkpoints", fname))
+        except Exception:
+            pass
+        if not advprop:
+            return next((c for c in cands if os.path.isfile(c)), None)
+        import glob        # advprop checkpoints carry other hashes: match by prefix
+        for c in cands:
+            hit = glob.glob(os.path.join(os.path.dirname(c), f"adv-{model_name}-*.pth"))
+            if hit:
+                return hit[0]
+        return None
+
     @classmethod
     def from_pretrained(cls, model_name, weights_path=None, advprop=False, in_channels=3, num_classes=1000, **override_params):
-        """Reference :340-373 downloads ImageNet weights; offline, only a local `weights_path` state dict is honoured."""
+        """Reference :340-373 loads ImageNet weights (downloaded on first use).  There is no network here: the checkpoint is
+        taken from `weights_path`, $MCLIP_EFFICIENTNET_WEIGHTS or the torch.hub cache; if none exists the tower keeps its
+        random initialisation and says so LOUDLY (training results differ from the reference's in that case)."""
         model = cls.from_name(model_name, in_channels=in_channels)
-        if isinstance(weights_path, str):
-            sd = torch.load(weights_path, map_location="cpu")
+        path = cls._find_pretrained(model_name, weights_path, advprop)
+        if path is not None:
+            sd = torch.load(path, map_location="cpu")
             sd = {k: v for k, v in sd.items() if not k.startswith("_fc.")}
-            model.load_state_dict(sd, strict=False)
+            ret = model.load_state_dict(sd, strict=False)
+            assert not ret.unexpected_keys, f"unexpected keys in {path}: {ret.unexpected_keys[:5]}"
+            assert not ret.missing_keys, f"missing keys in {path}: {ret.missing_keys[:5]}"
+        else:
+            import logging
+            import warnings
+            msg = (f"[mammoclip_b200] no ImageNet checkpoint found for {model_name}: the image tower starts from RANDOM weights, unlike "
+                   f"the reference's EfficientNet.from_pretrained (efficientnet_custom.py:340-373).  Provide image_encoder.weights_path, "
+                   f"set MCLIP_EFFICIENTNET_WEIGHTS, or place {cls._PRETRAINED[model_name]} in the torch.hub checkpoint cache.")
+            warnings.warn(msg, stacklevel=2)
+            logging.getLogger(__name__).warning(msg)
         return model
 
     def _weights(self):
@@ -429,7 +489,17 @@ class EfficientNet(nn.Module):
         images = inputs["image"] if as_dict else inputs
         if not images.is_cuda:
             raise RuntimeError("mammoclip_b200.EfficientNet runs on a B200 only (no CPU fallback)")
-        images = images.float()
+        if images.dim() != 4 or images.shape[1] not in (1, 3):
+            raise ValueError(f"expected images [B,3,H,W] (or the single-channel input edge [B,1,H,W]), got {tuple(images.shape)}")
+        if images.shape[1] == 3:
+            images = images.float()           # the reference trainer's tensor (trainer_ddp.py:288-291)
+        elif images.dtype not in (torch.float32, torch.float16, torch.bfloat16, torch.uint8):
+            images = images.float()
+        elif images.dtype == torch.uint8:
+            images = images.contiguous()
+        ops._require_cuda(images)
+        if getattr(self, "_flat_optimizer", None) is not None:
+            self._flat_optimizer.note_forward(self)
         scales, mult = self._stochastic_inputs(images.shape[0], images.device)
         params = [p for _, p in self.named_parameters()]
         out = _EncoderFn.apply(self, images, scales, mult, as_dict, *params)

@@ -8,9 +8,19 @@ from ._lib import GemmArgs, LossArgs, WgradArgs, call, check, lib, ptr, stream_p
 
 
 def _require_cuda(*tensors):
+    """Tensors must live on the CURRENT CUDA device: kernels launch on that device's current stream (a model moved
+    to cuda:1 without torch.cuda.set_device(1) would otherwise launch on device 0 with device-1 pointers)."""
+    cur = None
     for t in tensors:
-        if t is not None and not t.is_cuda:
+        if t is None:
+            continue
+        if not t.is_cuda:
             raise _lib.MclipError("mammoclip_b200 kernels need CUDA tensors on a B200; there is no CPU fallback")
+        if cur is None:
+            cur = torch.cuda.current_device()
+        if t.device.index != cur:
+            raise _lib.MclipError(f"tensor on cuda:{t.device.index} but the current device is cuda:{cur}: call torch.cuda.set_device({t.device.index}) "
+                                  "(kernels launch on the current device's stream)")
 
 
 # ------------------------------------------------------------------------------------------------ GEMMs
@@ -84,6 +94,23 @@ def gemm_wgrad(a, b, out=None, accumulate=False):
 # ------------------------------------------------------------------------------------------------ loss
 
 _loss_ws = {}
+_loss_status = {}     # device index -> (device int32 status word, pinned host mirror)
+
+
+def _loss_status_words(dev):
+    """Status word of the fused loss kernel (peer time-out) and its pinned host mirror.  The mirror is refreshed by an async
+    copy after every call and inspected before the next one: a rank whose peer never arrived raises here instead of the
+    kernel trapping the CUDA context."""
+    st = _loss_status.get(dev.index)
+    if st is None:
+        st = (torch.zeros(1, dtype=torch.int32, device=dev), torch.zeros(1, dtype=torch.int32).pin_memory())
+        _loss_status[dev.index] = st
+    code = int(st[1][0])
+    if code != 0:
+        st[0].zero_(); st[1].zero_()
+        raise _lib.MclipError(f"fused contrastive loss: the embeddings of rank {code - 1} never arrived (MCLIP_PEER_TIMEOUT_S); "
+                              "the loss of that step is NaN")
+    return st
 
 
 def contrastive_loss_raw(local, pairs, scale, world=1, rank=0, symm=None):
@@ -119,7 +146,11 @@ def contrastive_loss_raw(local, pairs, scale, world=1, rank=0, symm=None):
     args.out = out.data_ptr()
     if world > 1:
         symm.fill_args(args, K)
+        st_dev, st_host = _loss_status_words(dev)
+        args.status = st_dev.data_ptr()
     call("mclip_contrastive_loss", C.byref(args))
+    if world > 1:
+        st_host.copy_(st_dev, non_blocking=True)
     return out, grads
 
 
@@ -157,11 +188,28 @@ def bn_finalize(partials, count, gamma, beta, running_mean, running_var, num_bat
     return st
 
 
-def stem_im2col(images, pads):
-    """images: [N,3,H,W] fp32 (any strides) -> (patches [N*Ho*Wo, 32] bf16, Ho, Wo); taps t = ci*9 + ky*3 + kx, zero padded."""
+_STEM_DTYPES = {torch.float32: 0, torch.float16: 1, torch.bfloat16: 2, torch.uint8: 3}
+
+
+def image_norm_lut_u8(images, mean, std):
+    """uint8 [N,1,H,W] (contiguous) -> (fp32 [N,2] per-image (min, max - min), bf16 [N,256] normalisation table):
+    lut[n,u] = bf16(((u - min) / (max - min) - mean) / std), the fp32 arithmetic of datasets/imagetext.py:129-134 per grey level."""
+    _require_cuda(images)
+    assert images.dtype == torch.uint8 and images.is_contiguous()
+    n = images.shape[0]
+    mm = torch.empty((n, 2), dtype=torch.float32, device=images.device)
+    lut = torch.empty((n, 256), dtype=torch.bfloat16, device=images.device)
+    call("mclip_image_norm_lut_u8", ptr(images), n, C.c_longlong(images[0].numel()), C.c_float(mean), C.c_float(std), ptr(mm), ptr(lut))
+    return mm, lut
+
+
+def stem_im2col(images, pads, norm_lut=None):
+    """images: [N,3,H,W] fp32 (any strides), or the input edge [N,1,H,W] fp32/fp16/bf16/uint8 (one grey channel, written to
+    the three tap groups: bit-identical to three identical channels) -> (patches [N*Ho*Wo, 32] bf16, Ho, Wo);
+    taps t = ci*9 + ky*3 + kx, zero padded.  norm_lut (bf16 [N,256] from image_norm_lut_u8) applies imagetext.py:129-134 on load."""
     _require_cuda(images)
     n, ci, h, w = images.shape
-    assert ci == 3 and images.dtype == torch.float32
+    assert (ci == 3 and images.dtype == torch.float32) or (ci == 1 and images.dtype in _STEM_DTYPES), (ci, images.dtype)
     pl, pr, pt, pb = pads
     ho, wo = (h + pt + pb - 3) // 2 + 1, (w + pl + pr - 3) // 2 + 1
     out = torch.empty((n * ho * wo, 32), dtype=torch.bfloat16, device=images.device)
@@ -171,7 +219,11 @@ def stem_im2col(images, pads):
     a.in_ = images.data_ptr()
     a.stride_n, a.stride_c, a.stride_h, a.stride_w = images.stride()
     a.out = out.data_ptr()
-    call("mclip_stem_im2col", C.byref(a), nbytes=4 * images.numel() + 2 * out.numel())
+    a.in_channels, a.in_dtype = ci, _STEM_DTYPES[images.dtype]
+    if norm_lut is not None:
+        assert images.dtype == torch.uint8 and norm_lut.shape == (n, 256) and norm_lut.dtype == torch.bfloat16 and norm_lut.is_contiguous()
+        a.norm_lut = norm_lut.data_ptr()
+    call("mclip_stem_im2col", C.byref(a), nbytes=images.element_size() * images.numel() + 2 * out.numel())
     return out, ho, wo
 
 
@@ -184,9 +236,9 @@ def stem_weight_bf16(weight):
     return w
 
 
-def stem_forward(images, weight, pads, want_stats=True, w_bf16=None, return_patches=False):
+def stem_forward(images, weight, pads, want_stats=True, w_bf16=None, return_patches=False, norm_lut=None):
     """Stem conv = im2col + tcgen05 GEMM.  -> (Y [N,Ho,Wo,C] bf16, stats) (+ patches for the weight gradient)."""
-    patches, ho, wo = stem_im2col(images, pads)
+    patches, ho, wo = stem_im2col(images, pads, norm_lut=norm_lut)
     wb = w_bf16 if w_bf16 is not None else stem_weight_bf16(weight)
     y, stats = gemm_tn(patches, wb, want_stats=bool(want_stats))
     y = y.view(images.shape[0], ho, wo, weight.shape[0])

@@ -106,6 +106,42 @@ def test_stem(n, h, w, c, pads, nhwc):
     assert rel_err(dwt, wref.grad) < 2e-3
 
 
+def test_stem_input_edge_single_channel_and_uint8_are_bit_identical():
+    """the data pipeline's image is ONE grey channel replicated three times (datasets/imagetext.py:121) and
+    normalised per image on the CPU (:129-134).  The single-channel fp32 input and the raw uint8 input (normalised on load in
+    the reference's fp32 operation order) must reproduce the 3-identical-channel fp32 path bit for bit: patches, stem output,
+    BN partials and the stem weight gradient."""
+    from mammoclip_b200 import ops
+    n, h, w, c, pads = 3, 70, 52, 48, (0, 1, 0, 1)
+    g = torch.Generator(device="cuda").manual_seed(11)
+    u8 = torch.randint(3, 250, (n, 1, h, w), generator=g, device="cuda", dtype=torch.uint8)
+    mean, std = 0.3089279, 0.25053555408335154
+    t = u8.float()
+    t = t - t.amin(dim=(1, 2, 3), keepdim=True)                 # image -= image.min()
+    t = t / t.amax(dim=(1, 2, 3), keepdim=True)                 # image /= image.max()
+    x1 = (t - mean) / std                                       # fp32, like numpy float32 with python-float scalars
+    x3 = x1.expand(n, 3, h, w)                                  # what convert('RGB') + the trainer's permute deliver
+    wt = _rand((c, 3, 3, 3), 6, 0.3, torch.float32)
+    dy = None
+    outs = []
+    mm, lut = ops.image_norm_lut_u8(u8, mean, std)
+    for img, kw in ((x3, {}), (x1, {}), (u8, dict(norm_lut=lut))):
+        y, stats, patches = ops.stem_forward(img, wt, pads, return_patches=True, **kw)
+        if dy is None:
+            dy = _rand(y.shape, 7)
+        dwt = torch.empty_like(wt)
+        ops.stem_wgrad(img, dy, pads, dwt, patches=patches)
+        outs.append((patches, y, stats, dwt))
+    for other in outs[1:]:
+        for a, b in zip(outs[0], other):
+            assert torch.equal(a, b)
+    assert torch.equal(mm[:, 0], u8.float().amin(dim=(1, 2, 3))) and torch.equal(mm[:, 1], (u8.float().amax(dim=(1, 2, 3)) - u8.float().amin(dim=(1, 2, 3))))
+    # fp16 single channel: same kernel path, values rounded to fp16 by the producer
+    y16, _ = ops.stem_forward(x1.half(), wt, pads)
+    y32, _ = ops.stem_forward(x1.half().float(), wt, pads)
+    assert torch.equal(y16, y32)
+
+
 @pytest.fixture(params=[0, 15], ids=["regs", "cp_async_ring"])
 def ew_async(request):
     """Both staging variants of the streaming passes (registers / per-thread cp.async ring)."""

@@ -320,7 +320,7 @@ def test_dwconv_k3s2_over_2g_elements():
     st = stats.double().sum(0)
     assert rel_err(st[0], s0) < 1e-4 and rel_err(st[1], s1) < 1e-4
     p = bnp.double().sum(0)
-    assert rel_err(p[0], p0) < 1e-3 and rel_err(p[1], p1) < 1e-3
+    assert rel_err(p[0], p0) < 5e-3 and rel_err(p[1], p1) < 5e-3       # sums of the fp32 gradient vs sums of the stored bf16 values
 
 
 def test_streaming_passes_over_2g_elements():
