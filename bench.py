@@ -427,10 +427,14 @@ def run_ours(args):
     if parity is not None and not parity < 1e-3:
         raise SystemExit(f"fused P2P loss disagrees with all_gather/reduce_scatter: worst rel err {parity}")
 
-    enc_cfg, enc_name, layers, batch, h, w, L = WORKLOADS[args.workload]
+    mvs = args.workload.endswith("-mvs")               # the shipped YAML's loss (configs/pre_train_b5_clip.yaml:11): 2 image views + 2 texts per pair
+    wl = args.workload[:-4] if mvs else args.workload
+    enc_cfg, enc_name, layers, batch, h, w, L = WORKLOADS[wl]
     if args.batch:
         batch = args.batch
     cfg, loss_cfg = _model_cfg(enc_cfg, layers)
+    if mvs:
+        loss_cfg = {"breast_clip": {"label_smoothing": 0.0, "i2i_weight": 1.0, "t2t_weight": 0.5, "loss_ratio": 1.0}}
 
     class Tok:
         vocab_size = 28996
@@ -442,6 +446,13 @@ def run_ours(args):
     img_h, tok_h = _synth_host(batch, h, w, L, rank)
     img_d = img_h.to(dev, non_blocking=True).permute(0, 3, 1, 2)
     tok_d = BatchEncoding({k: v.to(dev, non_blocking=True) for k, v in tok_h.items()})
+    extra_d = {}
+    if mvs:                                            # second view / second text of every pair (device resident; the e2e leg copies the first view only)
+        img2_h, tok2_h = _synth_host(batch, h, w, L, rank + 100)
+        g82 = torch.Generator().manual_seed(8765 + rank)
+        extra_d = {"image_views": torch.randint(0, 256, (batch, 1, h, w), generator=g82, dtype=torch.uint8).to(dev),
+                   "text_tokens2": BatchEncoding({k: v.to(dev) for k, v in tok2_h.items()})}
+        del img2_h
     # end-to-end leg = the input edge: the loader's grey-level image as ONE uint8 channel in pinned host memory;
     # per-image min-max + mean/std normalisation and the 1 -> 3 channel replication happen inside the stem's im2col kernel
     # (bit-identical to the reference-shaped 3 x fp32 tensor, tests/test_gpu_conv.py).  --e2e-fp32 times the old 3 x fp32 copy.
@@ -454,7 +465,7 @@ def run_ours(args):
 
     def step(images, tokens):
         opt.zero_grad()
-        out = model({"images": images, "text_tokens": tokens}, dev)
+        out = model(dict({"images": images, "text_tokens": tokens}, **extra_d), dev)
         loss = loss_fn(**out, is_train=True)["total"]
         loss.backward()                                  # finished gradient buckets are all-reduced on a side stream meanwhile
         if world > 1 and ar_events is not None:
@@ -557,12 +568,16 @@ def run_ours(args):
     value = pairs / (ms_step * 1e-3)
     hbm_peak, tf_peak, peak_src = _peaks()
     achieved = (dom[2] / 1e9) / (dom[1] * 1e-3) if dom[1] > 0 else 0.0
-    bytes_pair, flops_pair = ALGO[args.workload]
+    bytes_pair, flops_pair = ALGO[wl]
+    if mvs:
+        bytes_pair, flops_pair = 2 * bytes_pair, 2 * flops_pair      # two image views per pair (recompute traffic is not credited)
     line = {
         "metric": "image-text pairs/sec", "value": value, "unit": "pairs/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
         "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
         "config": {"workload": f"{args.workload}: {enc_name} + BERT-{layers}L (random init), batch {batch}/GPU, {h}x{w} 3-ch fp32 images, {L}-token text, "
-                               f"single-view InfoNCE, fwd+loss+bwd+grad-allreduce+AdamW, train mode (drop-connect/dropout on)",
+                               + ("multi-view loss (breast_clip.py: 2 image views + 2 texts per pair, 6 pair terms; second view uint8 single-channel), "
+                                  f"memory plan {getattr(model.image_encoder, 'last_plan', 'auto')}, " if mvs else "single-view InfoNCE, ")
+                               + "fwd+loss+bwd+grad-allreduce+AdamW, train mode (drop-connect/dropout on)",
                    "e2e_input": "3 x fp32 [B,3,H,W] pinned host images" if args.e2e_fp32 else
                                 "input edge: 1 x uint8 [B,1,H,W] pinned host images, normalised + replicated to 3 channels inside the stem kernel",
                    "l2": "inputs larger than L2 (images %.0f MB/step, activations GBs); no explicit flush" % (img_h.numel() * 4 / 1e6),
@@ -575,7 +590,7 @@ def run_ours(args):
         "grad_allreduce": None if world == 1 else {"collective": "ncclAllReduce(sum) over fp32 gradient buckets on a side stream, overlapped with the backward",
                                                    "calls_per_step": ar_stats[0], "bytes_per_step": ar_stats[1], "exposed_ms_per_step": round(ar_exposed_ms, 3)},
         "roofline": {"bound": "hbm", "kernel": dominant, "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
-                     "traffic": (_traffic(dominant) or {}).get("bytes_per_launch") if args.workload == "c3" else None,
+                     "traffic": (_traffic(dominant) or {}).get("bytes_per_launch") if wl == "c3" else None,
                      "traffic_note": (_traffic(dominant) or {}).get("note"),
                      "algorithmic_bytes_per_launch": dom[2] / max(dom[0], 1), "launches": dom[0], "avg_launch_ms": dom[1] / max(dom[0], 1), "peak_source": peak_src,
                      "step_share_ms": share,
@@ -586,8 +601,8 @@ def run_ours(args):
                                     "tensor_tflops": value / world * flops_pair / 1e12, "frac_of_bf16": value / world * flops_pair / 1e12 / tf_peak}},
     }
     if world == 1 and not args.no_cpu:
-        sample = 1 if args.workload == "c3" else 2 if args.workload == "c2" else 4
-        line["cpu_baseline"], _ = cpu_reference_run(args.workload, 2 if args.workload == "c3" else 3, 1, sample)
+        sample = 1 if wl == "c3" else 2 if wl == "c2" else 4
+        line["cpu_baseline"], _ = cpu_reference_run(wl, 2 if wl == "c3" else 3, 1, sample)
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

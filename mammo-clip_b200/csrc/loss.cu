@@ -439,9 +439,12 @@ extern "C" int mclip_contrastive_loss(const mclip_loss_args* a, void* stream_) {
     double secs = a->peer_timeout_s;
     if (secs <= 0.0) { const char* e = getenv("MCLIP_PEER_TIMEOUT_S"); secs = e ? atof(e) : 600.0; }
     if (secs <= 0.0) secs = 600.0;
-    int khz = 0, dev = 0;
-    cudaGetDevice(&dev);
-    if (cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, dev) != cudaSuccess || khz <= 0) khz = 2000000;
+    static int khz = 0;                              // cudaDevAttrClockRate is a slow driver query (~1 ms): once per process
+    if (khz == 0) {
+        int dev = 0, v = 0;
+        cudaGetDevice(&dev);
+        khz = (cudaDeviceGetAttribute(&v, cudaDevAttrClockRate, dev) == cudaSuccess && v > 0) ? v : 2000000;
+    }
     p.timeout_cycles = (long long)(secs * (double)khz * 1e3);
   }
   void* kargs[] = {(void*)&p};

@@ -84,7 +84,14 @@ class BreastClip(nn.Module):
 
     def forward(self, batch, device=None):
         device = batch["images"].device if device is None else device
-        image_features_g = self.encode_image(batch["images"].to(device))
+        mvs = "text_tokens2" in batch and "image_views" in batch
+        image_view_encode = None
+        if mvs and hasattr(self.image_encoder, "forward_views") and self.model_config["image_encoder"]["model_type"].lower() == "cnn":
+            # two image batches in one step: let the tower choose its memory plan (both views' state resident, or recompute)
+            image_features_g, image_view_encode = self.image_encoder.forward_views([batch["images"].to(device), batch["image_views"].to(device)],
+                                                                                   plan=getattr(self, "mvs_memory_plan", "auto"))
+        else:
+            image_features_g = self.encode_image(batch["images"].to(device))
         text_features_g = self.encode_text(batch["text_tokens"].to(device))
         image_embeddings = self._embed(image_features_g, self.image_projection if self.projection else None)
         text_embeddings = self._embed(text_features_g, self.text_projection if self.projection else None)
@@ -96,6 +103,7 @@ class BreastClip(nn.Module):
             # clip.py:105 falls back to text_features_g (the FIRST text) without a projection head; kept as is
             out["text_embeddings2"] = self._embed(text_features_g2 if self.projection else text_features_g,
                                                   self.text_projection if self.projection else None)
-            image_view_encode = self.encode_image(batch["image_views"].to(device))
+            if image_view_encode is None:
+                image_view_encode = self.encode_image(batch["image_views"].to(device))
             out["image_view_embeddings"] = self._embed(image_view_encode, self.image_projection if self.projection else None)
         return out

@@ -209,7 +209,7 @@ class _BertFn(torch.autograd.Function):
         ctx.saved = None
         if direct:
             owner._direct_written_at = opt.zero_count
-            if opt.single_use(owner):            # data parallel: the text tower's gradients are final, reduce them while the image tower's backward runs
+            if hasattr(opt, "single_use") and opt.single_use(owner):            # data parallel: the text tower's gradients are final, reduce them while the image tower's backward runs
                 opt.reduce_params(trainable, flush=True)
             return (None,) * (7 + len(list(bert.parameters())))
         return (None, None, None, None, None, None, None, *[grads.get(id(p)) for p in bert.parameters()])
@@ -239,6 +239,6 @@ def bert_forward(bert, input_ids, token_type_ids, attention_mask, training, owne
     params = list(bert.parameters())
     need_grad = torch.is_grad_enabled() and any(p.requires_grad for p in params)
     opt = getattr(owner, "_flat_optimizer", None) if owner is not None else None
-    if opt is not None and need_grad:
+    if opt is not None and need_grad and hasattr(opt, "note_forward"):
         opt.note_forward(owner)
     return _BertFn.apply(owner, bert, ids, tts, amask, masks, need_grad, *params)

@@ -126,7 +126,12 @@ class MBConvBlock(nn.Module):
 
 
 # ----------------------------------------------------------------------------------------------- the engine
+_UPDATE_RUNNING = [True]      # False during the recompute pass of the multi-view memory plan (the statistics were already folded in)
+
+
 def _bn_fin(part, count, bn: _BNParams, training):
+    if training and not _UPDATE_RUNNING[0]:
+        return ops.bn_finalize(part, count, bn.weight, bn.bias, bn.running_mean, bn.running_var, None, training, 0.0, bn.eps)
     return ops.bn_finalize(part, count, bn.weight, bn.bias, bn.running_mean, bn.running_var, bn.num_batches_tracked, training, bn.momentum, bn.eps)
 
 
@@ -197,8 +202,9 @@ def _block_forward(net, i, x, pending, n, h, w, training, rowscale=None):
     return x_out.view(n, ho, wo, g.cout), B
 
 
-def _forward(net, images, training, drop_rowscales, dropout_mult, want_raw):
-    """Returns (features [N,Chead] fp32, saved state for backward, raw head activation or None)."""
+def _forward(net, images, training, drop_rowscales, dropout_mult, want_raw, save=True):
+    """Returns (features [N,Chead] fp32, saved state for backward, raw head activation or None).  save=False keeps nothing
+    for a backward pass (every intermediate is freed as soon as its consumer has run)."""
     geom = net.geom
     n, _, h_in, w_in = images.shape
     wc = net._weights()
@@ -222,14 +228,22 @@ def _forward(net, images, training, drop_rowscales, dropout_mult, want_raw):
             x, pending = x.view(n, h, w, -1), None
             S["stem_materialised"] = True
         x, B = _block_forward(net, i, x, pending, n, h, w, training, drop_rowscales.get(i) if drop_rowscales else None)
-        S["blocks"].append(B)
         h, w, pending = B["ho"], B["wo"], None
+        if save:
+            S["blocks"].append(B)
+        else:
+            if i == 0:
+                S.pop("stem", None); S.pop("patches", None)
+            del B
     yh, st = ops.gemm_tn(x.view(n * h * w, x.shape[-1]), wc.bf16[("h",)], want_stats=training)
     yh = yh.view(n, h * w, geom.head_out)
     bnh = _bn_fin(st, n * h * w, net._bn1, training)
     raw, pool = ops.ew_forward(yh, bn=bnh, act=1, write=want_raw, pool=True)
     feat = ops.pool_finalize(pool, h * w, dropout_mult)
-    S.update(x_last=x, yh=yh, bnh=bnh, h=h, w=w, dropout_mult=dropout_mult)
+    if save:
+        S.update(x_last=x, yh=yh, bnh=bnh, h=h, w=w, dropout_mult=dropout_mult)
+    else:
+        S = None
     if want_raw:
         raw = raw.view(n, h, w, geom.head_out).permute(0, 3, 1, 2).float()
     return feat, S, raw
@@ -379,6 +393,45 @@ class _EncoderFn(torch.autograd.Function):
         return (None, None, None, None, None, *out)
 
 
+class _MultiViewFn(torch.autograd.Function):
+    """Memory plan for the multi-view loss (loss/breast_clip.py: two image views per step, clip.py:103-112) at the metric
+    scale: the saved pre-BN tensors of ONE EN-B5 view at B = 64, 1520x912 are 91.5 GB, two do not fit 180 GB.  The forward
+    runs every view WITHOUT keeping anything (features only); the backward re-runs one view at a time with saving (same
+    drop-connect / dropout draws, batch statistics bit-identical, running statistics not updated again) and backpropagates
+    the feature gradient the loss delivered.  Peak = one view's state; cost = one extra forward per view."""
+
+    @staticmethod
+    def forward(ctx, net, views, draws, *params):
+        feats = []
+        for v, (scales, mult) in zip(views, draws):
+            f, _, _ = _forward(net, v, net.training, scales, mult, False, save=False)
+            feats.append(f)
+        ctx.net, ctx.views, ctx.draws, ctx.training = net, views, draws, net.training
+        return tuple(feats)
+
+    @staticmethod
+    def backward(ctx, *dfeats):
+        net = ctx.net
+        total = None
+        _UPDATE_RUNNING[0] = False
+        try:
+            for v, (scales, mult), d in zip(ctx.views, ctx.draws, dfeats):
+                if d is None:
+                    continue
+                _, S, _ = _forward(net, v, ctx.training, scales, mult, False, save=True)
+                g = _backward(net, S, d.contiguous().float(), direct=False)
+                del S
+                if total is None:
+                    total = g
+                else:
+                    for k, t in g.items():
+                        total[k].add_(t)
+        finally:
+            _UPDATE_RUNNING[0] = True
+        out = [None if total is None else total.get(name) for name, _ in net.named_parameters()]
+        return (None, None, None, *out)
+
+
 class EfficientNet(nn.Module):
     """Drop-in for the reference EfficientNet (efficientnet_custom.py:143).  `num_classes`, `include_top`, `advprop`,
     `weights_path` are accepted for signature compatibility; this copy has no `_fc` either (:211 is commented out)."""
@@ -484,9 +537,8 @@ class EfficientNet(nn.Module):
         mult = (torch.rand(n, self.out_dim, device=device) >= p).float() / (1.0 - p)
         return scales, mult
 
-    def forward(self, inputs):
-        as_dict = isinstance(inputs, dict) and "image" in inputs
-        images = inputs["image"] if as_dict else inputs
+    @staticmethod
+    def _prep(images):
         if not images.is_cuda:
             raise RuntimeError("mammoclip_b200.EfficientNet runs on a B200 only (no CPU fallback)")
         if images.dim() != 4 or images.shape[1] not in (1, 3):
@@ -498,12 +550,51 @@ class EfficientNet(nn.Module):
         elif images.dtype == torch.uint8:
             images = images.contiguous()
         ops._require_cuda(images)
+        return images
+
+    def forward(self, inputs):
+        as_dict = isinstance(inputs, dict) and "image" in inputs
+        images = self._prep(inputs["image"] if as_dict else inputs)
         if getattr(self, "_flat_optimizer", None) is not None:
             self._flat_optimizer.note_forward(self)
         scales, mult = self._stochastic_inputs(images.shape[0], images.device)
         params = [p for _, p in self.named_parameters()]
         out = _EncoderFn.apply(self, images, scales, mult, as_dict, *params)
         return out if as_dict else out
+
+    def saved_bytes(self, n, h, w):
+        """bf16 bytes of the pre-BN tensors one training forward keeps for its backward (the memory plan's unit)."""
+        g = self.geom
+        pl, pr, pt, pb = g.stem_pads
+        h, w = (h + pt + pb - 3) // 2 + 1, (w + pl + pr - 3) // 2 + 1
+        elems = h * w * (g.stem_out + 32)                     # stem output + im2col patches
+        for b in g.blocks:
+            l, r, t, bb = b.pads
+            ho, wo = (h + t + bb - b.k) // b.s + 1, (w + l + r - b.k) // b.s + 1
+            elems += (h * w * b.cexp if b.expand else 0) + ho * wo * (b.cexp + 2 * b.cout)
+            h, w = ho, wo
+        elems += h * w * g.head_out
+        return 2 * n * elems
+
+    def forward_views(self, views, plan="auto"):
+        """Features of several image batches of ONE step (multi-view loss).  plan: "keep" = ordinary forwards (every view's
+        state stays resident), "recompute" = _MultiViewFn, "auto" = recompute iff the kept state would not fit the free HBM."""
+        views = [self._prep(v) for v in views]
+        if plan == "auto":
+            need = sum(self.saved_bytes(v.shape[0], v.shape[2], v.shape[3]) for v in views) if (self.training and torch.is_grad_enabled()) else 0
+            free = torch.cuda.mem_get_info(views[0].device)[0] + torch.cuda.memory_reserved(views[0].device) - torch.cuda.memory_allocated(views[0].device)
+            plan = "recompute" if need + (40 << 30) > free else "keep"
+        object.__setattr__(self, "last_plan", plan)
+        if plan == "keep" or not (self.training and torch.is_grad_enabled()):
+            return [self.forward(v) for v in views]
+        opt = getattr(self, "_flat_optimizer", None)
+        draws = []
+        for v in views:
+            if opt is not None:
+                opt.note_forward(self)
+            draws.append(self._stochastic_inputs(v.shape[0], v.device))
+        params = [p for _, p in self.named_parameters()]
+        return list(_MultiViewFn.apply(self, views, draws, *params))
 
     def extract_features(self, inputs):
         return self.forward({"image": inputs})[1]

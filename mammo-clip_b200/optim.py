@@ -28,6 +28,9 @@ class FlatAdamW(torch.optim.Optimizer):
         self.zero_count = 0
         self._works, self._reduced, self._comm, self._bucket, self._bucket_bytes = [], set(), None, [], 0
         self.bucket_bytes = 32 << 20
+        # MCLIP_AR_OVERLAP=0: reduce everything after the backward (one ncclAllReduce); 1: overlapped buckets (default)
+        import os
+        self.overlap = os.environ.get("MCLIP_AR_OVERLAP", "1") != "0"
         self._nbytes, self.comm_stats = 0, (0, 0)   # (all-reduce calls, bytes) of the last step, for bench.py
 
     # ------------------------------------------------------------------------------------------------ layout
@@ -154,6 +157,10 @@ class FlatAdamW(torch.optim.Optimizer):
         adjacent in the flat buffer (a tower hands over its blocks in backward order)."""
         if not (dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1):
             return
+        if not self.overlap and not flush:
+            return
+        if not self.overlap:
+            params = []
         if not self._works and not self._bucket:
             self._nbytes = 0
         params = [p for p in params if id(p) in self.offsets and id(p) not in self._reduced]
