@@ -86,6 +86,10 @@ typedef struct mclip_gemm_args {
   const void* dropmask; float drop_scale;         /* uint8 keep-mask [batches*m, n] applied before the residual, or NULL */
   void* aux_pre; long long ld_aux;                /* NULL, or bf16 [batches*m, ld_aux]: the value BEFORE `act` (after the bias), kept for the
                                                      activation's backward (BertIntermediate's GELU) */
+  /* ABI 4: optional SECOND A operand concatenated along K: A = [a (k columns) | a2 (k2 columns)], same rows / batches.
+   * b then holds [n, ceil64(k) + k2] with zeros in columns [k, ceil64(k)).  Used by the folded BatchNorm backward of the
+   * expand convolution: dX = [dV0 | X] [diag(a)We ; G] (efficientnet_custom.py:105-106 autograd). */
+  const void* a2; long long lda2, a2_batch_stride; int k2;
 } mclip_gemm_args;
 int mclip_gemm_tn_stat_slots(int m, int n, int batches);
 int mclip_gemm_tn(const mclip_gemm_args* args, void* stream);
@@ -156,6 +160,28 @@ int mclip_stem_im2col(const mclip_stem_args* args, void* stream);
 /* uint8 [n, hw] image batch -> per-image {min, max - min} as fp32 [n][2] (imagetext.py:130-131) and the normalisation table
  * lut[n][u] = bf16(((u - min) / (max - min) - mean) / std) in the reference's fp32 operation order (IEEE division). */
 int mclip_image_norm_lut_u8(const void* in, int n, long long hw, float mean, float std, float* minmax, void* lut, void* stream);
+
+/* ---- folded BatchNorm backward of the expand convolution (ABI 4) ---------------------------------------------------
+ * Autograd of MBConvBlock's `_bn0(_expand_conv(x))` (efficientnet_custom.py:105-106) normally applies
+ *   dY0 = a (dV0 - c1 - yhat c2),  a = gamma*invstd, c1 = mean(dV0), c2 = mean(dV0*yhat)
+ * in a pass over the 6x-wide tensor and then runs dX = dY0 We and dWe = dY0^T X.  Both consumers are LINEAR in dY0 and
+ * Y0 = X We^T, so the correction folds into the operands (T = diag(t), t = -a c2 invstd, xbar = mean of X):
+ *   dX  = [dV0 | X] [diag(a) We ; G] + bias,   G = We^T T We,   bias = -(a c1)^T We - xbar G
+ *   dWe = diag(a) (dV0^T X - c1 (sum X)^T) + T We (X^T X - (sum X)(sum X)^T / count)
+ * phase 0: We, BN vectors -> wcat[:, :k1pad] = bf16(diag(a) We)^T (zeros up to k1pad), twe = bf16(T We), bias = -(a c1)^T We
+ * phase 1: G (fp32 [cin,cin] = twe^T We from mclip_gemm_wgrad), sum X -> wcat[:, k1pad:] = bf16(G), bias -= xbar bf16(G)
+ * phase 2: X^T X (fp32 [cin,cin]), sum X -> gc = bf16(X^T X - (sum X)(sum X)^T / count)
+ * phase 3: dwe (holding dV0^T X), q = bf16(We gc) -> dwe = a (dwe - c1 (sum X)^T) + t q                       */
+typedef struct mclip_bn0_fold_args {
+  int cexp, cin, k1pad; long long ldw; double count;
+  const float* we;                                  /* fp32 [cexp, cin] */
+  const float* scale; const float* invstd; const float* c1; const float* c2;     /* fp32 [cexp] */
+  void* wcat; void* twe; float* bias;               /* bf16 [cin, ldw], bf16 [cexp, cin], fp32 [cin] */
+  const float* g; const float* sumx;                /* fp32 [cin, cin], fp32 [cin] */
+  void* gc;                                         /* bf16 [cin, cin] */
+  float* dwe; const void* q;                        /* fp32 [cexp, cin] in/out, bf16 [cexp, cin] */
+} mclip_bn0_fold_args;
+int mclip_bn0_fold(const mclip_bn0_fold_args* args, int phase, void* stream);
 
 /* ---- BatchNorm / swish / squeeze-excite / pooling passes ---------------------------------------------------------
  * Producer kernels (GEMM, depthwise, stem) emit per-channel (sum, sum sq) partials; mclip_bn_finalize turns them

@@ -48,6 +48,7 @@ class GemmArgs(C.Structure):
         ("stats", C.c_void_p), ("stat_slots", C.c_int),
         ("dropmask", C.c_void_p), ("drop_scale", C.c_float),
         ("aux_pre", C.c_void_p), ("ld_aux", C.c_longlong),
+        ("a2", C.c_void_p), ("lda2", C.c_longlong), ("a2_batch_stride", C.c_longlong), ("k2", C.c_int),
     ]
 
 
@@ -170,6 +171,15 @@ class StemArgs(C.Structure):
         ("in_", C.c_void_p), ("stride_n", C.c_longlong), ("stride_c", C.c_longlong), ("stride_h", C.c_longlong), ("stride_w", C.c_longlong),
         ("out", C.c_void_p),
         ("in_channels", C.c_int), ("in_dtype", C.c_int), ("norm_lut", C.c_void_p),
+    ]
+
+
+class Bn0FoldArgs(C.Structure):
+    _fields_ = [
+        ("cexp", C.c_int), ("cin", C.c_int), ("k1pad", C.c_int), ("ldw", C.c_longlong), ("count", C.c_double),
+        ("we", C.c_void_p), ("scale", C.c_void_p), ("invstd", C.c_void_p), ("c1", C.c_void_p), ("c2", C.c_void_p),
+        ("wcat", C.c_void_p), ("twe", C.c_void_p), ("bias", C.c_void_p),
+        ("g", C.c_void_p), ("sumx", C.c_void_p), ("gc", C.c_void_p), ("dwe", C.c_void_p), ("q", C.c_void_p),
     ]
 
 

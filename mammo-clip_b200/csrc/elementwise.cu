@@ -754,6 +754,104 @@ extern "C" int mclip_weight_prep(const void* table_dev, int n_entries, void* str
   return MCLIP_OK;
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// folded BatchNorm backward of the expand convolution (see include/mclip.h): small per-block weight-space kernels
+// ------------------------------------------------------------------------------------------------
+// phase 0: 32x32 tiles of We [cexp, cin]: twe = bf16(t We) (straight), wcat[j, k] = bf16(a[k] We[k, j]) (transposed)
+__global__ void __launch_bounds__(256) mclip_bn0_fold_prep_kernel(const mclip_bn0_fold_args a) {
+  __shared__ float tile[32][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int tiles_j = (a.cin + 31) >> 5, tiles_k = (a.k1pad + 31) >> 5;
+  bf16* wcat = (bf16*)a.wcat; bf16* twe = (bf16*)a.twe;
+  for (int tl = blockIdx.x; tl < tiles_j * tiles_k; tl += gridDim.x) {
+    const int k0 = (tl / tiles_j) << 5, j0 = (tl % tiles_j) << 5;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int k = k0 + ty + 8 * i, j = j0 + tx;
+      float av = 0.f;
+      if (k < a.cexp && j < a.cin) {
+        const float w = a.we[(size_t)k * a.cin + j], sc = a.scale[k];
+        av = sc * w;
+        twe[(size_t)k * a.cin + j] = __float2bfloat16_rn(-sc * a.c2[k] * a.invstd[k] * w);
+      }
+      tile[ty + 8 * i][tx] = av;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int j = j0 + ty + 8 * i, k = k0 + tx;                 // transposed write: row j, column k (zeros in [cexp, k1pad))
+      if (j < a.cin && k < a.k1pad) wcat[(size_t)j * a.ldw + k] = __float2bfloat16_rn(tile[tx][ty + 8 * i]);
+    }
+    __syncthreads();
+  }
+}
+// bias[j] = - sum_k a[k] c1[k] We[k, j]
+__global__ void mclip_bn0_fold_bias_kernel(const mclip_bn0_fold_args a) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= a.cin) return;
+  float s = 0.f;
+  for (int k = 0; k < a.cexp; ++k) s = fmaf(a.scale[k] * a.c1[k], a.we[(size_t)k * a.cin + j], s);
+  a.bias[j] = -s;
+}
+// phase 1: wcat[j, k1pad + i] = bf16(G[i, j]);  bias[j] -= sum_i xbar[i] * bf16(G[i, j])   (the SAME rounded G the GEMM multiplies X by)
+__global__ void mclip_bn0_fold_g_kernel(const mclip_bn0_fold_args a) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= a.cin) return;
+  bf16* wcat = (bf16*)a.wcat;
+  const float inv = (float)(1.0 / a.count);
+  float s = 0.f;
+  for (int i = 0; i < a.cin; ++i) {
+    const bf16 g = __float2bfloat16_rn(a.g[(size_t)i * a.cin + j]);
+    wcat[(size_t)j * a.ldw + a.k1pad + i] = g;
+    s = fmaf(a.sumx[i] * inv, __bfloat162float(g), s);
+  }
+  a.bias[j] -= s;
+}
+// phase 2: gc[j, i] = bf16(XtX[i, j] - sumx[i] sumx[j] / count)     (symmetric; stored as the [N, K] operand of mclip_gemm_tn)
+__global__ void mclip_bn0_fold_center_kernel(const mclip_bn0_fold_args a) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= a.cin * a.cin) return;
+  const int j = idx / a.cin, i = idx % a.cin;
+  ((bf16*)a.gc)[idx] = __float2bfloat16_rn(a.g[(size_t)i * a.cin + j] - (float)((double)a.sumx[i] * (double)a.sumx[j] / a.count));
+}
+// phase 3: dwe[k, j] = a[k] (dwe[k, j] - c1[k] sumx[j]) + t[k] q[k, j]
+__global__ void mclip_bn0_fold_dwe_kernel(const mclip_bn0_fold_args a) {
+  const size_t total = (size_t)a.cexp * a.cin;
+  for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+    const int k = (int)(idx / a.cin), j = (int)(idx % a.cin);
+    const float sc = a.scale[k], t = -sc * a.c2[k] * a.invstd[k];
+    a.dwe[idx] = sc * (a.dwe[idx] - a.c1[k] * a.sumx[j]) + t * __bfloat162float(((const bf16*)a.q)[idx]);
+  }
+}
+
+extern "C" int mclip_bn0_fold(const mclip_bn0_fold_args* a, int phase, void* stream_) {
+  cudaStream_t st = (cudaStream_t)stream_;
+  MCLIP_REQUIRE(a && a->cexp > 0 && a->cin > 0 && a->count > 0, "mclip_bn0_fold: bad arguments");
+  if (phase == 0) {
+    MCLIP_REQUIRE(a->we && a->scale && a->invstd && a->c1 && a->c2 && a->wcat && a->twe && a->bias && a->k1pad >= a->cexp && a->ldw >= a->k1pad + a->cin,
+                  "mclip_bn0_fold phase 0: null operand / bad layout");
+    const int tiles = ((a->cin + 31) >> 5) * ((a->k1pad + 31) >> 5);
+    mclip_bn0_fold_prep_kernel<<<tiles < 1184 ? tiles : 1184, 256, 0, st>>>(*a);
+    mclip_bn0_fold_bias_kernel<<<ceil_div(a->cin, 64), 64, 0, st>>>(*a);
+  } else if (phase == 1) {
+    MCLIP_REQUIRE(a->g && a->sumx && a->wcat && a->bias, "mclip_bn0_fold phase 1: null operand");
+    mclip_bn0_fold_g_kernel<<<ceil_div(a->cin, 64), 64, 0, st>>>(*a);
+  } else if (phase == 2) {
+    MCLIP_REQUIRE(a->g && a->sumx && a->gc, "mclip_bn0_fold phase 2: null operand");
+    mclip_bn0_fold_center_kernel<<<ceil_div((long long)a->cin * a->cin, 256), 256, 0, st>>>(*a);
+  } else if (phase == 3) {
+    MCLIP_REQUIRE(a->dwe && a->q && a->sumx && a->scale && a->invstd && a->c1 && a->c2, "mclip_bn0_fold phase 3: null operand");
+    const long long total = (long long)a->cexp * a->cin;
+    int grid = (int)((total + 255) / 256); if (grid > mclip_num_sms() * 8) grid = mclip_num_sms() * 8;
+    mclip_bn0_fold_dwe_kernel<<<grid, 256, 0, st>>>(*a);
+  } else {
+    MCLIP_REQUIRE(false, "mclip_bn0_fold: phase %d", phase);
+  }
+  MCLIP_CHECK_LAUNCH();
+  return MCLIP_OK;
+}
+
 // ------------------------------------------------------------------------------------------------
 // small row-wise ops of the CLIP head: fp32 -> bf16 cast, L2 normalisation fwd/bwd (clip.py:90-91), bias gradient
 // ------------------------------------------------------------------------------------------------

@@ -36,6 +36,8 @@ struct GemmDev {
   float* stats;     // [(gridDim.x / n_blocks) * 4][2][N]
   const uint8_t* dropmask; float drop_scale;
   bf16* aux; long long aux_ld;   // optional bf16 copy of the pre-activation value (after the bias), [batches*M, aux_ld]
+  int K1, k1_blocks;   // K-concatenated A operand: columns [0,K1) come from tmA, the rest (K - K1pad... see host) from tmA2; k1_blocks = ceil(K1/64)
+  int K2;              // columns of the second A operand (0: single operand, K1 == K)
   int small_k;      // K <= 64 and shared B: B panel resident in smem, A tiles staged with cp.async by warp 0
   const bf16* a_ptr; long long lda, a_bs;
   int debug;        // MCLIP_GEMM_DEBUG bitmask (experiments only): 1 no stats, 2 no TMA store, 4 no TMEM load/convert
@@ -92,7 +94,7 @@ __device__ __forceinline__ float gelu_erf(float v) { return 0.5f * v * (1.0f + e
 template <int MODE, bool STATS>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 mclip_gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                     const __grid_constant__ CUtensorMap tmD, const GemmDev p) {
+                     const __grid_constant__ CUtensorMap tmD, const __grid_constant__ CUtensorMap tmA2, const GemmDev p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const uint32_t a_bytes = GEMM_BM * GEMM_BK * 2, b_bytes = (uint32_t)p.block_n * GEMM_BK * 2;
@@ -190,7 +192,8 @@ mclip_gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
           mbar_wait(&empty[stage], phase ^ 1);
           uint8_t* sa = smem + (size_t)stage * stage_bytes;
           mbar_expect_tx(&full[stage], stage_bytes);
-          tma_load_3d(sa, &tmA, &full[stage], kb * GEMM_BK, m0, b);
+          if (kb < p.k1_blocks) tma_load_3d(sa, &tmA, &full[stage], kb * GEMM_BK, m0, b);
+          else tma_load_3d(sa, &tmA2, &full[stage], (kb - p.k1_blocks) * GEMM_BK, m0, b);     // second operand of a K-concatenated A
           tma_load_3d(sa + a_bytes, &tmB, &full[stage], kb * GEMM_BK, n0, p.b_batched ? b : 0);
           if (++stage == p.stages) { stage = 0; phase ^= 1; }
         }
@@ -208,7 +211,7 @@ mclip_gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
           mbar_wait(&full[stage], phase);
           tc_fence_after();
           const uint32_t sa = smem_u32(smem + (size_t)stage * stage_bytes), sb = p.small_k ? smem_u32(bpanel) : sa + a_bytes;
-          const int krem = p.K - kb * GEMM_BK;
+          const int krem = kb < p.k1_blocks ? p.K1 - kb * GEMM_BK : p.K2 - (kb - p.k1_blocks) * GEMM_BK;
           const int nk = krem >= GEMM_BK ? 4 : (krem + 15) >> 4;
           for (int kk = 0; kk < nk; ++kk)
             umma_bf16(d_tmem, umma_smem_desc_sw128(sa + kk * 32, 16, 1024), umma_smem_desc_sw128(sb + kk * 32, 16, 1024), p.idesc,
@@ -380,13 +383,19 @@ extern "C" int mclip_gemm_tn(const mclip_gemm_args* g, void* stream_) {
   MCLIP_REQUIRE(g && g->a && g->b && g->d, "mclip_gemm_tn: null operand");
   MCLIP_REQUIRE(g->m > 0 && g->n > 0 && g->k > 0 && g->batches > 0, "mclip_gemm_tn: empty problem %d x %d x %d x %d", g->batches, g->m, g->n, g->k);
   MCLIP_REQUIRE(g->n % 8 == 0 && g->k % 8 == 0, "mclip_gemm_tn: N=%d and K=%d must be multiples of 8", g->n, g->k);
-  MCLIP_REQUIRE(g->lda >= g->k && g->ldb >= g->k && g->ldd >= g->n, "mclip_gemm_tn: leading dimensions too small");
+  MCLIP_REQUIRE(g->lda >= g->k && g->ldd >= g->n, "mclip_gemm_tn: leading dimensions too small");
   GemmDev p;
   memset(&p, 0, sizeof(p));
   p.M = g->m; p.N = g->n; p.K = g->k; p.batches = g->batches; p.b_batched = g->b_batch_stride != 0;
   p.block_n = pick_block_n(p.N, &p.n_blocks);
   p.m_blocks = ceil_div(p.M, GEMM_BM);
-  p.k_blocks = ceil_div(p.K, GEMM_BK);
+  p.K1 = p.K; p.k1_blocks = ceil_div(p.K, GEMM_BK);
+  p.K2 = g->a2 ? g->k2 : 0;
+  if (p.K2 > 0) {     // A = [a | a2] along K; b = [n, k1_blocks*64 + k2] with zeros in columns [k, k1_blocks*64)
+    MCLIP_REQUIRE(g->k2 % 8 == 0 && g->lda2 >= g->k2 && ((uintptr_t)g->a2 & 15) == 0 && g->lda2 % 8 == 0, "mclip_gemm_tn: bad second A operand (k2=%d)", g->k2);
+    MCLIP_REQUIRE(g->ldb >= p.k1_blocks * GEMM_BK + p.K2, "mclip_gemm_tn: ldb too small for the K-concatenated weights");
+  } else MCLIP_REQUIRE(g->ldb >= g->k, "mclip_gemm_tn: leading dimensions too small");
+  p.k_blocks = p.k1_blocks + ceil_div(p.K2, GEMM_BK);
   p.m_tiles_total = p.batches * p.m_blocks;
   p.idesc = umma_idesc_bf16(GEMM_BM, p.block_n, 0, 0);
   p.bias = g->bias; p.residual = (const bf16*)g->residual; p.res_ld = g->ldr; p.res_bs = g->r_batch_stride; p.act = g->act;
@@ -396,7 +405,7 @@ extern "C" int mclip_gemm_tn(const mclip_gemm_args* g, void* stream_) {
   if (g->dropmask) MCLIP_REQUIRE(g->n % 16 == 0, "mclip_gemm_tn: dropout mask needs N %% 16 == 0");
   p.aux = (bf16*)g->aux_pre; p.aux_ld = g->ld_aux;
   if (g->aux_pre) MCLIP_REQUIRE(g->ld_aux >= g->n && g->ld_aux % 8 == 0 && ((uintptr_t)g->aux_pre & 15) == 0, "mclip_gemm_tn: aux_pre needs a 16-byte aligned row layout");
-  p.small_k = (p.k_blocks == 1 && !p.b_batched && g->lda % 8 == 0 && g->a_batch_stride % 8 == 0 && ((uintptr_t)g->a & 15) == 0) ? 1 : 0;
+  p.small_k = (p.k_blocks == 1 && p.K2 == 0 && !p.b_batched && g->lda % 8 == 0 && g->a_batch_stride % 8 == 0 && ((uintptr_t)g->a & 15) == 0) ? 1 : 0;
   if (getenv("MCLIP_GEMM_NO_SMALLK")) p.small_k = 0;
   p.a_ptr = (const bf16*)g->a; p.lda = g->lda; p.a_bs = g->a_batch_stride;
   const int stage_bytes = p.small_k ? GEMM_BM * GEMM_BK * 2 : GEMM_BM * GEMM_BK * 2 + p.block_n * GEMM_BK * 2;
@@ -406,17 +415,22 @@ extern "C" int mclip_gemm_tn(const mclip_gemm_args* g, void* stream_) {
   if (p.small_k) MCLIP_REQUIRE(p.stages >= 6, "mclip_gemm_tn: small-K mode needs 6 stages");   // always true for block_n <= 256
   MCLIP_REQUIRE(p.stages >= 2, "mclip_gemm_tn: tile does not fit in shared memory");
   const int smem = p.stages * stage_bytes + fixed;
-  CUtensorMap tmA, tmB, tmD;
+  CUtensorMap tmA, tmB, tmD, tmA2;
   int rc;
-  if ((rc = make_tmap_bf16_3d(&tmA, g->a, p.K, p.M, p.batches, g->lda, g->a_batch_stride, GEMM_BK, GEMM_BM, 1))) return rc;
-  if ((rc = make_tmap_bf16_3d(&tmB, g->b, p.K, p.N, p.b_batched ? p.batches : 1, g->ldb, g->b_batch_stride, GEMM_BK, p.block_n, 1))) return rc;
+  if ((rc = make_tmap_bf16_3d(&tmA, g->a, p.K1, p.M, p.batches, g->lda, g->a_batch_stride, GEMM_BK, GEMM_BM, 1))) return rc;
+  if (p.K2 > 0) {
+    if ((rc = make_tmap_bf16_3d(&tmA2, g->a2, p.K2, p.M, p.batches, g->lda2, g->a2_batch_stride, GEMM_BK, GEMM_BM, 1))) return rc;
+  } else tmA2 = tmA;
+  // B holds the K-concatenated weights: columns [0, k1_blocks*64) pair with A (zero beyond K1), the next K2 columns with A2
+  const int kb_total = p.K2 > 0 ? p.k1_blocks * GEMM_BK + p.K2 : p.K;
+  if ((rc = make_tmap_bf16_3d(&tmB, g->b, kb_total, p.N, p.b_batched ? p.batches : 1, g->ldb, g->b_batch_stride, GEMM_BK, p.block_n, 1))) return rc;
   if ((rc = make_tmap_bf16_3d(&tmD, g->d, p.N, p.M, p.batches, g->ldd, g->d_batch_stride, 64, 32, 1))) return rc;
   int cap = mclip_num_sms() / p.n_blocks * p.n_blocks;
   if (cap < p.n_blocks) cap = p.n_blocks;
   long long tiles = (long long)p.m_tiles_total * p.n_blocks;
   int grid = tiles < cap ? (int)tiles : cap;
   if (g->stats) MCLIP_REQUIRE(g->stat_slots == grid / p.n_blocks * 4, "mclip_gemm_tn: stat_slots=%d, expected %d", g->stat_slots, grid / p.n_blocks * 4);
-  typedef void (*kern_t)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const GemmDev);
+  typedef void (*kern_t)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap, const GemmDev);
   static const kern_t kerns[3][2] = {{mclip_gemm_tn_kernel<0, false>, mclip_gemm_tn_kernel<0, true>},
                                      {mclip_gemm_tn_kernel<1, false>, mclip_gemm_tn_kernel<1, true>},
                                      {mclip_gemm_tn_kernel<2, false>, mclip_gemm_tn_kernel<2, true>}};
@@ -429,7 +443,7 @@ extern "C" int mclip_gemm_tn(const mclip_gemm_args* g, void* stream_) {
   int mode = (p.bias || p.dropmask || p.aux || p.act != 0) ? 2 : (p.residual ? 1 : 0);
   if (getenv("MCLIP_GEMM_GENERIC")) mode = 2;                 // experiments: force the all-in-one epilogue
   // the generic epilogue is instantiated once (STATS checked at run time there: its no-statistics build spills)
-  kerns[mode][(p.stats || mode == 2) ? 1 : 0]<<<grid, GEMM_THREADS, smem, stream>>>(tmA, tmB, tmD, p);
+  kerns[mode][(p.stats || mode == 2) ? 1 : 0]<<<grid, GEMM_THREADS, smem, stream>>>(tmA, tmB, tmD, tmA2, p);
   MCLIP_CHECK_LAUNCH();
   return MCLIP_OK;
 }

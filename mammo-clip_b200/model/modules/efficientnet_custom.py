@@ -126,6 +126,8 @@ class MBConvBlock(nn.Module):
 
 
 # ----------------------------------------------------------------------------------------------- the engine
+import os as _os
+_FOLD_BN0 = [_os.environ.get("MCLIP_FOLD_BN0", "1") != "0"]      # fold the expand conv's BN backward into its dgrad / wgrad GEMM operands
 _UPDATE_RUNNING = [True]      # False during the recompute pass of the multi-view memory plan (the statistics were already folded in)
 
 
@@ -294,15 +296,22 @@ def _block_backward(net, i, B, dx, n, training, grads, G, S=None):
         dg0, db0 = G(blk._bn0.weight), G(blk._bn0.bias)
         c1, c2 = ops.bn_bwd_finalize(bnp, bn0.count, training, dg0, db0)
         grads[pre + "_bn0.weight"], grads[pre + "_bn0.bias"] = dg0, db0
-        dy0 = ops.ew_backward(1, y0.view(n, h * w, g.cexp), bn0, 0, du=dv0.view(n, h * w, g.cexp), dv_given=True, c1=c1, c2=c2)
-        del dv0
-        dy0 = dy0.view(n * h * w, g.cexp)
         x_in = B["x_in"].view(n * h * w, g.cin)
         ge = G(blk._expand_conv.weight)
-        ops.gemm_wgrad(dy0, x_in, out=ge.view(g.cexp, g.cin))
         grads[pre + "_expand_conv.weight"] = ge
-        dx = ops.gemm_tn(dy0, wc.bf16_t[("e", i)], residual=dx.view(n * h * w, g.cin) if g.skip else None).view(n, h, w, g.cin)
-        del dy0
+        skip_grad = dx.view(n * h * w, g.cin) if g.skip else None
+        if _FOLD_BN0[0] and g.cexp % 8 == 0 and g.cin % 8 == 0:
+            # both consumers of dY0 are linear: the BN0-backward apply pass over the 6x-wide tensor folds into the GEMM operands
+            dx = ops.bn0_fold_backward(dv0.view(n * h * w, g.cexp), x_in, blk._expand_conv.weight.view(g.cexp, g.cin), wc.bf16[("e", i)], bn0, c1, c2,
+                                       ge.view(g.cexp, g.cin), residual=skip_grad).view(n, h, w, g.cin)
+            del dv0
+        else:
+            dy0 = ops.ew_backward(1, y0.view(n, h * w, g.cexp), bn0, 0, du=dv0.view(n, h * w, g.cexp), dv_given=True, c1=c1, c2=c2)
+            del dv0
+            dy0 = dy0.view(n * h * w, g.cexp)
+            ops.gemm_wgrad(dy0, x_in, out=ge.view(g.cexp, g.cin))
+            dx = ops.gemm_tn(dy0, wc.bf16_t[("e", i)], residual=skip_grad).view(n, h, w, g.cin)
+            del dy0
     elif B.get("from_stem"):
         ys, bns = S["stem"]
         dvs, bnp = ops.dwconv_backward(ys, blk._depthwise_conv.weight, g.k, g.s, g.pads, dy1, ddw, bn=bns)

@@ -25,7 +25,7 @@ def _require_cuda(*tensors):
 
 # ------------------------------------------------------------------------------------------------ GEMMs
 
-def gemm_tn(a, b, out=None, bias=None, residual=None, act=0, want_stats=None, dropmask=None, drop_scale=1.0, aux_pre=None):
+def gemm_tn(a, b, out=None, bias=None, residual=None, act=0, want_stats=None, dropmask=None, drop_scale=1.0, aux_pre=None, a2=None):
     """out[b,m,n] = epi(sum_k a[b,m,k] * w[b|0,n,k]).  a: [M,K] or [Bt,M,K] bf16; b: [N,K] or [Bt,N,K] bf16.
     want_stats=None: returns out (bf16).  want_stats=True/False: returns (out, stats[slots,2,N] fp32 or None)."""
     _require_cuda(a, b)
@@ -34,7 +34,13 @@ def gemm_tn(a, b, out=None, bias=None, residual=None, act=0, want_stats=None, dr
     bt, m, k = a3.shape
     b_batched = b.dim() == 3
     n = b.shape[-2]
-    assert b.shape[-1] == k and a3.stride(2) == 1 and b.stride(-1) == 1
+    if a2 is not None:       # A = [a | a2] along K, b = [n, ceil64(k) + k2]
+        a23 = a2 if a2.dim() == 3 else a2.unsqueeze(0)
+        assert a23.shape[:2] == a3.shape[:2] and a23.dtype == torch.bfloat16 and a23.stride(2) == 1
+        assert b.shape[-1] == (k + 63) // 64 * 64 + a23.shape[2] and b.stride(-1) == 1
+    else:
+        assert b.shape[-1] == k and b.stride(-1) == 1
+    assert a3.stride(2) == 1
     if out is None:
         out = torch.empty((bt, m, n) if a.dim() == 3 else (m, n), dtype=torch.bfloat16, device=a.device)
     o3 = out if out.dim() == 3 else out.unsqueeze(0)
@@ -44,6 +50,8 @@ def gemm_tn(a, b, out=None, bias=None, residual=None, act=0, want_stats=None, dr
     g.b_batch_stride = b.stride(0) if b_batched else 0
     g.d, g.ldd, g.d_batch_stride = o3.data_ptr(), o3.stride(1), o3.stride(0) if bt > 1 else 0
     g.m, g.n, g.k, g.batches = m, n, k, bt
+    if a2 is not None:
+        g.a2, g.lda2, g.a2_batch_stride, g.k2 = a23.data_ptr(), a23.stride(1), a23.stride(0) if bt > 1 else 0, a23.shape[2]
     g.bias = bias.data_ptr() if bias is not None else None
     if residual is not None:
         r3 = residual if residual.dim() == 3 else residual.unsqueeze(0)
@@ -89,6 +97,41 @@ def gemm_wgrad(a, b, out=None, accumulate=False):
     g.workspace, g.workspace_bytes = ws.data_ptr(), ws.numel()
     call("mclip_gemm_wgrad", C.byref(g), nbytes=2 * r * (i + j) + 4 * i * j)
     return out
+
+
+def bn0_fold_backward(dv0, x, we, we_bf16, bn, c1, c2, dwe_out, residual=None):
+    """Folded BatchNorm backward of the expand convolution (include/mclip.h, mclip_bn0_fold): from dV0 [M,Cexp] (gradient
+    w.r.t. the BN output, swish' applied), X [M,Cin] (bf16), the conv weight We (fp32 [Cexp,Cin] + its bf16 copy) and the BN
+    backward means (c1, c2) -> dX [M,Cin] bf16 (+ residual) and dWe (written to dwe_out) WITHOUT materialising dY0."""
+    from ._lib import Bn0FoldArgs
+    m, cexp = dv0.shape
+    cin = x.shape[1]
+    dev = dv0.device
+    k1pad = (cexp + 63) // 64 * 64
+    ldw = k1pad + cin
+    wcat = torch.empty((cin, ldw), dtype=torch.bfloat16, device=dev)
+    twe = torch.empty((cexp, cin), dtype=torch.bfloat16, device=dev)
+    bias = torch.empty(cin, dtype=torch.float32, device=dev)
+    sumx = torch.empty(cin, dtype=torch.float32, device=dev)
+    colsum(x, sumx)
+    f = Bn0FoldArgs()
+    f.cexp, f.cin, f.k1pad, f.ldw, f.count = cexp, cin, k1pad, ldw, float(m)
+    f.we, f.scale, f.invstd, f.c1, f.c2 = we.data_ptr(), bn.scale.data_ptr(), bn.invstd.data_ptr(), c1.data_ptr(), c2.data_ptr()
+    f.wcat, f.twe, f.bias, f.sumx = wcat.data_ptr(), twe.data_ptr(), bias.data_ptr(), sumx.data_ptr()
+    call("mclip_bn0_fold", C.byref(f), 0)
+    g = gemm_wgrad(twe, we_bf16)                               # G = (T We)^T We  [cin, cin]
+    f.g = g.data_ptr()
+    call("mclip_bn0_fold", C.byref(f), 1)
+    dx = gemm_tn(dv0, wcat, a2=x, bias=bias, residual=residual)
+    gemm_wgrad(dv0, x, out=dwe_out)                            # dV0^T X
+    xtx = gemm_wgrad(x, x)                                     # X^T X
+    gc = torch.empty((cin, cin), dtype=torch.bfloat16, device=dev)
+    f.g, f.gc = xtx.data_ptr(), gc.data_ptr()
+    call("mclip_bn0_fold", C.byref(f), 2)
+    q = gemm_tn(we_bf16, gc)                                   # We (X^T X - sum sum^T / M)  [cexp, cin]
+    f.dwe, f.q = dwe_out.data_ptr(), q.data_ptr()
+    call("mclip_bn0_fold", C.byref(f), 3)
+    return dx
 
 
 # ------------------------------------------------------------------------------------------------ loss

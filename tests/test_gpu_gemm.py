@@ -146,3 +146,56 @@ def test_gemm_tn_epilogue_instantiations_agree(bt, m, n, k, monkeypatch):
     assert torch.equal(o_plain, o_gen) and torch.equal(s_plain, s_gen) and torch.equal(o_res, o_gres)
     ref = torch.einsum("bmk,bnk->bmn", a.float(), w.float()) if bt > 1 else a.float() @ w.float().T
     assert rel_err(o_plain.float(), ref) < 6e-3 and rel_err(o_res.float(), ref + res.float()) < 6e-3
+
+
+def test_gemm_tn_k_concatenated_second_operand():
+    """A = [a | a2] along K with the weights laid out as [n, ceil64(k) + k2] (zeros in the padding columns)."""
+    from mammoclip_b200 import ops
+    for m, n, k, k2 in [(5000, 40, 240, 40), (777, 24, 144, 24), (4096, 304, 1824, 304), (300, 64, 384, 64)]:
+        a, a2 = _mk((m, k), 21), _mk((m, k2), 22)
+        w, w2 = _mk((n, k), 23, 1.0 / k ** 0.5), _mk((n, k2), 24, 1.0 / k2 ** 0.5)
+        kp = (k + 63) // 64 * 64
+        wcat = torch.zeros((n, kp + k2), dtype=torch.bfloat16, device="cuda")
+        wcat[:, :k], wcat[:, kp:] = w, w2
+        bias = torch.randn(n, device="cuda")
+        res = _mk((m, n), 25)
+        out = ops.gemm_tn(a, wcat, a2=a2, bias=bias, residual=res)
+        ref = a.float() @ w.float().T + a2.float() @ w2.float().T + bias + res.float()
+        assert rel_err(out.float(), ref) < 6e-3, (m, n, k, k2)
+
+
+@pytest.mark.parametrize("m,cin,cexp,training", [(20000, 40, 240, True), (6000, 24, 144, True), (3000, 304, 1824, True), (5000, 64, 384, False)])
+def test_bn0_fold_backward_matches_the_unfolded_path(m, cin, cexp, training):
+    """Folded BatchNorm backward of the expand conv (dX = [dV0|X][aWe;G] + bias, dWe from dV0^T X and X^T X) vs fp32 autograd
+    algebra of bn0(conv(x)) on the same bf16 tensors; X carries a non-zero mean so that the centring matters."""
+    from mammoclip_b200 import ops
+    torch.manual_seed(m + cin)
+    x = (torch.randn(m, cin, device="cuda") * 0.7 + torch.randn(cin, device="cuda") * 0.8).to(torch.bfloat16)
+    we = torch.randn(cexp, cin, device="cuda") / cin ** 0.5
+    we_b = we.to(torch.bfloat16)
+    y0 = (x.float() @ we_b.float().T).to(torch.bfloat16)                    # what the forward stored
+    dv0 = (torch.randn(m, cexp, device="cuda") * 0.3 + torch.randn(cexp, device="cuda") * 0.05).to(torch.bfloat16)
+    gamma = torch.rand(cexp, device="cuda") + 0.5
+    yf = y0.float()
+    mean, var = yf.mean(0), yf.var(0, unbiased=False)
+    bn = ops.BNState(cexp, "cuda")
+    bn.mean.copy_(mean); bn.invstd.copy_((var + 1e-3).rsqrt()); bn.scale.copy_(gamma * bn.invstd); bn.shift.zero_()
+    yhat = (yf - bn.mean) * bn.invstd
+    dvf = dv0.float()
+    if training:
+        c1, c2 = dvf.mean(0), (dvf * yhat).mean(0)
+    else:
+        c1, c2 = torch.zeros(cexp, device="cuda"), torch.zeros(cexp, device="cuda")
+    dy0 = bn.scale * (dvf - c1 - yhat * c2)
+    dx_ref = dy0 @ we                                                          # fp32 truth on the stored tensors
+    dwe_ref = dy0.T @ x.float()
+    skip = (torch.randn(m, cin, device="cuda") * 0.1).to(torch.bfloat16)
+    dwe = torch.empty_like(we)
+    dx = ops.bn0_fold_backward(dv0, x, we, we_b, bn, c1.contiguous(), c2.contiguous(), dwe, residual=skip)
+    # today's path for comparison: dY0 rounded to bf16, bf16 weights
+    dy0_b = dy0.to(torch.bfloat16)
+    dx_old = ops.gemm_tn(dy0_b, we_b.t().contiguous(), residual=skip)
+    e_new, e_old = rel_err(dx.float(), dx_ref + skip.float()), rel_err(dx_old.float(), dx_ref + skip.float())
+    w_new, w_old = rel_err(dwe, dwe_ref), rel_err(ops.gemm_wgrad(dy0_b, x), dwe_ref)
+    print(f"bn0 fold m={m} cin={cin} cexp={cexp}: dX err {e_new:.2e} (unfolded {e_old:.2e}), dWe err {w_new:.2e} (unfolded {w_old:.2e})")
+    assert e_new < 1e-2 and w_new < 1e-2
