@@ -280,6 +280,10 @@ mclip_gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
               for (int i = 0; i < 16; ++i) v[i] *= ((mw[i >> 2] >> ((i & 3) * 8)) & 0xffu) ? p.drop_scale : 0.f;
             }
           }
+          if (MODE == 3) {                          // lean "+ bias (+ residual)" epilogue: the folded BN-backward data gradient
+#pragma unroll
+            for (int i = 0; i < 16; ++i) if (cc + i < p.N) v[i] += __ldg(p.bias + cc + i);
+          }
           if (MODE >= 1 && p.residual && row < p.M) {
             const bf16* rp = p.residual + (size_t)b * p.res_bs + (size_t)row * p.res_ld + cc;
 #pragma unroll
@@ -431,16 +435,17 @@ extern "C" int mclip_gemm_tn(const mclip_gemm_args* g, void* stream_) {
   int grid = tiles < cap ? (int)tiles : cap;
   if (g->stats) MCLIP_REQUIRE(g->stat_slots == grid / p.n_blocks * 4, "mclip_gemm_tn: stat_slots=%d, expected %d", g->stat_slots, grid / p.n_blocks * 4);
   typedef void (*kern_t)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap, const GemmDev);
-  static const kern_t kerns[3][2] = {{mclip_gemm_tn_kernel<0, false>, mclip_gemm_tn_kernel<0, true>},
+  static const kern_t kerns[4][2] = {{mclip_gemm_tn_kernel<0, false>, mclip_gemm_tn_kernel<0, true>},
                                      {mclip_gemm_tn_kernel<1, false>, mclip_gemm_tn_kernel<1, true>},
-                                     {mclip_gemm_tn_kernel<2, false>, mclip_gemm_tn_kernel<2, true>}};
+                                     {mclip_gemm_tn_kernel<2, false>, mclip_gemm_tn_kernel<2, true>},
+                                     {mclip_gemm_tn_kernel<3, false>, mclip_gemm_tn_kernel<3, true>}};
   static int attr_set = 0;
   if (!attr_set) {
-    for (int m = 0; m < 3; ++m)
+    for (int m = 0; m < 4; ++m)
       for (int t = 0; t < 2; ++t) MCLIP_CHECK_CUDA(cudaFuncSetAttribute(kerns[m][t], cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_LIMIT));
     attr_set = 1;
   }
-  int mode = (p.bias || p.dropmask || p.aux || p.act != 0) ? 2 : (p.residual ? 1 : 0);
+  int mode = (p.dropmask || p.aux || p.act != 0) ? 2 : p.bias ? 3 : (p.residual ? 1 : 0);
   if (getenv("MCLIP_GEMM_GENERIC")) mode = 2;                 // experiments: force the all-in-one epilogue
   // the generic epilogue is instantiated once (STATS checked at run time there: its no-statistics build spills)
   kerns[mode][(p.stats || mode == 2) ? 1 : 0]<<<grid, GEMM_THREADS, smem, stream>>>(tmA, tmB, tmD, tmA2, p);

@@ -199,8 +199,9 @@ def _block_forward(net, i, x, pending, n, h, w, training, rowscale=None):
     del u, wg
     bn2 = _bn_fin(st, n * ho * wo, blk._bn2, training)
     rs = rowscale if g.skip else None
-    x_out, _ = ops.ew_forward(y2, bn=bn2, act=0, rowscale=rs, residual=x.view(n, h * w, g.cin) if g.skip else None)
-    B.update(y1=y1, bn1=bn1, pooled=pooled, z1=z1, gate=gate, y2=y2, bn2=bn2, rowscale=rs, ho=ho, wo=wo)
+    # per-channel sums of the block output ride along (pool partials): the next block's folded BN0 backward needs sum(X)
+    x_out, xsum = ops.ew_forward(y2, bn=bn2, act=0, rowscale=rs, residual=x.view(n, h * w, g.cin) if g.skip else None, pool=training and _FOLD_BN0[0])
+    B.update(y1=y1, bn1=bn1, pooled=pooled, z1=z1, gate=gate, y2=y2, bn2=bn2, rowscale=rs, ho=ho, wo=wo, out_sum_part=xsum)
     return x_out.view(n, ho, wo, g.cout), B
 
 
@@ -223,6 +224,7 @@ def _forward(net, images, training, drop_rowscales, dropout_mult, want_raw, save
     S["stem"] = (y, bn)
     pending = (y, bn)      # a pre-BN tensor whose BN+swish is applied by the consumer
     x = None               # materialised block input [N,H,W,C] bf16
+    prev_sum = None        # pool partials [N,chunks,C] of the pass that wrote x
     for i, blk in enumerate(net._blocks):
         if blk.geom.expand and pending is not None:
             # (never the case for B0-B7, whose first stage has expand_ratio 1) the expand GEMM needs a materialised input
@@ -230,6 +232,7 @@ def _forward(net, images, training, drop_rowscales, dropout_mult, want_raw, save
             x, pending = x.view(n, h, w, -1), None
             S["stem_materialised"] = True
         x, B = _block_forward(net, i, x, pending, n, h, w, training, drop_rowscales.get(i) if drop_rowscales else None)
+        B["x_sum_part"], prev_sum = prev_sum, B.pop("out_sum_part", None)
         h, w, pending = B["ho"], B["wo"], None
         if save:
             S["blocks"].append(B)
@@ -302,8 +305,9 @@ def _block_backward(net, i, B, dx, n, training, grads, G, S=None):
         skip_grad = dx.view(n * h * w, g.cin) if g.skip else None
         if _FOLD_BN0[0] and g.cexp % 8 == 0 and g.cin % 8 == 0:
             # both consumers of dY0 are linear: the BN0-backward apply pass over the 6x-wide tensor folds into the GEMM operands
+            part = B.get("x_sum_part")
             dx = ops.bn0_fold_backward(dv0.view(n * h * w, g.cexp), x_in, blk._expand_conv.weight.view(g.cexp, g.cin), wc.bf16[("e", i)], bn0, c1, c2,
-                                       ge.view(g.cexp, g.cin), residual=skip_grad).view(n, h, w, g.cin)
+                                       ge.view(g.cexp, g.cin), residual=skip_grad, sumx=None if part is None else part.sum((0, 1))).view(n, h, w, g.cin)
             del dv0
         else:
             dy0 = ops.ew_backward(1, y0.view(n, h * w, g.cexp), bn0, 0, du=dv0.view(n, h * w, g.cexp), dv_given=True, c1=c1, c2=c2)

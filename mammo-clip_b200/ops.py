@@ -99,7 +99,7 @@ def gemm_wgrad(a, b, out=None, accumulate=False):
     return out
 
 
-def bn0_fold_backward(dv0, x, we, we_bf16, bn, c1, c2, dwe_out, residual=None):
+def bn0_fold_backward(dv0, x, we, we_bf16, bn, c1, c2, dwe_out, residual=None, sumx=None):
     """Folded BatchNorm backward of the expand convolution (include/mclip.h, mclip_bn0_fold): from dV0 [M,Cexp] (gradient
     w.r.t. the BN output, swish' applied), X [M,Cin] (bf16), the conv weight We (fp32 [Cexp,Cin] + its bf16 copy) and the BN
     backward means (c1, c2) -> dX [M,Cin] bf16 (+ residual) and dWe (written to dwe_out) WITHOUT materialising dY0."""
@@ -112,8 +112,9 @@ def bn0_fold_backward(dv0, x, we, we_bf16, bn, c1, c2, dwe_out, residual=None):
     wcat = torch.empty((cin, ldw), dtype=torch.bfloat16, device=dev)
     twe = torch.empty((cexp, cin), dtype=torch.bfloat16, device=dev)
     bias = torch.empty(cin, dtype=torch.float32, device=dev)
-    sumx = torch.empty(cin, dtype=torch.float32, device=dev)
-    colsum(x, sumx)
+    if sumx is None:                    # normally handed over by the forward (pool partials of the pass that wrote X)
+        sumx = torch.empty(cin, dtype=torch.float32, device=dev)
+        colsum(x, sumx)
     f = Bn0FoldArgs()
     f.cexp, f.cin, f.k1pad, f.ldw, f.count = cexp, cin, k1pad, ldw, float(m)
     f.we, f.scale, f.invstd, f.c1, f.c2 = we.data_ptr(), bn.scale.data_ptr(), bn.invstd.data_ptr(), c1.data_ptr(), c2.data_ptr()
