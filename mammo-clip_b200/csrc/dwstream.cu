@@ -358,7 +358,7 @@ __global__ void __launch_bounds__(128, FwdCfg<K, S>::CTAS) mclip_dws_fwd_kernel(
 #ifndef DWS_BWD_NSLOT
 #define DWS_BWD_NSLOT 3
 #endif
-template <int K, int NSLOT, int REP, bool BN, int NS>
+template <int K, int NSLOT, int REP, bool BN, int NS, bool ROT>
 __global__ void __launch_bounds__(NS * 64, NS == 4 ? 2 : 3) mclip_dws_bwd_s1_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constant__ CUtensorMap tmDy, const DwsDev p) {
   constexpr int SW = 4, NW = 2 * NS, TW = SW * NS, IW = TW + K - 1, PC = SW + K - 1, RB = K * REP, KK = K;
   constexpr uint32_t ROW_BYTES = IW * 128, PART_BYTES = RB * ROW_BYTES, SLOT_BYTES = 2 * PART_BYTES;
@@ -367,8 +367,10 @@ __global__ void __launch_bounds__(NS * 64, NS == 4 ? 2 : 3) mclip_dws_bwd_s1_ker
   __shared__ __align__(8) uint64_t full[NSLOT];
   __shared__ uint32_t arrivals[NSLOT];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int strip = warp % NS;
-  const bool wrole = warp < NS;                      // first NS warps: weight gradient, last NS warps: data gradient
+  // NS == 4: first NS warps weight gradient, last NS warps data gradient (every SM sub-partition gets one of each).  NS == 2 (four
+  // warps, one per sub-partition): alternate the roles with the CTA parity so that no sub-partition runs only the heavier role
+  const int strip = NS == 2 ? (warp >> 1) : (warp % NS);
+  const bool wrole = NS == 2 ? (((warp ^ blockIdx.x) & 1) == 0) : (warp < NS);
   const int chunk = blockIdx.x % p.n_chunks, slot = blockIdx.x / p.n_chunks;
   const int c0 = chunk * 64, c = c0 + lane * 2;
   const bool cvalid = c < p.C;
@@ -537,7 +539,45 @@ __global__ void __launch_bounds__(NS * 64, NS == 4 ? 2 : 3) mclip_dws_bwd_s1_ker
     for (int blk = 0; blk < ci.nblk; ++blk, ++count) {
       const int s = count % NSLOT;
       mbar_wait(&full[s], (uint32_t)(count / NSLOT) & 1u);
-      if (wactive) {
+      if (wactive && ROT) {
+        // ROT: ONE step body per role (the K-times unrolled static-role bodies of k5 are 5500 SASS instructions, and the two roles
+        // thrash the instruction caches: 38 % of the stall samples were no_instruction); the rolling window / accumulator rows
+        // are rotated with register moves instead (16 float2 per 100 FFMA2)
+        const uint32_t sbase = ring + (uint32_t)s * SLOT_BYTES + (uint32_t)lane * 4u + (uint32_t)(strip * SW) * 128u;
+        const int tb = t0 + blk * RB;                  // input row of the block's first step
+        // one loop per (role, fast/edge) so that the rotation's register moves are not doubled by branch joins inside the loop
+        auto wloop = [&](auto fast_c) {
+#pragma unroll 1
+          for (int rr = 0; rr < RB; ++rr) {
+            const uint32_t ybase = sbase + (uint32_t)rr * ROW_BYTES;
+            wstep(fast_c, std::integral_constant<int, 0>{}, ybase, ybase + PART_BYTES, tb + rr);
+            // next step: the row that is j steps old must sit in window slot K-j
+#pragma unroll
+            for (int j = 1; j < K; ++j)
+#pragma unroll
+              for (int o = 0; o < SW; ++o) acc[j][o] = acc[(j + 1) % K][o];
+          }
+        };
+        auto dloop = [&](auto fast_c) {
+#pragma unroll 1
+          for (int rr = 0; rr < RB; ++rr) {
+            const uint32_t ybase = sbase + (uint32_t)rr * ROW_BYTES;
+            dstep(fast_c, std::integral_constant<int, 0>{}, ybase, ybase + PART_BYTES, tb + rr);
+            // slot q completes q steps ahead: everything moves one step closer (slot K-1 is re-initialised by the next step)
+#pragma unroll
+            for (int j = 0; j < K - 1; ++j)
+#pragma unroll
+              for (int o = 0; o < SW; ++o) acc[j][o] = acc[j + 1][o];
+          }
+        };
+        if (wrole) {
+          if (warp_fast && tb >= 0 && tb + RB <= p.H && tb + p.pt >= ci.r0 && tb + p.pt + RB <= r1) wloop(std::true_type{});
+          else wloop(std::false_type{});
+        } else {
+          if (warp_fast && tb >= ci.r0 && tb + RB <= r1) dloop(std::true_type{});
+          else dloop(std::false_type{});
+        }
+      } else if (wactive) {
 #pragma unroll 1
         for (int rep = 0; rep < REP; ++rep) {
           const uint32_t sbase = ring + (uint32_t)s * SLOT_BYTES + (uint32_t)(rep * K) * ROW_BYTES + (uint32_t)lane * 4u;
@@ -953,7 +993,13 @@ static int dws_fwd_ctas(const mclip_dwconv_args* a) {
 }
 
 #ifndef DWS_BWD_K5_NS
-#define DWS_BWD_K5_NS 4
+#define DWS_BWD_K5_NS 2
+#endif
+#ifndef DWS_BWD_K3_ROT
+#define DWS_BWD_K3_ROT 0
+#endif
+#ifndef DWS_BWD_K5_ROT
+#define DWS_BWD_K5_ROT 1
 #endif
 template <int K>
 struct BwdCfg {
@@ -961,6 +1007,7 @@ struct BwdCfg {
   static constexpr int REP = (K == 3) ? 2 : 1;
   static constexpr int NS = (K == 3) ? 4 : DWS_BWD_K5_NS;      // column strips per CTA (k5: 2 -> 128 threads, 3 CTAs/SM at 168 registers, no spills)
   static constexpr int CTAS = NS == 4 ? 2 : 3;
+  static constexpr bool ROT = (K == 3) ? (DWS_BWD_K3_ROT != 0) : (DWS_BWD_K5_ROT != 0);
   static constexpr int TW = 4 * NS, IW = TW + K - 1;
   static constexpr int RING = NSLOT * 2 * K * REP * IW * 128;
   static constexpr int SMEM = RING > NS * K * K * 64 * 4 ? RING : NS * K * K * 64 * 4;
@@ -973,7 +1020,8 @@ int dws_launch_bwd_s1(const mclip_dwconv_args* a, DwsDev& p, cudaStream_t stream
   if (rc) return rc;
   if ((rc = dws_tmap(&tmDy, p.dy, p.N, p.Ho, p.Wo, p.C, BwdCfg<K>::IW, K * BwdCfg<K>::REP))) return rc;
   const bool bn = p.scale != nullptr;
-  auto kern = bn ? mclip_dws_bwd_s1_kernel<K, BwdCfg<K>::NSLOT, BwdCfg<K>::REP, true, BwdCfg<K>::NS> : mclip_dws_bwd_s1_kernel<K, BwdCfg<K>::NSLOT, BwdCfg<K>::REP, false, BwdCfg<K>::NS>;
+  auto kern = bn ? mclip_dws_bwd_s1_kernel<K, BwdCfg<K>::NSLOT, BwdCfg<K>::REP, true, BwdCfg<K>::NS, BwdCfg<K>::ROT>
+                 : mclip_dws_bwd_s1_kernel<K, BwdCfg<K>::NSLOT, BwdCfg<K>::REP, false, BwdCfg<K>::NS, BwdCfg<K>::ROT>;
   static bool attr[2] = {false, false};
   if (!attr[bn]) { MCLIP_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, BwdCfg<K>::SMEM)); attr[bn] = true; }
   kern<<<p.n_chunks * p.slots, BwdCfg<K>::NS * 64, BwdCfg<K>::SMEM, stream>>>(tmIn, tmDy, p);
