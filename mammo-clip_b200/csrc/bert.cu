@@ -195,6 +195,8 @@ extern "C" int mclip_bert_attention(const void* qkv, const void* attention_mask,
                                     int batch, int seq_len, int heads, int head_dim, void* stream) {
   MCLIP_REQUIRE(qkv && attention_mask && out && batch > 0 && seq_len > 0, "mclip_bert_attention: bad arguments");
   MCLIP_REQUIRE(head_dim == ATT_D, "mclip_bert_attention: head_dim %d not built (64 only)", head_dim);
+  if (mclip_att_tc_covers(seq_len, heads, head_dim))
+    return mclip_att_tc_forward(qkv, attention_mask, dropmask, drop_scale, out, lse, batch, seq_len, heads, stream);
   dim3 grid(ceil_div(seq_len, ATT_BQ), heads, batch);
   mclip_bert_attention_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const bf16*)qkv, (const long long*)attention_mask, (const uint8_t*)dropmask, drop_scale,
                                                                       (bf16*)out, lse, batch, seq_len, heads);
@@ -746,6 +748,8 @@ extern "C" int mclip_bert_attention_backward(const void* qkv, const void* d_out,
                                              void* stream) {
   MCLIP_REQUIRE(qkv && d_out && lse && attention_mask && delta_ws && dqkv && batch > 0 && seq_len > 0, "mclip_bert_attention_backward: bad arguments");
   MCLIP_REQUIRE(head_dim == ATT_D, "mclip_bert_attention_backward: head_dim %d not built (64 only)", head_dim);
+  if (mclip_att_tc_covers(seq_len, heads, head_dim))
+    return mclip_att_tc_backward(qkv, d_out, lse, attention_mask, dropmask, drop_scale, dqkv, batch, seq_len, heads, stream);
   static int attr_set = 0;
   if (!attr_set) {
     MCLIP_CHECK_CUDA(cudaFuncSetAttribute(mclip_bert_attention_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(AttBwdSmem)));
