@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Benchmark of the Mammo-CLIP contrastive pre-training step (BASELINE.json metric: image-text pairs/sec).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference|oracle-gpu] [--workload c3|c2|c1|c3-mvs|loss-sweep]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference|oracle-gpu] [--workload c3|c2|c1|c3-mvs|c3-eval|loss-sweep]
 
 One step = forward (EfficientNet + BERT + projection heads + L2-norm) + fused InfoNCE (+ NVLink gather) + backward +
 gradient all-reduce (N>1) + AdamW, on synthetic data of the named shape with seeded random-init weights.
@@ -403,6 +403,94 @@ def run_loss_sweep(args):
 
 
 # ------------------------------------------------------------------------------------------------------------------
+def run_eval(args):
+    """Inference / evaluation edge (the reference's evaluator.py:126-171 calls encode_image / encode_text under
+    torch.no_grad() in eval mode): embeddings of one batch per step, running-statistics BatchNorm applied by the consumers on
+    load (no separate BN pass, nothing saved for a backward).  value = pairs embedded per second, device-resident inputs;
+    e2e = uint8 images + tokens from pinned host memory in, both embedding matrices back to the host, inside the timed region."""
+    import torch
+    from transformers import BatchEncoding
+    from mammoclip_b200 import _lib
+    from mammoclip_b200.loss import build_loss  # noqa: F401  (same import surface as training)
+    from mammoclip_b200.model import build_model
+    from mammoclip_b200.util import GlobalEnv
+
+    rank, world, local = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        import torch.distributed as dist
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    GlobalEnv.reset()
+    _lib.check(_lib.lib().mclip_device_check(), "mclip_device_check")
+    wl = args.workload[:-5]
+    enc_cfg, enc_name, layers, batch, h, w, L = WORKLOADS[wl]
+    if args.batch:
+        batch = args.batch
+    cfg, loss_cfg = _model_cfg(enc_cfg, layers)
+
+    class Tok:
+        vocab_size = 28996
+
+    torch.manual_seed(0)
+    model = build_model(cfg, loss_cfg, Tok()).to(dev).eval()
+    _, tok_h = _synth_host(batch, 8, 8, L, rank)      # tokens only (the small fp32 image it returns is not used)
+    g8 = torch.Generator().manual_seed(4321 + rank)
+    img8_h = torch.randint(0, 256, (batch, 1, h, w), generator=g8, dtype=torch.uint8).pin_memory()
+    img_d = img8_h.to(dev)
+    tok_d = BatchEncoding({k: v.to(dev) for k, v in tok_h.items()})
+    out_h = {k: torch.empty(batch, 512, dtype=torch.float32).pin_memory() for k in ("image_embeddings", "text_embeddings")}
+
+    def step(images, tokens):
+        with torch.no_grad():
+            return model({"images": images, "text_tokens": tokens}, dev)
+
+    def step_e2e():
+        images = img8_h.to(dev, non_blocking=True)
+        tokens = BatchEncoding({k: v.to(dev, non_blocking=True) for k, v in tok_h.items()})
+        out = step(images, tokens)
+        for k, buf in out_h.items():
+            buf.copy_(out[k], non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        step(img_d, tok_d)
+    torch.cuda.synchronize()
+    _lib.PROF.reset()
+    _lib.PROF.enable([])
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ms_total = _timed_events(lambda: step(img_d, tok_d), args.steps, barrier, dev, world)
+    clocks = sampler.stop() if rank == 0 else None
+    launches = _lib.PROF.launches()
+    step_e2e()
+    e2e_steps = max(2, min(args.steps, 10))
+    ms_e2e = _timed_events(step_e2e, e2e_steps, barrier, dev, world)
+    if rank == 0:
+        ms_step = ms_total / args.steps
+        pairs = batch * world
+        h2d = img8_h.numel() + sum(v.numel() * 8 for v in tok_h.values())
+        print(json.dumps({
+            "metric": "image-text pairs embedded/sec (eval mode, forward only)", "value": pairs / (ms_step * 1e-3), "unit": "pairs/s", "n_gpus": world,
+            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": f"{args.workload}: {enc_name} + BERT-{layers}L (random init), batch {batch}/GPU, {h}x{w} uint8 single-channel images, {L}-token text, "
+                                   "eval mode under no_grad: image + text embeddings (encode_image / encode_text / projection / L2-norm), running-statistics "
+                                   "BatchNorm folded into the consumers' loads", "parallelism": f"dp{world}", "l2": "inputs and activations larger than L2; no explicit flush"},
+            "clocks": clocks, "gpu_launches": launches,
+            "e2e": {"value": pairs / (ms_e2e / e2e_steps * 1e-3), "unit": "pairs/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 2 * batch * 512 * 4, "steps": e2e_steps}}))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+# ------------------------------------------------------------------------------------------------------------------
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -617,13 +705,15 @@ def main():
     ap.add_argument("--e2e-fp32", action="store_true", help="end-to-end leg copies the reference-shaped 3 x fp32 images instead of the uint8 input edge")
     ap.add_argument("--compile", action="store_true", help="oracle-gpu only: wrap the model in torch.compile")
     ap.add_argument("--checkpoint", action="store_true", help="oracle-gpu only: recompute every MBConv block in the backward so that the metric batch fits")
-    ap.add_argument("--workload", default="c3", choices=list(WORKLOADS) + ["loss-sweep", "c3-mvs"])
+    ap.add_argument("--workload", default="c3", choices=list(WORKLOADS) + ["loss-sweep", "c3-mvs", "c3-eval", "c2-eval"])
     ap.add_argument("--batch", type=int, default=0, help="debug only: override the per-GPU batch of the workload")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--ncu-range", action="store_true", help="run warm-up, then ONE step inside cudaProfilerStart/Stop and exit (ncu launch list)")
     args = ap.parse_args()
     if args.workload == "loss-sweep":
         run_loss_sweep(args)
+    elif args.workload.endswith("-eval") and args.impl == "ours":
+        run_eval(args)
     elif args.impl == "reference":
         run_reference(args)
     elif args.impl == "oracle-gpu":
