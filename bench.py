@@ -387,15 +387,37 @@ def run_loss_sweep(args):
                 fn()
             res[name] = _timed_events(fn, args.steps, barrier, dev, world) / args.steps * 1e3      # us per fwd+bwd call
         recv = (world - 1) * 2 * B * 512 * 4
+        # transfer window of the fused kernel on this rank: first push of the local slab -> last remote arrival flag seen
+        win_us = None
+        if world > 1:
+            import ctypes
+            from mammoclip_b200 import _lib
+            buf, wins = (ctypes.c_ulonglong * 2)(), []
+            for _ in range(12):
+                barrier()
+                _lib.check(_lib.lib().mclip_loss_window(None, 1), "mclip_loss_window")
+                fused()
+                _lib.check(_lib.lib().mclip_loss_window(buf, 0), "mclip_loss_window")
+                if buf[1] > buf[0]:
+                    wins.append((buf[1] - buf[0]) / 1e3)
+            wins.sort()
+            w_t = torch.tensor([wins[len(wins) // 2] if wins else 0.0], device=dev)
+            dist.all_reduce(w_t, op=dist.ReduceOp.MAX)                   # the slowest rank's median window
+            win_us = w_t.item() or None
         rows.append({"pairs_per_gpu": B, "global_batch": B * world, "fused_us": round(res["fused"], 1), "nccl_torch_us": round(res["nccl_torch"], 1),
                      "recv_bytes_per_rank": recv, "achieved_gbs": round(recv / (res["fused"] * 1e-6) / 1e9, 2) if world > 1 else None,
-                     "frac_of_770": round(recv / (res["fused"] * 1e-6) / 770e9, 4) if world > 1 else None})
+                     "frac_of_770": round(recv / (res["fused"] * 1e-6) / 770e9, 4) if world > 1 else None,
+                     "transfer_window_us": round(win_us, 2) if win_us else None,
+                     "window_gbs": round(recv / (win_us * 1e-6) / 1e9, 1) if win_us else None,
+                     "window_frac_of_900": round(recv / (win_us * 1e-6) / 900e9, 4) if win_us else None})
     if rank == 0:
         print(json.dumps({"metric": "fused gather+InfoNCE calls/sec (fwd+bwd, B=64/GPU)", "value": 1e6 / rows[0]["fused_us"], "unit": "calls/s", "n_gpus": world,
                           "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": rows[0]["fused_us"] / 1e3, "higher_is_better": True, "scaling": "weak",
                           "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                           "config": {"workload": "loss-sweep: L2-normalised [B,512] fp32 embeddings per GPU, contrastive loss fwd+bwd incl. the gather (BASELINE config 5)",
-                                     "note": "time per call includes the host launch; achieved_gbs = bytes received per rank / call time (whole call, not only the transfer)"},
+                                     "note": "time per call includes the host launch; achieved_gbs = bytes received per rank / call time (whole call, not only the transfer); "
+                                             "transfer_window_us = %globaltimer from the first push of the local slab to the last remote arrival flag observed on the same "
+                                             "rank (median of 12 calls, max over ranks; includes the skew between ranks' kernel starts); window_gbs = bytes received / window"},
                           "p2p_parity": None if parity is None else {"status": "ok" if parity < 1e-3 else "FAILED", "worst_rel_err": parity},
                           "sweep": rows}))
     if world > 1:

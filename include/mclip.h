@@ -59,6 +59,9 @@ typedef struct mclip_loss_args {
 long long mclip_loss_workspace_bytes(int world, int batch, int dim, int n_pairs);
 int mclip_loss_grid(int world, int batch, int n_pairs);
 int mclip_contrastive_loss(const mclip_loss_args* args, void* stream);
+/* Measurement hook (bench.py --workload loss-sweep): out2 (host, may be NULL) receives {earliest push start, latest remote-flag
+   observation} in ns of %globaltimer over the calls since the last reset; then resets and switches the recording on/off. */
+int mclip_loss_window(unsigned long long* out2, int enable);
 
 /* Peer-mapped buffers for world > 1 (cudaMalloc + CUDA IPC; handles are 64 bytes, exchanged by the host). */
 int mclip_ipc_alloc(long long bytes, void** out);          /* zero-filled */

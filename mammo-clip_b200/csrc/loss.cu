@@ -59,7 +59,29 @@ struct LossDev {
   float* out;        // [2 + 2P]: loss, dscale, then per pair (row CE mean, col CE mean)
   int* status;       // device int or nullptr: 1 + rank of a peer that never arrived
   long long timeout_cycles;
+  int window;        // record the transfer window (mclip_loss_win)
 };
+
+// Transfer-window instrumentation (bench.py --workload loss-sweep; SURVEY 8d "first remote store to last flag observed"):
+// [0] = earliest %globaltimer at which a CTA of this rank started pushing, [1] = latest %globaltimer at which a tile of this
+// rank saw the arrival counter of a REMOTE source reach its target.  Off unless mclip_loss_window(.., enable) switched it on.
+__device__ unsigned long long mclip_loss_win[2];
+static int g_loss_window = 0;
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+extern "C" int mclip_loss_window(unsigned long long* out2, int enable) {
+  g_loss_window = enable;
+  if (out2) {
+    MCLIP_CHECK_CUDA(cudaDeviceSynchronize());
+    MCLIP_CHECK_CUDA(cudaMemcpyFromSymbol(out2, mclip_loss_win, 2 * sizeof(unsigned long long)));
+  }
+  const unsigned long long init[2] = {~0ull, 0ull};
+  MCLIP_CHECK_CUDA(cudaMemcpyToSymbol(mclip_loss_win, init, sizeof(init)));
+  return MCLIP_OK;
+}
 
 __device__ __forceinline__ unsigned int ld_acquire_sys(const unsigned int* p) {
   unsigned int v;
@@ -86,6 +108,7 @@ __device__ __forceinline__ void wait_sources(const LossDev& p, int r0, int r1) {
         }
         __nanosleep(200);
       }
+      if (p.window) atomicMax(&mclip_loss_win[1], globaltimer_ns());
     }
   }
   __syncthreads();
@@ -159,6 +182,7 @@ __global__ void __launch_bounds__(LOSS_THREADS) mclip_loss_kernel(const LossDev 
 
   // ---------------- phase 0: push the local slab to every rank's gather buffer ----------------
   if (p.W > 1) {
+    if (p.window && tid == 0) atomicMin(&mclip_loss_win[0], globaltimer_ns());
     const int vecs = B * D / 4;   // float4 per tensor
     for (int dst = 0; dst < p.W; ++dst) {
       int peer = (p.rank + dst) % p.W;   // stagger destinations across ranks
@@ -447,6 +471,7 @@ extern "C" int mclip_contrastive_loss(const mclip_loss_args* a, void* stream_) {
     }
     p.timeout_cycles = (long long)(secs * (double)khz * 1e3);
   }
+  p.window = g_loss_window;
   void* kargs[] = {(void*)&p};
   MCLIP_CHECK_CUDA(cudaLaunchCooperativeKernel((void*)mclip_loss_kernel, dim3(grid), dim3(LOSS_THREADS), kargs, 0, stream));
   return MCLIP_OK;
