@@ -110,9 +110,14 @@ struct DwsIter {
 };
 
 // compile-time configuration of the forward kernel for (kernel size, stride)
-template <int K, int S>
+// CG = channels per lane group: 64 (a warp = 32 lanes x 2 channels of ONE 4-column strip) or 16 (a warp = 4 groups of 8 lanes, each
+// group a different 5-column sub-strip of the same 16 channels: the C <= 48 layers of blocks 0-2 would leave 25-62 % of the lanes idle
+// with 64-channel chunks).  A pixel is CG*2 bytes in shared memory; 5-column sub-strips start 5*32 bytes apart, so the four groups of a
+// warp hit four different 32-byte bank groups on every load (4-column strips would all hit the same one).
+template <int K, int S, int CG = 64>
 struct FwdCfg {
-  static constexpr int SW = 4, NW = 4, TW = SW * NW;
+  static constexpr int SUBS = 64 / CG, LPG = CG / 2, PIXB = CG * 2;      // sub-strips per warp, lanes per group, bytes per pixel
+  static constexpr int SW = CG == 64 ? 4 : 5, NW = 4, TW = SW * SUBS * NW;
   static constexpr int NA = (K + S - 1) / S;         // live accumulator rows: output row oy lives in slot oy % NA
   static constexpr int G = S * NA;                   // input rows per fully unrolled group (all slot roles static)
   static constexpr int REP = (S == 1 && K == 3) ? DWS_K3_REP : (S == 1 ? DWS_K5_REP : 1);
@@ -120,21 +125,24 @@ struct FwdCfg {
   static constexpr int IW = (TW - 1) * S + K, PC = (SW - 1) * S + K;
   static constexpr int NSLOT = (S == 1) ? (K == 3 ? DWS_K3_NSLOT : DWS_K5_NSLOT) : (K == 3 ? 3 : 2);
   static constexpr int CTAS = (S == 1) ? (K == 3 ? DWS_K3_CTAS : DWS_K5_CTAS) : (K == 3 ? 4 : 3);
-  static constexpr int SMEM = NSLOT * RB * IW * 128;
+  static constexpr int SMEM = NSLOT * RB * IW * PIXB;
+  static_assert((RB * IW * PIXB) % 128 == 0, "ring slots must stay 128-byte aligned for TMA");
 };
 
-template <int K, int S, bool ACT>
-__global__ void __launch_bounds__(128, FwdCfg<K, S>::CTAS) mclip_dws_fwd_kernel(const __grid_constant__ CUtensorMap tmIn, const DwsDev p) {
-  using Cfg = FwdCfg<K, S>;
+template <int K, int S, bool ACT, int CG>
+__global__ void __launch_bounds__(128, FwdCfg<K, S, CG>::CTAS) mclip_dws_fwd_kernel(const __grid_constant__ CUtensorMap tmIn, const DwsDev p) {
+  using Cfg = FwdCfg<K, S, CG>;
   constexpr int SW = Cfg::SW, NW = Cfg::NW, TW = Cfg::TW, IW = Cfg::IW, PC = Cfg::PC, RB = Cfg::RB, NA = Cfg::NA, G = Cfg::G, REP = Cfg::REP, NSLOT = Cfg::NSLOT;
-  constexpr uint32_t ROW_BYTES = IW * 128, SLOT_BYTES = RB * ROW_BYTES;
+  constexpr int SUBS = Cfg::SUBS, LPG = Cfg::LPG;
+  constexpr uint32_t PIXB = Cfg::PIXB, ROW_BYTES = IW * PIXB, SLOT_BYTES = RB * ROW_BYTES;
   extern __shared__ __align__(1024) uint8_t dws_smem[];
   __shared__ float red[NW][4][32];
   __shared__ __align__(8) uint64_t full[NSLOT];
   __shared__ uint32_t arrivals[NSLOT];               // monotonic: arrival number a of a slot is the last of its round iff a % NW == NW-1
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int chunk = blockIdx.x % p.n_chunks, slot = blockIdx.x / p.n_chunks;
-  const int c0 = chunk * 64, c = c0 + lane * 2;
+  const int sub = lane / LPG, gl = lane % LPG;        // lane group (sub-strip) and lane within the group
+  const int c0 = chunk * CG, c = c0 + gl * 2;
   const bool cvalid = c < p.C;
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tmIn);
@@ -201,7 +209,7 @@ __global__ void __launch_bounds__(128, FwdCfg<K, S>::CTAS) mclip_dws_fwd_kernel(
 #pragma unroll 1
   for (; ci.item < my_items; ++ci.item) {
     load_item(ci);
-    const int wx = ci.x0 + warp * SW;                // first output column of this warp
+    const int wx = ci.x0 + (warp * SUBS + sub) * SW;  // first output column of this lane group
     const bool wactive = wx < p.Wo;
     // validity masks of the warp's PC input columns / SW output columns
     uint32_t inmask = 0, outmask = 0;
@@ -230,7 +238,7 @@ __global__ void __launch_bounds__(128, FwdCfg<K, S>::CTAS) mclip_dws_fwd_kernel(
         float2 x[PC];
 #pragma unroll
         for (int ix = 0; ix < PC; ++ix) {
-          float2 h = ffma2r(bf2_to_f2(lds32(base + s * ROW_BYTES + ix * 128)), a2, b2);
+          float2 h = ffma2r(bf2_to_f2(lds32(base + s * ROW_BYTES + ix * PIXB)), a2, b2);
           if (ACT) h = ffma2r(h, make_float2(fast_tanh(h.x), fast_tanh(h.y)), h);
           x[ix] = h;
         }
@@ -290,7 +298,7 @@ __global__ void __launch_bounds__(128, FwdCfg<K, S>::CTAS) mclip_dws_fwd_kernel(
 #endif
 #pragma unroll 1
         for (int rep = 0; rep < REP; ++rep) {
-          const uint32_t base = ring + (uint32_t)sl * SLOT_BYTES + (uint32_t)(rep * G) * ROW_BYTES + (uint32_t)(warp * SW * S) * 128u + (uint32_t)lane * 4u;
+          const uint32_t base = ring + (uint32_t)sl * SLOT_BYTES + (uint32_t)(rep * G) * ROW_BYTES + (uint32_t)((warp * SUBS + sub) * SW * S) * PIXB + (uint32_t)gl * 4u;
           const int j0 = blk * RB + rep * G;         // local step of position s = 0
           // all G input rows inside the image and every output row completing in this group inside the segment?
           // (first completion: step >= K-1; last completing output: (j0 + G - 1 - (K-1)) / S rounded down to a completion step)
@@ -337,10 +345,15 @@ __global__ void __launch_bounds__(128, FwdCfg<K, S>::CTAS) mclip_dws_fwd_kernel(
   if (p.stats) {
     red[warp][0][lane] = s_sum.x; red[warp][1][lane] = s_sum.y; red[warp][2][lane] = s_sq.x; red[warp][3][lane] = s_sq.y;
     __syncthreads();
-    if (warp == 0 && cvalid) {
+    if (warp == 0 && cvalid && sub == 0) {
       float a = 0.f, b = 0.f, cc = 0.f, d = 0.f;
 #pragma unroll
-      for (int w2 = 0; w2 < NW; ++w2) { a += red[w2][0][lane]; b += red[w2][1][lane]; cc += red[w2][2][lane]; d += red[w2][3][lane]; }
+      for (int w2 = 0; w2 < NW; ++w2)
+#pragma unroll
+        for (int s2 = 0; s2 < SUBS; ++s2) {
+          const int l2 = s2 * LPG + gl;
+          a += red[w2][0][l2]; b += red[w2][1][l2]; cc += red[w2][2][l2]; d += red[w2][3][l2];
+        }
       float* stp = p.stats + (size_t)slot * 2 * p.C;
       stp[c] = a; stp[c + 1] = b; stp[p.C + c] = cc; stp[p.C + c + 1] = d;
     }
@@ -358,10 +371,12 @@ __global__ void __launch_bounds__(128, FwdCfg<K, S>::CTAS) mclip_dws_fwd_kernel(
 #ifndef DWS_BWD_NSLOT
 #define DWS_BWD_NSLOT 3
 #endif
-template <int K, int NSLOT, int REP, bool BN, int NS, bool ROT>
+template <int K, int NSLOT, int REP, bool BN, int NS, bool ROT, int CG>
 __global__ void __launch_bounds__(NS * 64, NS == 4 ? 2 : 3) mclip_dws_bwd_s1_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constant__ CUtensorMap tmDy, const DwsDev p) {
-  constexpr int SW = 4, NW = 2 * NS, TW = SW * NS, IW = TW + K - 1, PC = SW + K - 1, RB = K * REP, KK = K;
-  constexpr uint32_t ROW_BYTES = IW * 128, PART_BYTES = RB * ROW_BYTES, SLOT_BYTES = 2 * PART_BYTES;
+  constexpr int SUBS = 64 / CG, LPG = CG / 2;          // lane groups per warp / lanes per group (see FwdCfg)
+  constexpr int SW = CG == 64 ? 4 : 5, NW = 2 * NS, TW = SW * SUBS * NS, IW = TW + K - 1, PC = SW + K - 1, RB = K * REP, KK = K;
+  constexpr uint32_t PIXB = CG * 2, ROW_BYTES = IW * PIXB, PART_BYTES = RB * ROW_BYTES, SLOT_BYTES = 2 * PART_BYTES;
+  static_assert(PART_BYTES % 128 == 0, "ring parts must stay 128-byte aligned for TMA");
   extern __shared__ __align__(1024) uint8_t dws_smem[];
   __shared__ float red[NS][4][32];
   __shared__ __align__(8) uint64_t full[NSLOT];
@@ -372,7 +387,8 @@ __global__ void __launch_bounds__(NS * 64, NS == 4 ? 2 : 3) mclip_dws_bwd_s1_ker
   const int strip = NS == 2 ? (warp >> 1) : (warp % NS);
   const bool wrole = NS == 2 ? (((warp ^ blockIdx.x) & 1) == 0) : (warp < NS);
   const int chunk = blockIdx.x % p.n_chunks, slot = blockIdx.x / p.n_chunks;
-  const int c0 = chunk * 64, c = c0 + lane * 2;
+  const int sub = lane / LPG, gl = lane % LPG;
+  const int c0 = chunk * CG, c = c0 + gl * 2;
   const bool cvalid = c < p.C;
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tmIn); tma_prefetch_desc(&tmDy);
@@ -441,7 +457,7 @@ __global__ void __launch_bounds__(NS * 64, NS == 4 ? 2 : 3) mclip_dws_bwd_s1_ker
 #pragma unroll 1
   for (; ci.item < my_items; ++ci.item) {
     load_item(ci);
-    const int wx = ci.x0 + strip * SW;
+    const int wx = ci.x0 + (strip * SUBS + sub) * SW;
     const bool wactive = wx < p.W;
     uint32_t inmask = 0, outmask = 0;
 #pragma unroll
@@ -467,7 +483,7 @@ __global__ void __launch_bounds__(NS * 64, NS == 4 ? 2 : 3) mclip_dws_bwd_s1_ker
       const int oy = t + p.pt;
       if (FAST || (oy >= ci.r0 && oy < r1)) {
 #pragma unroll
-        for (int o = 0; o < SW; ++o) acc[r][o] = bf2_to_f2(lds32(gbase + r * ROW_BYTES + (K - 1 + o) * 128 - p.pl * 128));
+        for (int o = 0; o < SW; ++o) acc[r][o] = bf2_to_f2(lds32(gbase + r * ROW_BYTES + (K - 1 + o) * PIXB - p.pl * PIXB));
       } else {
 #pragma unroll
         for (int o = 0; o < SW; ++o) acc[r][o] = make_float2(0.f, 0.f);
@@ -476,7 +492,7 @@ __global__ void __launch_bounds__(NS * 64, NS == 4 ? 2 : 3) mclip_dws_bwd_s1_ker
         float2 x[PC];
 #pragma unroll
         for (int ix = 0; ix < PC; ++ix) {
-          float2 h = ffma2r(bf2_to_f2(lds32(ybase + r * ROW_BYTES + ix * 128)), a2, b2);
+          float2 h = ffma2r(bf2_to_f2(lds32(ybase + r * ROW_BYTES + ix * PIXB)), a2, b2);
           if (BN) h = ffma2r(h, make_float2(fast_tanh(h.x), fast_tanh(h.y)), h);
           x[ix] = h;
         }
@@ -501,7 +517,7 @@ __global__ void __launch_bounds__(NS * 64, NS == 4 ? 2 : 3) mclip_dws_bwd_s1_ker
       constexpr int r = decltype(r_c)::value;
       float2 x[PC];                                    // dY[t+pt][wx + pl - (K-1) + j]; TMA zero-fills rows/columns outside dY
 #pragma unroll
-      for (int j = 0; j < PC; ++j) x[j] = bf2_to_f2(lds32(gbase + r * ROW_BYTES + j * 128));
+      for (int j = 0; j < PC; ++j) x[j] = bf2_to_f2(lds32(gbase + r * ROW_BYTES + j * PIXB));
 #pragma unroll
       for (int q = 0; q < K; ++q) {
         const int ky = (q - r + KK) % KK;              // slot q completes ky steps ahead: input row t+ky takes tap row ky
@@ -521,7 +537,7 @@ __global__ void __launch_bounds__(NS * 64, NS == 4 ? 2 : 3) mclip_dws_bwd_s1_ker
           float2 d = acc[r][o];
           if (BN) {
             // dv = dA * swish'(v), v = a*y+b; swish'(v) = s + s(1-s)v with s = sigma(v) = 0.5 + 0.5 tanh(v/2)
-            const float2 yv = bf2_to_f2(lds32(ybase + r * ROW_BYTES + (o * 128) + p.pl * 128));
+            const float2 yv = bf2_to_f2(lds32(ybase + r * ROW_BYTES + (o * PIXB) + p.pl * PIXB));
             const float2 hv = ffma2r(yv, a2, b2);                                          // v / 2
             const float2 sg = ffma2r(make_float2(fast_tanh(hv.x), fast_tanh(hv.y)), half2, half2);
             const float2 om = ffma2r(sg, neg1, one);                                       // 1 - s
@@ -543,7 +559,7 @@ __global__ void __launch_bounds__(NS * 64, NS == 4 ? 2 : 3) mclip_dws_bwd_s1_ker
         // ROT: ONE step body per role (the K-times unrolled static-role bodies of k5 are 5500 SASS instructions, and the two roles
         // thrash the instruction caches: 38 % of the stall samples were no_instruction); the rolling window / accumulator rows
         // are rotated with register moves instead (16 float2 per 100 FFMA2)
-        const uint32_t sbase = ring + (uint32_t)s * SLOT_BYTES + (uint32_t)lane * 4u + (uint32_t)(strip * SW) * 128u;
+        const uint32_t sbase = ring + (uint32_t)s * SLOT_BYTES + (uint32_t)gl * 4u + (uint32_t)((strip * SUBS + sub) * SW) * PIXB;
         const int tb = t0 + blk * RB;                  // input row of the block's first step
         // one loop per (role, fast/edge) so that the rotation's register moves are not doubled by branch joins inside the loop
         auto wloop = [&](auto fast_c) {
@@ -580,8 +596,8 @@ __global__ void __launch_bounds__(NS * 64, NS == 4 ? 2 : 3) mclip_dws_bwd_s1_ker
       } else if (wactive) {
 #pragma unroll 1
         for (int rep = 0; rep < REP; ++rep) {
-          const uint32_t sbase = ring + (uint32_t)s * SLOT_BYTES + (uint32_t)(rep * K) * ROW_BYTES + (uint32_t)lane * 4u;
-          const uint32_t ybase = sbase + (uint32_t)(strip * SW) * 128u, gbase = ybase + PART_BYTES;
+          const uint32_t sbase = ring + (uint32_t)s * SLOT_BYTES + (uint32_t)(rep * K) * ROW_BYTES + (uint32_t)gl * 4u;
+          const uint32_t ybase = sbase + (uint32_t)((strip * SUBS + sub) * SW) * PIXB, gbase = ybase + PART_BYTES;
           const int t = t0 + blk * RB + rep * K;       // input row of step r = 0 of this group
           if (wrole) {
             const bool fast = warp_fast && t >= 0 && t + K <= p.H && t + p.pt >= ci.r0 && t + p.pt + K <= r1;
@@ -644,19 +660,26 @@ __global__ void __launch_bounds__(NS * 64, NS == 4 ? 2 : 3) mclip_dws_bwd_s1_ker
     red[strip][0][lane] = bs.x; red[strip][1][lane] = bs.y; red[strip][2][lane] = bq.x; red[strip][3][lane] = bq.y;
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < K * K * 64; i += NS * 64) {
-    const int t = i / 64, ch = i % 64;
+  for (int i = threadIdx.x; i < K * K * CG; i += NS * 64) {
+    const int t = i / CG, ch = i % CG;
     if (c0 + ch < p.C) {
       float s2 = 0.f;
 #pragma unroll
-      for (int w2 = 0; w2 < NS; ++w2) s2 += wred[((size_t)w2 * K * K + t) * 64 + ch];
+      for (int w2 = 0; w2 < NS; ++w2)
+#pragma unroll
+        for (int g2 = 0; g2 < SUBS; ++g2) s2 += wred[((size_t)w2 * K * K + t) * 64 + g2 * CG + ch];      // lane l of a warp wrote floats 2l, 2l+1
       p.dw_part[((size_t)slot * K * K + t) * p.C + c0 + ch] = s2;
     }
   }
-  if (BN && p.bn_part && warp == 0 && cvalid) {
+  if (BN && p.bn_part && warp == 0 && cvalid && sub == 0) {
     float a = 0.f, b = 0.f, cc = 0.f, d = 0.f;
 #pragma unroll
-    for (int w2 = 0; w2 < NS; ++w2) { a += red[w2][0][lane]; b += red[w2][1][lane]; cc += red[w2][2][lane]; d += red[w2][3][lane]; }
+    for (int w2 = 0; w2 < NS; ++w2)
+#pragma unroll
+      for (int g2 = 0; g2 < SUBS; ++g2) {
+        const int l2 = g2 * LPG + gl;
+        a += red[w2][0][l2]; b += red[w2][1][l2]; cc += red[w2][2][l2]; d += red[w2][3][l2];
+      }
     float* st = p.bn_part + (size_t)slot * 2 * p.C;
     st[c] = a; st[c + 1] = b; st[p.C + c] = cc; st[p.C + c + 1] = d;
   }
@@ -947,10 +970,10 @@ __global__ void __launch_bounds__(256, 2) mclip_dws_bwd_s2_kernel(const __grid_c
 }
 
 // 4-D tensor map over an NHWC bf16 tensor: dims {C, W, H, N}, box {64 channels, box_w, box_h, 1}, no swizzle.
-int dws_tmap(CUtensorMap* m, const void* ptr, int N, int H, int W, int C, int box_w, int box_h) {
+int dws_tmap(CUtensorMap* m, const void* ptr, int N, int H, int W, int C, int box_w, int box_h, int cg = 64) {
   const unsigned long long dims[4] = {(unsigned long long)C, (unsigned long long)W, (unsigned long long)H, (unsigned long long)N};
   const unsigned long long strides[3] = {(unsigned long long)C * 2, (unsigned long long)W * C * 2, (unsigned long long)H * W * C * 2};
-  const unsigned box[4] = {64u, (unsigned)box_w, (unsigned)box_h, 1u};
+  const unsigned box[4] = {(unsigned)cg, (unsigned)box_w, (unsigned)box_h, 1u};
 #ifndef DWS_L2PROMO
 #define DWS_L2PROMO 2
 #endif
@@ -958,8 +981,8 @@ int dws_tmap(CUtensorMap* m, const void* ptr, int N, int H, int W, int C, int bo
 }
 
 // work decomposition shared by mclip_dws_slots and the launchers
-void dws_plan(const mclip_dwconv_args* a, int ctas_per_sm, int rows_total, DwsDev& p, int TW = 16) {
-  p.n_chunks = ceil_div(a->c, 64);
+void dws_plan(const mclip_dwconv_args* a, int ctas_per_sm, int rows_total, DwsDev& p, int TW = 16, int cg = 64) {
+  p.n_chunks = ceil_div(a->c, cg);
   p.strips_x = ceil_div(a->wo, TW);
   int ctas = (mclip_num_sms() * ctas_per_sm) / p.n_chunks;
   if (ctas < 1) ctas = 1;
@@ -973,13 +996,22 @@ void dws_plan(const mclip_dwconv_args* a, int ctas_per_sm, int rows_total, DwsDe
   p.slots = std::min(ctas, p.items);
 }
 
-template <int K, int S>
+// 16-channel lane groups: the narrow k3 s1 layers (EN-B5 blocks 0-2: C = 48, 24, 24; EN-B2 blocks 0-1: 32, 16)
+// (measured, EN-B5 blocks 0-2 at B = 64: C = 24 forward 1.24 -> 0.77 ms, backward 2.55 -> 1.63 ms; C = 48 backward 2.56 -> 2.33 ms but
+// forward 1.24 -> 1.49 ms: three 16-channel chunks cost more than one 64-channel chunk with a quarter of its lanes idle)
+static int dws_cg(const mclip_dwconv_args* a, bool backward) {
+  static int enabled = -1;
+  if (enabled < 0) { const char* e = getenv("MCLIP_DW_CG16"); enabled = e ? atoi(e) : 1; }
+  return (enabled && a->k == 3 && a->stride == 1 && a->c <= (backward ? 48 : 32) && a->c % 2 == 0) ? 16 : 64;
+}
+
+template <int K, int S, int CG = 64>
 int dws_launch_fwd(const mclip_dwconv_args* a, DwsDev& p, cudaStream_t stream) {
-  using Cfg = FwdCfg<K, S>;
+  using Cfg = FwdCfg<K, S, CG>;
   CUtensorMap tm;
-  int rc = dws_tmap(&tm, p.in, p.N, p.H, p.W, p.C, Cfg::IW, Cfg::RB);
+  int rc = dws_tmap(&tm, p.in, p.N, p.H, p.W, p.C, Cfg::IW, Cfg::RB, CG);
   if (rc) return rc;
-  auto kern = p.act ? mclip_dws_fwd_kernel<K, S, true> : mclip_dws_fwd_kernel<K, S, false>;
+  auto kern = p.act ? mclip_dws_fwd_kernel<K, S, true, CG> : mclip_dws_fwd_kernel<K, S, false, CG>;
   static bool attr[2] = {false, false};
   if (!attr[p.act]) { MCLIP_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM)); attr[p.act] = true; }
   kern<<<p.n_chunks * p.slots, 128, Cfg::SMEM, stream>>>(tm, p);
@@ -988,6 +1020,7 @@ int dws_launch_fwd(const mclip_dwconv_args* a, DwsDev& p, cudaStream_t stream) {
 }
 
 static int dws_fwd_ctas(const mclip_dwconv_args* a) {
+  if (dws_cg(a, false) == 16) return FwdCfg<3, 1, 16>::CTAS;
   if (a->stride == 1) return a->k == 3 ? FwdCfg<3, 1>::CTAS : FwdCfg<5, 1>::CTAS;
   return a->k == 3 ? FwdCfg<3, 2>::CTAS : FwdCfg<5, 2>::CTAS;
 }
@@ -1001,30 +1034,31 @@ static int dws_fwd_ctas(const mclip_dwconv_args* a) {
 #ifndef DWS_BWD_K5_ROT
 #define DWS_BWD_K5_ROT 1
 #endif
-template <int K>
+template <int K, int CG = 64>
 struct BwdCfg {
   static constexpr int NSLOT = DWS_BWD_NSLOT;
   static constexpr int REP = (K == 3) ? 2 : 1;
   static constexpr int NS = (K == 3) ? 4 : DWS_BWD_K5_NS;      // column strips per CTA (k5: 2 -> 128 threads, 3 CTAs/SM at 168 registers, no spills)
   static constexpr int CTAS = NS == 4 ? 2 : 3;
   static constexpr bool ROT = (K == 3) ? (DWS_BWD_K3_ROT != 0) : (DWS_BWD_K5_ROT != 0);
-  static constexpr int TW = 4 * NS, IW = TW + K - 1;
-  static constexpr int RING = NSLOT * 2 * K * REP * IW * 128;
+  static constexpr int TW = (CG == 64 ? 4 : 5) * (64 / CG) * NS, IW = TW + K - 1;
+  static constexpr int RING = NSLOT * 2 * K * REP * IW * CG * 2;
   static constexpr int SMEM = RING > NS * K * K * 64 * 4 ? RING : NS * K * K * 64 * 4;
 };
 
-template <int K>
+template <int K, int CG = 64>
 int dws_launch_bwd_s1(const mclip_dwconv_args* a, DwsDev& p, cudaStream_t stream) {
+  using Cfg = BwdCfg<K, CG>;
   CUtensorMap tmIn, tmDy;
-  int rc = dws_tmap(&tmIn, p.in, p.N, p.H, p.W, p.C, BwdCfg<K>::IW, K * BwdCfg<K>::REP);
+  int rc = dws_tmap(&tmIn, p.in, p.N, p.H, p.W, p.C, Cfg::IW, K * Cfg::REP, CG);
   if (rc) return rc;
-  if ((rc = dws_tmap(&tmDy, p.dy, p.N, p.Ho, p.Wo, p.C, BwdCfg<K>::IW, K * BwdCfg<K>::REP))) return rc;
+  if ((rc = dws_tmap(&tmDy, p.dy, p.N, p.Ho, p.Wo, p.C, Cfg::IW, K * Cfg::REP, CG))) return rc;
   const bool bn = p.scale != nullptr;
-  auto kern = bn ? mclip_dws_bwd_s1_kernel<K, BwdCfg<K>::NSLOT, BwdCfg<K>::REP, true, BwdCfg<K>::NS, BwdCfg<K>::ROT>
-                 : mclip_dws_bwd_s1_kernel<K, BwdCfg<K>::NSLOT, BwdCfg<K>::REP, false, BwdCfg<K>::NS, BwdCfg<K>::ROT>;
+  auto kern = bn ? mclip_dws_bwd_s1_kernel<K, Cfg::NSLOT, Cfg::REP, true, Cfg::NS, Cfg::ROT, CG>
+                 : mclip_dws_bwd_s1_kernel<K, Cfg::NSLOT, Cfg::REP, false, Cfg::NS, Cfg::ROT, CG>;
   static bool attr[2] = {false, false};
-  if (!attr[bn]) { MCLIP_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, BwdCfg<K>::SMEM)); attr[bn] = true; }
-  kern<<<p.n_chunks * p.slots, BwdCfg<K>::NS * 64, BwdCfg<K>::SMEM, stream>>>(tmIn, tmDy, p);
+  if (!attr[bn]) { MCLIP_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM)); attr[bn] = true; }
+  kern<<<p.n_chunks * p.slots, Cfg::NS * 64, Cfg::SMEM, stream>>>(tmIn, tmDy, p);
   MCLIP_CHECK_LAUNCH();
   return MCLIP_OK;
 }
@@ -1053,7 +1087,8 @@ int dws_launch_bwd_s2(const mclip_dwconv_args* a, DwsDev& p, cudaStream_t stream
 }
 
 static void dws_plan_bwd1(const mclip_dwconv_args* a, DwsDev& p) {
-  if (a->k == 3) dws_plan(a, BwdCfg<3>::CTAS, a->h, p, BwdCfg<3>::TW);
+  if (dws_cg(a, true) == 16) dws_plan(a, BwdCfg<3, 16>::CTAS, a->h, p, BwdCfg<3, 16>::TW, 16);
+  else if (a->k == 3) dws_plan(a, BwdCfg<3>::CTAS, a->h, p, BwdCfg<3>::TW);
   else dws_plan(a, BwdCfg<5>::CTAS, a->h, p, BwdCfg<5>::TW);
 }
 
@@ -1089,6 +1124,7 @@ int mclip_dws_slots(const mclip_dwconv_args* a, int backward) {
   dws_fill(a, p);
   if (backward && a->stride == 2) dws_plan_bwd2(a, p);
   else if (backward) dws_plan_bwd1(a, p);
+  else if (dws_cg(a, false) == 16) dws_plan(a, dws_fwd_ctas(a), a->ho, p, FwdCfg<3, 1, 16>::TW, 16);
   else dws_plan(a, dws_fwd_ctas(a), a->ho, p);
   return p.slots;
 }
@@ -1115,6 +1151,7 @@ int mclip_dws_backward(const mclip_dwconv_args* a, void* stream_) {
   if (p.bn_part) MCLIP_REQUIRE(p.mean && p.invstd, "mclip_dwconv_backward: input BN statistics missing");
   int rc;
   if (a->stride == 2) rc = a->k == 3 ? dws_launch_bwd_s2<3>(a, p, stream) : dws_launch_bwd_s2<5>(a, p, stream);
+  else if (dws_cg(a, true) == 16) rc = dws_launch_bwd_s1<3, 16>(a, p, stream);
   else rc = a->k == 3 ? dws_launch_bwd_s1<3>(a, p, stream) : dws_launch_bwd_s1<5>(a, p, stream);
   if (rc) return rc;
   const int KK = a->k * a->k;
@@ -1126,10 +1163,13 @@ int mclip_dws_backward(const mclip_dwconv_args* a, void* stream_) {
 int mclip_dws_forward(const mclip_dwconv_args* a, void* stream_) {
   DwsDev p;
   dws_fill(a, p);
-  dws_plan(a, dws_fwd_ctas(a), a->ho, p);
+  const int cg = dws_cg(a, false);
+  if (cg == 16) dws_plan(a, dws_fwd_ctas(a), a->ho, p, FwdCfg<3, 1, 16>::TW, 16);
+  else dws_plan(a, dws_fwd_ctas(a), a->ho, p);
   p.out = (bf16*)a->out; p.stats = a->stats;
   if (a->stats) MCLIP_REQUIRE(a->stat_slots == p.slots, "mclip_dwconv_forward: stat_slots=%d, expected %d", a->stat_slots, p.slots);
   cudaStream_t st = (cudaStream_t)stream_;
+  if (cg == 16) return dws_launch_fwd<3, 1, 16>(a, p, st);
   if (a->stride == 1) return a->k == 3 ? dws_launch_fwd<3, 1>(a, p, st) : dws_launch_fwd<5, 1>(a, p, st);
   return a->k == 3 ? dws_launch_fwd<3, 2>(a, p, st) : dws_launch_fwd<5, 2>(a, p, st);
 }

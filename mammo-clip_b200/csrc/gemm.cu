@@ -107,15 +107,21 @@ mclip_gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
   uint64_t* full = bars;
   uint64_t* empty = bars + p.stages;
   uint64_t* tfull = bars + 2 * p.stages;
-  uint64_t* tempty = tfull + 2;
-  uint64_t* bfull = tempty + 2;
+  uint64_t* tempty = tfull + 4;
+  uint64_t* bfull = tempty + 4;
+  // TMEM accumulator stages: 2 x 256 columns; 4 x 128 when a tile is one 64-column slab (block_n <= 64).  Such tiles are tiny
+  // (K <= 64 x N <= 64): with two stages the MMA -> commit -> epilogue -> release round trip (~1 us) bounded the whole kernel.
+  const int nst = p.block_n <= 64 ? 4 : 2;
+  const uint32_t st_cols = 512u / (uint32_t)nst;
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bfull + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA); tma_prefetch_desc(&tmB); tma_prefetch_desc(&tmD);
     for (int s = 0; s < p.stages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-    for (int a = 0; a < 2; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], GEMM_EPI_WARPS); }
+    // one 64-column slab per tile (block_n <= 64): the two epilogue warp groups take ALTERNATE tiles (= alternate TMEM stages)
+    // instead of one group idling, so a stage is released by 4 warps
+    for (int a = 0; a < 4; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], p.block_n <= 64 ? GEMM_EPI_WARPS / 2 : GEMM_EPI_WARPS); }
     mbar_init(bfull, 1);
     fence_mbar_init();
   }
@@ -206,7 +212,7 @@ mclip_gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
       for (int mt = mt0; mt < p.m_tiles_total; mt += mt_step) {
         mbar_wait(&tempty[as], aphase ^ 1);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + (uint32_t)as * 256u;
+        const uint32_t d_tmem = tmem_base + (uint32_t)as * st_cols;
         for (int kb = 0; kb < p.k_blocks; ++kb) {
           mbar_wait(&full[stage], phase);
           tc_fence_after();
@@ -220,7 +226,7 @@ mclip_gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
           if (++stage == p.stages) { stage = 0; phase ^= 1; }
         }
         umma_commit(&tfull[as]);
-        as ^= 1; if (as == 0) aphase ^= 1;
+        if (++as == nst) { as = 0; aphase ^= 1; }
       }
     }
   } else {
@@ -231,8 +237,12 @@ mclip_gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
     const int nslabs = (p.block_n + 63) >> 6;
     uint8_t* my_buf = dstage + (size_t)ew * 2 * GEMM_SLAB_BYTES;
     float st_sum[2][2] = {{0.f, 0.f}, {0.f, 0.f}}, st_sq[2][2] = {{0.f, 0.f}, {0.f, 0.f}};
-    int as = 0; uint32_t aphase = 0; int buf = 0;
-    for (int mt = mt0; mt < p.m_tiles_total; mt += mt_step) {
+    const bool split = nslabs == 1;
+    int buf = 0, it = 0;
+    for (int mt = mt0; mt < p.m_tiles_total; mt += mt_step, ++it) {
+      if (split && (it & 1) != h) continue;
+      const int as = it % nst;
+      const uint32_t aphase = (uint32_t)(it / nst) & 1u;
       const int b = mt / p.m_blocks, m0 = (mt % p.m_blocks) * GEMM_BM;
       const int row = m0 + q * 32 + lane;
       const int nvalid = min(32, max(0, p.M - (m0 + q * 32)));
@@ -240,14 +250,14 @@ mclip_gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
       tc_fence_after();
 #pragma unroll
       for (int si = 0; si < 2; ++si) {
-        const int s = h + 2 * si;
+        const int s = split ? si : h + 2 * si;
         if (s >= nslabs) break;
         const int c0 = n0 + s * 64;
         if (c0 >= p.N) break;
         uint8_t* sb = my_buf + (size_t)buf * GEMM_SLAB_BYTES;
         if (lane == 0) tma_store_wait_read1();     // the store issued two slabs ago (same buffer) has drained
         __syncwarp();
-        const uint32_t taddr = tmem_base + (uint32_t)as * 256u + (uint32_t)(s * 64) + ((uint32_t)(q * 32) << 16);
+        const uint32_t taddr = tmem_base + (uint32_t)as * st_cols + (uint32_t)(s * 64) + ((uint32_t)(q * 32) << 16);
         uint32_t r[64];                                       // one 64-column TMEM load and ONE wait per slab
         if (!(p.debug & 4)) tmem_ld64(taddr, r);
         tmem_ld_wait();
@@ -334,13 +344,20 @@ mclip_gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty[as]);
-      as ^= 1; if (as == 0) aphase ^= 1;
     }
+    if (lane == 0) tma_store_wait_all0();
     if (STATS && (MODE != 2 || p.stats)) {
+      if (split) {                     // the h = 1 group hands its partial sums of the same columns to the h = 0 group (fixed order)
+        float* xch = reinterpret_cast<float*>(dstage) + (size_t)q * 128;
+        named_bar_sync(1, 32 * GEMM_EPI_WARPS);                                 // staging is idle: EVERY warp's TMA stores have drained
+        if (h == 1) { xch[lane * 4 + 0] = st_sum[0][0]; xch[lane * 4 + 1] = st_sum[0][1]; xch[lane * 4 + 2] = st_sq[0][0]; xch[lane * 4 + 3] = st_sq[0][1]; }
+        named_bar_sync(1, 32 * GEMM_EPI_WARPS);
+        if (h == 0) { st_sum[0][0] += xch[lane * 4 + 0]; st_sum[0][1] += xch[lane * 4 + 1]; st_sq[0][0] += xch[lane * 4 + 2]; st_sq[0][1] += xch[lane * 4 + 3]; }
+      }
       const int slot = (blockIdx.x / p.n_blocks) * 4 + q;
 #pragma unroll
       for (int si = 0; si < 2; ++si) {
-        const int s = h + 2 * si;
+        const int s = split ? (h == 0 ? si : 2) : h + 2 * si;
         if (s >= nslabs) break;
         const int col = n0 + s * 64 + lane * 2;
         // columns of this n block that belong to a later n block (block_n not a multiple of 64) are skipped
@@ -350,7 +367,6 @@ mclip_gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         }
       }
     }
-    if (lane == 0) tma_store_wait_all0();
   }
   tc_fence_before();
   __syncthreads();

@@ -34,6 +34,8 @@ c1 = torch.zeros(b.cexp, device="cuda")
 xe = torch.randn(n * h * w, b.cin, device="cuda").to(torch.bfloat16)
 we = (torch.randn(b.cexp, b.cin, device="cuda") * 0.1).to(torch.bfloat16)
 wg = (torch.randn(n, b.cout, b.cexp, device="cuda") * 0.1).to(torch.bfloat16)
+dy2 = torch.randn(n * ho * wo, b.cout, device="cuda").to(torch.bfloat16)
+wpt = (torch.randn(b.cexp, b.cout, device="cuda") * 0.1).to(torch.bfloat16)
 fns = {
     "dw_fwd": lambda: ops.dwconv_forward(y0, wdw, b.k, b.s, b.pads, bn=bn0),
     "dw_bwd": lambda: ops.dwconv_backward(y0, wdw, b.k, b.s, b.pads, dy1, dwg, bn=bn0),
@@ -42,6 +44,7 @@ fns = {
     "ew_apply": lambda: ops.ew_backward(1, y1v, bn0, 1, du=dy1.view_as(y1v), gate=gate, dpool=gate, c1=c1, c2=c1),
     "expand": lambda: ops.gemm_tn(xe, we, want_stats=True),
     "project": lambda: ops.gemm_tn(y1v, wg, want_stats=True),
+    "proj_dgrad": lambda: ops.gemm_tn(dy2, wpt),
 }
 for _ in range(a.reps):
     fns[a.op]()

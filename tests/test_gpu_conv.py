@@ -29,6 +29,9 @@ DW_CASES = [  # (N,H,W,C,k,s,pads(l,r,t,b), with_bn)
     (2, 20, 24, 48, 3, 1, (1, 1, 1, 1), True), (2, 33, 17, 144, 3, 2, (0, 1, 0, 1), True), (1, 19, 23, 240, 5, 2, (1, 2, 1, 2), True),
     (2, 24, 16, 384, 5, 1, (2, 2, 2, 2), True), (2, 31, 29, 64, 3, 2, (1, 1, 1, 1), True), (1, 29, 29, 88, 5, 2, (2, 2, 2, 2), True),
     (3, 12, 40, 24, 3, 1, (1, 1, 1, 1), False), (1, 7, 7, 3072, 3, 1, (1, 1, 1, 1), True), (2, 57, 57, 16, 3, 1, (1, 1, 1, 1), False),
+    # narrow k3 s1 layers on 16-channel lane groups (5-column sub-strips, 80-column CTA strips): several strips, ragged right edge
+    (2, 30, 170, 24, 3, 1, (1, 1, 1, 1), False), (1, 40, 95, 48, 3, 1, (1, 1, 1, 1), True), (2, 26, 81, 32, 3, 1, (1, 1, 1, 1), True),
+    (1, 50, 7, 16, 3, 1, (1, 1, 1, 1), True), (2, 64, 240, 24, 3, 1, (1, 1, 1, 1), True),
 ]
 
 
