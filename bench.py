@@ -416,8 +416,8 @@ def run_loss_sweep(args):
                           "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                           "config": {"workload": "loss-sweep: L2-normalised [B,512] fp32 embeddings per GPU, contrastive loss fwd+bwd incl. the gather (BASELINE config 5)",
                                      "note": "time per call includes the host launch; achieved_gbs = bytes received per rank / call time (whole call, not only the transfer); "
-                                             "transfer_window_us = %globaltimer from the first push of the local slab to the last remote arrival flag observed on the same "
-                                             "rank (median of 12 calls, max over ranks; includes the skew between ranks' kernel starts); window_gbs = bytes received / window"},
+                                             "transfer_window_us = %globaltimer from this rank's first push of its slab to the arrival of the LAST remote slab as first observed "
+                                             "on this rank (median of 12 calls, max over ranks; includes the skew between the ranks' kernel starts); window_gbs = bytes received / window"},
                           "p2p_parity": None if parity is None else {"status": "ok" if parity < 1e-3 else "FAILED", "worst_rel_err": parity},
                           "sweep": rows}))
     if world > 1:

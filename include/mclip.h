@@ -55,12 +55,19 @@ typedef struct mclip_loss_args {
    * 600 s, the order of NCCL's watchdog) the kernel stores 1 + <missing rank> in *status (device int, may be NULL), writes NaN
    * to out[0] and finishes; the host raises from the status word (mammoclip_b200.ops checks it on the next call). */
   int* status; double peer_timeout_s;
+  /* ABI 5: LSE exchange for large global batches (world > 1).  lse_all = this rank's [world*batch][2*MCLIP_LOSS_MAX_PAIRS] fp32
+   * table inside the symmetric allocation, peer_lse = device table [W] of every rank's lse_all.  With both set, a rank scores
+   * only its own rows x all columns and all rows x its own columns, pushes its 2*P*B log-sum-exps to the peers (a second arrival
+   * on the same counters, so the whole job must use one mode per buffer set) and reads the others' from the table; NULL = every
+   * rank evaluates the full (W*B)^2 score matrix (ABI 4 behaviour). */
+  float* lse_all; float* const* peer_lse;
 } mclip_loss_args;
 long long mclip_loss_workspace_bytes(int world, int batch, int dim, int n_pairs);
 int mclip_loss_grid(int world, int batch, int n_pairs);
 int mclip_contrastive_loss(const mclip_loss_args* args, void* stream);
-/* Measurement hook (bench.py --workload loss-sweep): out2 (host, may be NULL) receives {earliest push start, latest remote-flag
-   observation} in ns of %globaltimer over the calls since the last reset; then resets and switches the recording on/off. */
+/* Measurement hook (bench.py --workload loss-sweep): out2 (host, may be NULL) receives {earliest push start, arrival of the last
+   remote slab as first observed on this rank} in ns of %globaltimer for the call(s) since the last reset; then resets and switches
+   the recording on/off. */
 int mclip_loss_window(unsigned long long* out2, int enable);
 
 /* Peer-mapped buffers for world > 1 (cudaMalloc + CUDA IPC; handles are 64 bytes, exchanged by the host). */

@@ -33,6 +33,7 @@ class LossArgs(C.Structure):
         ("my_flags", C.c_void_p),
         ("epoch", C.c_longlong),
         ("status", C.c_void_p), ("peer_timeout_s", C.c_double),
+        ("lse_all", C.c_void_p), ("peer_lse", C.c_void_p),
     ]
 
 

@@ -23,6 +23,12 @@
 //   2  local rows x all columns and local columns x all rows: recompute the tile, build G, emit partial dE
 //      (G @ E) and the scalar partials (loss terms, d scale).
 //   3  deterministic fixed-order reduction of the partials into dE_k, loss, per-pair components, d scale.
+//
+// LSE exchange (world > 1, large global batches; ABI 5).  Phase 2 needs the row LSE of the local rows, the column LSE of the local
+// columns AND the LSEs of every other rank's rows / columns.  Without an exchange every rank evaluates the whole (W*B)^2 matrix in
+// phase 1 -- W/2 times more fp32 work than the "cross" (local rows x all columns + all rows x local columns) that yields its own
+// LSEs.  With lse_all set, phase 1 covers only the cross, phase 1b pushes the 2*P*B local LSEs to every peer (second arrival on
+// the same counters) and phase 2 reads the others' from the exchanged table.
 #include "common.cuh"
 #include "mclip_internal.h"
 #include <stdlib.h>
@@ -46,7 +52,10 @@ struct LossDev {
   float* const* peer_all;      // device table [W][K] of peers' gather buffers (W>1)
   unsigned int* const* peer_flags;  // device table [W] of peers' arrival counters (each [W] u32)
   const unsigned int* my_flags;     // this rank's arrival counters [W]
-  unsigned int flag_target;         // epoch * gridDim.x
+  unsigned int flag_target;         // arrivals (per source rank) that complete the embedding push of this call
+  unsigned int flag_target2;        // ... and the LSE push (exchange mode)
+  float* lse_all;                   // [W*B][2*MCLIP_LOSS_MAX_PAIRS]: (row LSE, col LSE) per pair of every global row/column, or nullptr
+  float* const* peer_lse;           // device table [W] of the peers' lse_all
   int pa[MCLIP_LOSS_MAX_PAIRS], pb[MCLIP_LOSS_MAX_PAIRS];
   float w_row[MCLIP_LOSS_MAX_PAIRS], w_col[MCLIP_LOSS_MAX_PAIRS], eps[MCLIP_LOSS_MAX_PAIRS];
   // workspace
@@ -63,9 +72,11 @@ struct LossDev {
 };
 
 // Transfer-window instrumentation (bench.py --workload loss-sweep; SURVEY 8d "first remote store to last flag observed"):
-// [0] = earliest %globaltimer at which a CTA of this rank started pushing, [1] = latest %globaltimer at which a tile of this
-// rank saw the arrival counter of a REMOTE source reach its target.  Off unless mclip_loss_window(.., enable) switched it on.
-__device__ unsigned long long mclip_loss_win[2];
+// [0] = earliest %globaltimer at which a CTA of this rank started pushing; [1 + s] = EARLIEST %globaltimer at which any tile of this
+// rank saw the arrival counter of remote source s complete (the first tile that needs a source polls from the start of phase 1, so
+// this is the arrival as seen here; later observers only find it already set).  Window = max_s [1 + s] - [0].  Off unless
+// mclip_loss_window(.., enable) switched it on.
+__device__ unsigned long long mclip_loss_win[1 + MCLIP_LOSS_MAX_WORLD];
 static int g_loss_window = 0;
 __device__ __forceinline__ unsigned long long globaltimer_ns() {
   unsigned long long t;
@@ -74,12 +85,17 @@ __device__ __forceinline__ unsigned long long globaltimer_ns() {
 }
 extern "C" int mclip_loss_window(unsigned long long* out2, int enable) {
   g_loss_window = enable;
+  unsigned long long w[1 + MCLIP_LOSS_MAX_WORLD];
   if (out2) {
     MCLIP_CHECK_CUDA(cudaDeviceSynchronize());
-    MCLIP_CHECK_CUDA(cudaMemcpyFromSymbol(out2, mclip_loss_win, 2 * sizeof(unsigned long long)));
+    MCLIP_CHECK_CUDA(cudaMemcpyFromSymbol(w, mclip_loss_win, sizeof(w)));
+    out2[0] = w[0];
+    out2[1] = 0;
+    for (int s2 = 0; s2 < MCLIP_LOSS_MAX_WORLD; ++s2)
+      if (w[1 + s2] != ~0ull && w[1 + s2] > out2[1]) out2[1] = w[1 + s2];
   }
-  const unsigned long long init[2] = {~0ull, 0ull};
-  MCLIP_CHECK_CUDA(cudaMemcpyToSymbol(mclip_loss_win, init, sizeof(init)));
+  for (int s2 = 0; s2 < 1 + MCLIP_LOSS_MAX_WORLD; ++s2) w[s2] = ~0ull;
+  MCLIP_CHECK_CUDA(cudaMemcpyToSymbol(mclip_loss_win, w, sizeof(w)));
   return MCLIP_OK;
 }
 
@@ -93,14 +109,14 @@ __device__ __forceinline__ void red_release_sys_add(unsigned int* p, unsigned in
 }
 
 // Wait until the slabs of every source rank that owns rows [r0, r1) have landed in this rank's gather buffer.
-__device__ __forceinline__ void wait_sources(const LossDev& p, int r0, int r1) {
+__device__ __forceinline__ void wait_sources(const LossDev& p, int r0, int r1, unsigned int target) {
   if (p.W == 1) return;
   if (threadIdx.x == 0) {
     int s0 = r0 / p.B, s1 = (min(r1, p.WB) - 1) / p.B;
     for (int s = s0; s <= s1; ++s) {
       if (s == p.rank) continue;   // own slab is written by this very grid before the phase barrier
       long long t0 = clock64();
-      while ((int)(ld_acquire_sys(p.my_flags + s) - p.flag_target) < 0) {
+      while ((int)(ld_acquire_sys(p.my_flags + s) - target) < 0) {
         if (clock64() - t0 > p.timeout_cycles) {   // a peer never arrived: report and finish (no trap: the context survives)
           if (p.status && atomicCAS(p.status, 0, 1 + s) == 0)
             printf("mclip loss: rank %d timed out waiting for the embeddings of rank %d\n", p.rank, s);
@@ -108,7 +124,7 @@ __device__ __forceinline__ void wait_sources(const LossDev& p, int r0, int r1) {
         }
         __nanosleep(200);
       }
-      if (p.window) atomicMax(&mclip_loss_win[1], globaltimer_ns());
+      if (p.window && target == p.flag_target) atomicMin(&mclip_loss_win[1 + s], globaltimer_ns());
     }
   }
   __syncthreads();
@@ -200,14 +216,22 @@ __global__ void __launch_bounds__(LOSS_THREADS) mclip_loss_kernel(const LossDev 
     grid.sync();   // own slab is complete in the local gather buffer
   }
 
-  // ---------------- phase 1: LSE partials over the full score matrix ----------------
+  // ---------------- phase 1: LSE partials over the full score matrix (or, exchange mode, over this rank's cross) ----------------
   {
-    const int per_pair = p.nI32 * p.nJ64;
+    const bool xch = p.lse_all != nullptr;
+    // tile ranges that contain the local rows / columns
+    const int it0 = (p.rank * B) / LT_M, it1 = ((p.rank + 1) * B - 1) / LT_M, nItL = it1 - it0 + 1;
+    const int jt0 = (p.rank * B) / LT_N, jt1 = ((p.rank + 1) * B - 1) / LT_N, nJtL = jt1 - jt0 + 1;
+    const int unitsA = nItL * p.nJ64, unitsB = (p.nI32 - nItL) * nJtL;
+    const int per_pair = xch ? unitsA + unitsB : p.nI32 * p.nJ64;
     for (int u = blockIdx.x; u < p.P * per_pair; u += gridDim.x) {
-      int pr = u / per_pair, r = u % per_pair, it = r / p.nJ64, jt = r % p.nJ64;
+      int pr = u / per_pair, r = u % per_pair, it, jt;
+      if (!xch) { it = r / p.nJ64; jt = r % p.nJ64; }
+      else if (r < unitsA) { it = it0 + r / p.nJ64; jt = r % p.nJ64; }                    // local rows x all columns
+      else { r -= unitsA; it = r / nJtL; if (it >= it0) it += nItL; jt = jt0 + r % nJtL; }   // other rows x local columns
       int x0 = it * LT_M, y0 = jt * LT_N;
-      wait_sources(p, x0, x0 + LT_M);
-      wait_sources(p, y0, y0 + LT_N);
+      wait_sources(p, x0, x0 + LT_M, p.flag_target);
+      wait_sources(p, y0, y0 + LT_N, p.flag_target);
       float acc[2][4];
       score_tile(p.all[p.pa[pr]], x0, WB, p.all[p.pb[pr]], y0, WB, D, p.scale, Xs, Ys, acc);
 #pragma unroll
@@ -239,6 +263,25 @@ __global__ void __launch_bounds__(LOSS_THREADS) mclip_loss_kernel(const LossDev 
       __syncthreads();
     }
   }
+  if (p.lse_all) {
+    // ---------------- phase 1b: combine the local LSEs and push them to every rank ----------------
+    __threadfence();
+    grid.sync();
+    for (int e = blockIdx.x * LOSS_THREADS + tid; e < p.P * B; e += gridDim.x * LOSS_THREADS) {
+      const int pr = e / B, gi = p.rank * B + e % B;
+      const float lr = lse_combine(p.rowpart + ((size_t)pr * WB + gi) * p.nJ64, p.nJ64);
+      const float lc = lse_combine(p.colpart + ((size_t)pr * WB + gi) * p.nI32, p.nI32);
+      for (int dst = 0; dst < p.W; ++dst) {
+        float* o = p.peer_lse[(p.rank + dst) % p.W] + (size_t)gi * (2 * MCLIP_LOSS_MAX_PAIRS) + 2 * pr;
+        *reinterpret_cast<float2*>(o) = make_float2(lr, lc);
+      }
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (tid == 0)
+      for (int peer = 0; peer < p.W; ++peer)
+        if (peer != p.rank) red_release_sys_add(p.peer_flags[peer] + p.rank, 1u);
+  }
   __threadfence();
   grid.sync();
 
@@ -260,8 +303,14 @@ __global__ void __launch_bounds__(LOSS_THREADS) mclip_loss_kernel(const LossDev 
       const int gx0 = p.rank * B + lx0;            // its global index
       const int y0 = jt * LT_N;
       const int nxv = min(LT_M, B - lx0), nyv = min(LT_N, WB - y0);
-      wait_sources(p, y0, y0 + LT_N);
-      if (tid < LT_M) lseX[tid] = (tid < nxv) ? lse_combine(partX + ((size_t)pr * WB + gx0 + tid) * nPX, nPX) : 0.f;
+      wait_sources(p, y0, y0 + LT_N, p.lse_all ? p.flag_target2 : p.flag_target);
+      if (p.lse_all) {                 // exchanged table: [global index][pair][row LSE, col LSE]; X takes side's own kind, Y the other
+        if (tid < LT_M) lseX[tid] = (tid < nxv) ? p.lse_all[(size_t)(gx0 + tid) * (2 * MCLIP_LOSS_MAX_PAIRS) + 2 * pr + side] : 0.f;
+        else if (tid >= 64 && tid < 64 + LT_N) {
+          int c = tid - 64;
+          lseY[c] = (c < nyv) ? p.lse_all[(size_t)(y0 + c) * (2 * MCLIP_LOSS_MAX_PAIRS) + 2 * pr + (1 - side)] : 0.f;
+        }
+      } else if (tid < LT_M) lseX[tid] = (tid < nxv) ? lse_combine(partX + ((size_t)pr * WB + gx0 + tid) * nPX, nPX) : 0.f;
       else if (tid >= 64 && tid < 64 + LT_N) {
         int c = tid - 64;
         lseY[c] = (c < nyv) ? lse_combine(partY + ((size_t)pr * WB + y0 + c) * nPY, nPY) : 0.f;
@@ -450,7 +499,11 @@ extern "C" int mclip_contrastive_loss(const mclip_loss_args* a, void* stream_) {
     p.peer_all = (float* const*)a->peer_gathered;
     p.peer_flags = (unsigned int* const*)a->peer_flags;
     p.my_flags = (const unsigned int*)a->my_flags;
-    p.flag_target = (unsigned int)a->epoch * (unsigned int)grid;
+    p.lse_all = a->lse_all; p.peer_lse = (float* const*)a->peer_lse;
+    if (p.lse_all) MCLIP_REQUIRE(p.peer_lse, "lse_all needs the peer_lse table");
+    const unsigned int per_call = p.lse_all ? 2u : 1u;       // arrivals per CTA and call on each peer's counter
+    p.flag_target = ((unsigned int)a->epoch * per_call - (per_call - 1u)) * (unsigned int)grid;
+    p.flag_target2 = (unsigned int)a->epoch * per_call * (unsigned int)grid;
   }
   char* ws = (char*)a->workspace;
   p.rowpart = (float2*)ws; ws += (size_t)p.P * p.WB * p.nJ64 * 8;
