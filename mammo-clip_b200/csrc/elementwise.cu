@@ -786,27 +786,47 @@ __global__ void __launch_bounds__(256) mclip_bn0_fold_prep_kernel(const mclip_bn
     __syncthreads();
   }
 }
-// bias[j] = - sum_k a[k] c1[k] We[k, j]
-__global__ void mclip_bn0_fold_bias_kernel(const mclip_bn0_fold_args a) {
-  const int j = blockIdx.x * blockDim.x + threadIdx.x;
-  if (j >= a.cin) return;
+// Column reductions over the weight matrices: CTA = 32 columns (lane = column, coalesced rows) x 32 warps striding the reduction
+// index, fixed-order cross-warp sum (deterministic).  (A thread per column walking all Cexp <= 3072 rows alone took 190 us per
+// launch: 10 ms per c3 step for two "tiny" kernels.)
+#define FOLD_WARPS 32
+__device__ __forceinline__ float fold_block_sum(float v, float (*red)[33]) {      // result valid in warp 0
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  red[warp][lane] = v;
+  __syncthreads();
   float s = 0.f;
-  for (int k = 0; k < a.cexp; ++k) s = fmaf(a.scale[k] * a.c1[k], a.we[(size_t)k * a.cin + j], s);
-  a.bias[j] = -s;
+  if (warp == 0)
+#pragma unroll
+    for (int w = 0; w < FOLD_WARPS; ++w) s += red[w][lane];
+  return s;
+}
+// bias[j] = - sum_k a[k] c1[k] We[k, j]
+__global__ void __launch_bounds__(32 * FOLD_WARPS) mclip_bn0_fold_bias_kernel(const mclip_bn0_fold_args a) {
+  __shared__ float red[FOLD_WARPS][33];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int j = blockIdx.x * 32 + lane;
+  float s = 0.f;
+  if (j < a.cin)
+    for (int k = warp; k < a.cexp; k += FOLD_WARPS) s = fmaf(a.scale[k] * a.c1[k], a.we[(size_t)k * a.cin + j], s);
+  s = fold_block_sum(s, red);
+  if (warp == 0 && j < a.cin) a.bias[j] = -s;
 }
 // phase 1: wcat[j, k1pad + i] = bf16(G[i, j]);  bias[j] -= sum_i xbar[i] * bf16(G[i, j])   (the SAME rounded G the GEMM multiplies X by)
-__global__ void mclip_bn0_fold_g_kernel(const mclip_bn0_fold_args a) {
-  const int j = blockIdx.x * blockDim.x + threadIdx.x;
-  if (j >= a.cin) return;
+__global__ void __launch_bounds__(32 * FOLD_WARPS) mclip_bn0_fold_g_kernel(const mclip_bn0_fold_args a) {
+  __shared__ float red[FOLD_WARPS][33];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int j = blockIdx.x * 32 + lane;
   bf16* wcat = (bf16*)a.wcat;
   const float inv = (float)(1.0 / a.count);
   float s = 0.f;
-  for (int i = 0; i < a.cin; ++i) {
-    const bf16 g = __float2bfloat16_rn(a.g[(size_t)i * a.cin + j]);
-    wcat[(size_t)j * a.ldw + a.k1pad + i] = g;
-    s = fmaf(a.sumx[i] * inv, __bfloat162float(g), s);
-  }
-  a.bias[j] -= s;
+  if (j < a.cin)
+    for (int i = warp; i < a.cin; i += FOLD_WARPS) {
+      const bf16 g = __float2bfloat16_rn(a.g[(size_t)i * a.cin + j]);
+      wcat[(size_t)j * a.ldw + a.k1pad + i] = g;
+      s = fmaf(a.sumx[i] * inv, __bfloat162float(g), s);
+    }
+  s = fold_block_sum(s, red);
+  if (warp == 0 && j < a.cin) a.bias[j] -= s;
 }
 // phase 2: gc[j, i] = bf16(XtX[i, j] - sumx[i] sumx[j] / count)     (symmetric; stored as the [N, K] operand of mclip_gemm_tn)
 __global__ void mclip_bn0_fold_center_kernel(const mclip_bn0_fold_args a) {
@@ -833,10 +853,10 @@ extern "C" int mclip_bn0_fold(const mclip_bn0_fold_args* a, int phase, void* str
                   "mclip_bn0_fold phase 0: null operand / bad layout");
     const int tiles = ((a->cin + 31) >> 5) * ((a->k1pad + 31) >> 5);
     mclip_bn0_fold_prep_kernel<<<tiles < 1184 ? tiles : 1184, 256, 0, st>>>(*a);
-    mclip_bn0_fold_bias_kernel<<<ceil_div(a->cin, 64), 64, 0, st>>>(*a);
+    mclip_bn0_fold_bias_kernel<<<ceil_div(a->cin, 32), 32 * FOLD_WARPS, 0, st>>>(*a);
   } else if (phase == 1) {
     MCLIP_REQUIRE(a->g && a->sumx && a->wcat && a->bias, "mclip_bn0_fold phase 1: null operand");
-    mclip_bn0_fold_g_kernel<<<ceil_div(a->cin, 64), 64, 0, st>>>(*a);
+    mclip_bn0_fold_g_kernel<<<ceil_div(a->cin, 32), 32 * FOLD_WARPS, 0, st>>>(*a);
   } else if (phase == 2) {
     MCLIP_REQUIRE(a->g && a->sumx && a->gc, "mclip_bn0_fold phase 2: null operand");
     mclip_bn0_fold_center_kernel<<<ceil_div((long long)a->cin * a->cin, 256), 256, 0, st>>>(*a);
