@@ -85,6 +85,50 @@ def test_comm_free_backward_identity(golden_dir):
         assert rel_err(txt.grad[r * B:(r + 1) * B], torch.from_numpy(z[f"rank{r}::con_eps0.1::dtxt"])) < 1e-4
 
 
+def _lse_exchange_worker(rank, world, port_no, golden_dir):
+    """The data flow of csrc/loss.cu in exchange mode (ABI 5), restated with torch + gloo: a rank scores ONLY its rows x all columns
+    and all rows x its columns, all-gathers the 2*B log-sum-exps it owns, and forms its gradients without any further exchange."""
+    import torch.distributed as dist
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port_no}", rank=rank, world_size=world)
+    z = np.load(os.path.join(golden_dir, "loss_w2_b6.npz"))
+    meta = json.loads(str(z["meta"]))
+    B, s, eps = meta["B"], meta["logit_scale"], 0.1
+    img_all, txt_all = (_embeds(world * B, sd) for sd in meta["seeds"][:2])
+    WB = world * B
+    mine = slice(rank * B, (rank + 1) * B)
+    # phase 0: the gather (here: everybody already holds both slabs); phase 1: the cross only
+    S_rows = s * img_all[mine] @ txt_all.T                 # [B, WB]  local rows x all columns
+    S_cols = s * img_all @ txt_all[mine].T                 # [WB, B]  all rows x local columns
+    lse_row_mine, lse_col_mine = torch.logsumexp(S_rows, 1), torch.logsumexp(S_cols, 0)
+    # phase 1b: exchange (2*B floats per rank)
+    rows, cols = [torch.empty(B) for _ in range(world)], [torch.empty(B) for _ in range(world)]
+    dist.all_gather(rows, lse_row_mine)
+    dist.all_gather(cols, lse_col_mine)
+    lse_row, lse_col = torch.cat(rows), torch.cat(cols)
+    # phase 2: G for (local rows, all columns) and (all rows, local columns) from the exchanged LSEs
+    w_row, w_col = 0.75, 0.25
+    q = torch.full((WB, WB), eps / WB) + (1 - eps) * torch.eye(WB)
+
+    def G(Sblk, rsel, csel):
+        return (w_row * (torch.exp(Sblk - lse_row[rsel, None]) - q[rsel][:, csel]) + w_col * (torch.exp(Sblk - lse_col[None, csel]) - q[rsel][:, csel])) / B
+
+    allr = slice(0, WB)
+    dimg = s * G(S_rows, mine, allr) @ txt_all             # dE_a[i] = scale * sum_j G_ij E_b[j], local i
+    dtxt = s * G(S_cols, allr, mine).T @ img_all           # dE_b[j] = scale * sum_i G_ij E_a[i], local j
+    loss = (w_row * (lse_row_mine - (q[mine] * S_rows).sum(1)).mean() + w_col * (lse_col_mine - (q[:, mine] * S_cols).sum(0)).mean())
+    assert abs(loss.item() - float(z[f"rank{rank}::con_eps0.1::loss"])) < 1e-5
+    assert rel_err(dimg, torch.from_numpy(z[f"rank{rank}::con_eps0.1::dimg"])) < 1e-4
+    assert rel_err(dtxt, torch.from_numpy(z[f"rank{rank}::con_eps0.1::dtxt"])) < 1e-4
+    dist.destroy_process_group()
+
+
+def test_lse_exchange_identity_world2(golden_dir):
+    """World-size-2 gloo run of the loss kernel's LSE-exchange algorithm against the reference's own all_gather / reduce_scatter
+    goldens (loss, dE_img, dE_txt per rank)."""
+    import torch.multiprocessing as mp
+    mp.spawn(_lse_exchange_worker, args=(2, 29741, golden_dir), nprocs=2, join=True)
+
+
 @pytest.mark.parametrize("tag", ["enc_b2_96x64", "enc_b5_80x48"])
 def test_encoder_oracle_matches_reference(golden_dir, tag):
     z = np.load(os.path.join(golden_dir, tag + ".npz"))
