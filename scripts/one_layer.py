@@ -45,6 +45,7 @@ fns = {
     "expand": lambda: ops.gemm_tn(xe, we, want_stats=True),
     "project": lambda: ops.gemm_tn(y1v, wg, want_stats=True),
     "proj_dgrad": lambda: ops.gemm_tn(dy2, wpt),
+    "proj_wgrad": lambda: ops.gemm_wgrad(dy2, y1v.view(n * ho * wo, b.cexp)),
 }
 for _ in range(a.reps):
     fns[a.op]()
