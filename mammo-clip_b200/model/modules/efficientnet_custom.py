@@ -129,6 +129,7 @@ class MBConvBlock(nn.Module):
 import os as _os
 _FOLD_BN0 = [_os.environ.get("MCLIP_FOLD_BN0", "1") != "0"]      # fold the expand conv's BN backward into its dgrad / wgrad GEMM operands
 _UPDATE_RUNNING = [True]      # False during the recompute pass of the multi-view memory plan (the statistics were already folded in)
+_DROP_Y0 = [False]            # "lean" multi-view plan: the expand conv's output is not kept; the backward re-runs that one GEMM
 
 
 def _bn_fin(part, count, bn: _BNParams, training):
@@ -189,6 +190,8 @@ def _block_forward(net, i, x, pending, n, h, w, training, rowscale=None):
     else:
         dw_in, dw_bn = x, None
     y1, st = ops.dwconv_forward(dw_in, blk._depthwise_conv.weight, g.k, g.s, g.pads, bn=dw_bn, want_stats=training)
+    if g.expand and _DROP_Y0[0]:
+        B["y0"] = y0 = dw_in = None       # 41 % of the saved state (37.9 of 92.9 GB per EN-B5 view at B = 64, 1520x912)
     ho, wo = y1.shape[1], y1.shape[2]
     bn1 = _bn_fin(st, n * ho * wo, blk._bn1, training)
     u, pool = ops.ew_forward(y1.view(n, ho * wo, g.cexp), bn=bn1, act=1, write=True, pool=True)
@@ -295,7 +298,10 @@ def _block_backward(net, i, B, dx, n, training, grads, G, S=None):
     grads[pre + "_depthwise_conv.weight"] = ddw
     if g.expand:
         y0, bn0 = B["y0"], B["bn0"]
+        if y0 is None:                    # lean plan: the same GEMM on the same bf16 operands reproduces the forward's tensor bit for bit
+            y0 = ops.gemm_tn(B["x_in"].view(n * h * w, g.cin), wc.bf16[("e", i)]).view(n, h, w, g.cexp)
         dv0, bnp = ops.dwconv_backward(y0, blk._depthwise_conv.weight, g.k, g.s, g.pads, dy1, ddw, bn=bn0)
+        del y0
         dg0, db0 = G(blk._bn0.weight), G(blk._bn0.bias)
         c1, c2 = ops.bn_bwd_finalize(bnp, bn0.count, training, dg0, db0)
         grads[pre + "_bn0.weight"], grads[pre + "_bn0.bias"] = dg0, db0
@@ -575,7 +581,7 @@ class EfficientNet(nn.Module):
         out = _EncoderFn.apply(self, images, scales, mult, as_dict, *params)
         return out if as_dict else out
 
-    def saved_bytes(self, n, h, w):
+    def saved_bytes(self, n, h, w, keep_y0=True):
         """bf16 bytes of the pre-BN tensors one training forward keeps for its backward (the memory plan's unit)."""
         g = self.geom
         pl, pr, pt, pb = g.stem_pads
@@ -584,22 +590,33 @@ class EfficientNet(nn.Module):
         for b in g.blocks:
             l, r, t, bb = b.pads
             ho, wo = (h + t + bb - b.k) // b.s + 1, (w + l + r - b.k) // b.s + 1
-            elems += (h * w * b.cexp if b.expand else 0) + ho * wo * (b.cexp + 2 * b.cout)
+            elems += (h * w * b.cexp if b.expand and keep_y0 else 0) + ho * wo * (b.cexp + 2 * b.cout)
             h, w = ho, wo
         elems += h * w * g.head_out
         return 2 * n * elems
 
     def forward_views(self, views, plan="auto"):
         """Features of several image batches of ONE step (multi-view loss).  plan: "keep" = ordinary forwards (every view's
-        state stays resident), "recompute" = _MultiViewFn, "auto" = recompute iff the kept state would not fit the free HBM."""
+        state stays resident); "lean" = ordinary forwards that do not keep the expand convs' outputs (41 % of the state; each is
+        re-made by one GEMM in the backward: 2 forwards + 2 backwards per step); "recompute" = _MultiViewFn (4 forwards + 2
+        backwards, one view resident at a time); "auto" = the first of these whose state fits the free HBM with 40 GB to spare
+        for the transients.  MCLIP_MVS_PLAN overrides "auto"."""
         views = [self._prep(v) for v in views]
         if plan == "auto":
-            need = sum(self.saved_bytes(v.shape[0], v.shape[2], v.shape[3]) for v in views) if (self.training and torch.is_grad_enabled()) else 0
+            plan = _os.environ.get("MCLIP_MVS_PLAN", "auto")
+        if plan == "auto":
+            grad = self.training and torch.is_grad_enabled()
+            need = sum(self.saved_bytes(v.shape[0], v.shape[2], v.shape[3]) for v in views) if grad else 0
+            lean = sum(self.saved_bytes(v.shape[0], v.shape[2], v.shape[3], keep_y0=False) for v in views) if grad else 0
             free = torch.cuda.mem_get_info(views[0].device)[0] + torch.cuda.memory_reserved(views[0].device) - torch.cuda.memory_allocated(views[0].device)
-            plan = "recompute" if need + (40 << 30) > free else "keep"
+            plan = "keep" if need + (40 << 30) <= free else "lean" if lean + (40 << 30) <= free else "recompute"
         object.__setattr__(self, "last_plan", plan)
-        if plan == "keep" or not (self.training and torch.is_grad_enabled()):
-            return [self.forward(v) for v in views]
+        if plan in ("keep", "lean") or not (self.training and torch.is_grad_enabled()):
+            _DROP_Y0[0] = plan == "lean"
+            try:
+                return [self.forward(v) for v in views]
+            finally:
+                _DROP_Y0[0] = False
         opt = getattr(self, "_flat_optimizer", None)
         draws = []
         for v in views:
