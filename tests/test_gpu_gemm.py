@@ -17,6 +17,8 @@ TN_SHAPES = [
     (1, 128, 64, 64), (1, 256, 16, 24), (1, 1000, 144, 24), (1, 4096, 240, 40), (1, 777, 40, 240),
     (1, 4096, 768, 768), (1, 4096, 3072, 768), (1, 4096, 768, 3072), (1, 2784, 304, 1824), (1, 1392, 1056, 176),
     (1, 33, 512, 2048), (1, 20000, 24, 144), (1, 300, 2048, 512), (1, 128, 1408, 352),
+    # many M tiles per CTA with a shared weight matrix whose [block_n, K] panel fits shared memory: the resident-panel mode
+    (1, 89088, 1824, 304), (1, 60001, 1056, 176), (1, 40000, 768, 128), (3, 30000, 384, 304),
 ]
 
 
@@ -43,7 +45,7 @@ def test_gemm_tn_batched_per_sample_weights():
     assert rel_err(out2.float(), ref2) < 6e-3
 
 
-@pytest.mark.parametrize("m,n,k", [(1000, 144, 24), (5000, 384, 64), (4096, 1824, 304), (257, 96, 16)])
+@pytest.mark.parametrize("m,n,k", [(1000, 144, 24), (5000, 384, 64), (4096, 1824, 304), (257, 96, 16), (89088, 1824, 304), (70000, 1056, 176)])
 def test_gemm_tn_bn_stats(m, n, k):
     from mammoclip_b200 import ops
     a, w = _mk((m, k), 5), _mk((n, k), 6, 1.0 / k ** 0.5)
