@@ -1,4 +1,4 @@
-// Depthwise convolutions as ROW-STREAMING stencils (round 2; replaces the halo-tile kernels of conv.cu for the shapes it covers).
+// Depthwise convolutions as ROW-STREAMING stencils (replaces the halo-tile kernels of conv.cu for the shapes it covers).
 //
 // Same contract as conv.cu (MBConvBlock._depthwise_conv, efficientnet_custom.py:66-73,109; static pads of
 // Conv2dStaticSamePadding, efficient_net_custom_utils.py:248-276; producer BN+swish applied on load, BN statistics of the
@@ -13,6 +13,15 @@
 //     role is static).  No transform pass over shared memory, no bf16 re-rounding of the activated input, no CTA barrier.
 //   * shared memory is addressed through 32-bit shared-window addresses (ld.shared), weights stay in registers.
 // Instruction mix per input row (k5): 8 LDS + 16 unpack + 8+8 FFMA2 (affine, swish) + 16 MUFU + 100 FFMA2.
+//
+// Variants (all measured on the EN-B5 c3 geometry, profiles/r02*):
+//   * backward = two warp ROLES (weight gradient / data gradient) over one ring of Y_in + dY rows.  k3: K-times unrolled bodies with
+//     static accumulator roles; k5: ONE step body per role and register ROTATION of the rolling rows (the unrolled k5 bodies were
+//     5568 SASS instructions and the two roles thrashed the instruction caches), 4-warp CTAs whose roles alternate with the CTA
+//     parity so that every SM sub-partition runs both;
+//   * CG = 16: the narrow k3 s1 layers (C <= 48) run four 8-lane groups per warp, each on its own 5-column sub-strip of the same 16
+//     channels (5 * 32 B apart => four different bank groups), instead of leaving 25-62 % of the lanes of a 64-channel chunk idle;
+//   * stride 2: forward with ceil(K/S) rolling rows, backward as a gather over a register window of dY rows.
 #include "common.cuh"
 #include "mclip_internal.h"
 #include <algorithm>
