@@ -704,7 +704,7 @@ __global__ void __launch_bounds__(NS * 64, NS == 4 ? 2 : 3) mclip_dws_bwd_s1_ker
 // local step jj = j + 2(NA-1) >= 0 (the dgrad window needs NA-1 earlier dY rows), groups of G = 2*NA steps.
 // Ring slot = G input rows of Y_in (33/35 px wide) + NA rows of dY (17/18 px wide).
 // -------------------------------------------------------------------------------------------------------------------
-template <int K, bool BN>
+template <int K, bool BN, bool ROT>
 __global__ void __launch_bounds__(256, 2) mclip_dws_bwd_s2_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constant__ CUtensorMap tmDy, const DwsDev p) {
   constexpr int SW = 4, NS = 4, NW = 8, TW = SW * NS, NA = (K + 1) / 2, G = 2 * NA, RB = G, NSLOT = 3;
   constexpr int IW = (TW - 1) * 2 + K, PC = (SW - 1) * 2 + K, IWG = TW + NA - 1, PCG = SW + NA - 1, OWN = 2 * SW;
@@ -896,7 +896,42 @@ __global__ void __launch_bounds__(256, 2) mclip_dws_bwd_s2_kernel(const __grid_c
         const uint32_t sbase = ring + (uint32_t)sl * SLOT_BYTES + (uint32_t)lane * 4u;
         const uint32_t ybase = sbase + (uint32_t)(strip * OWN) * 128u, gbase = sbase + PARTY + (uint32_t)(strip * SW) * 128u;
         const int j = JMIN + blk * RB;               // local step j of group position s = 0
-        if (wrole) {
+        if constexpr (ROT) {
+          // ROT: one PAIR of steps (s = 0, 1: the newest dY row always enters window slot 1, the row of age a sits in slot (1 - a) mod NA)
+          // per loop trip and a register rotation of the window, instead of G = 2*NA statically unrolled steps per role: a third of
+          // the code (the k5 kernel was 6440 SASS instructions for two roles)
+          auto rotate = [&]() {
+#pragma unroll
+            for (int a = NA - 1; a >= 1; --a)
+#pragma unroll
+              for (int b = 0; b < PCG; ++b) win[(1 - a + NA) % NA][b] = win[(2 - a + NA) % NA][b];
+          };
+          auto wloop = [&](auto fast_c) {
+#pragma unroll 1
+            for (int pp = 0; pp < NA; ++pp) {
+              const uint32_t yb = ybase + (uint32_t)(2 * pp) * ROWY, gb = gbase + (uint32_t)pp * ROWG;
+              wstep(fast_c, std::integral_constant<int, 0>{}, yb, gb, j + 2 * pp);
+              wstep(fast_c, std::integral_constant<int, 1>{}, yb, gb, j + 2 * pp + 1);
+              rotate();
+            }
+          };
+          auto dloop = [&](auto fast_c) {
+#pragma unroll 1
+            for (int pp = 0; pp < NA; ++pp) {
+              const uint32_t yb = ybase + (uint32_t)(2 * pp) * ROWY, gb = gbase + (uint32_t)pp * ROWG;
+              dstep(fast_c, std::integral_constant<int, 0>{}, yb, gb, j + 2 * pp);
+              dstep(fast_c, std::integral_constant<int, 1>{}, yb, gb, j + 2 * pp + 1);
+              rotate();
+            }
+          };
+          if (wrole) {
+            const bool fast = warp_fast && v0 + j >= 0 && v0 + j + G <= p.H && j >= 0 && (j + G - 2) / 2 < ci.rows && ci.r0 + (j + G - 2) / 2 < p.Ho;
+            if (fast) wloop(std::true_type{}); else wloop(std::false_type{});
+          } else {
+            const bool fast = warp_fast && j >= 0 && j + G <= 2 * ci.rows && v0 + j >= 0 && v0 + j + G <= p.H;
+            if (fast) dloop(std::true_type{}); else dloop(std::false_type{});
+          }
+        } else if (wrole) {
           // fast: every A row inside the image, every dY row entering the window owned by this segment and inside dY
           const bool fast = warp_fast && v0 + j >= 0 && v0 + j + G <= p.H && j >= 0 && (j + G - 2) / 2 < ci.rows && ci.r0 + (j + G - 2) / 2 < p.Ho;
           if (fast) {
@@ -1043,6 +1078,9 @@ static int dws_fwd_ctas(const mclip_dwconv_args* a) {
 #ifndef DWS_BWD_K5_ROT
 #define DWS_BWD_K5_ROT 1
 #endif
+#ifndef DWS_BWD2_K5_ROT
+#define DWS_BWD2_K5_ROT 1
+#endif
 template <int K, int CG = 64>
 struct BwdCfg {
   static constexpr int NSLOT = DWS_BWD_NSLOT;
@@ -1087,7 +1125,8 @@ int dws_launch_bwd_s2(const mclip_dwconv_args* a, DwsDev& p, cudaStream_t stream
   if (rc) return rc;
   if ((rc = dws_tmap(&tmDy, p.dy, p.N, p.Ho, p.Wo, p.C, Cfg::IWG, Cfg::NA))) return rc;
   const bool bn = p.scale != nullptr;
-  auto kern = bn ? mclip_dws_bwd_s2_kernel<K, true> : mclip_dws_bwd_s2_kernel<K, false>;
+  constexpr bool ROT = K == 5 && DWS_BWD2_K5_ROT != 0;
+  auto kern = bn ? mclip_dws_bwd_s2_kernel<K, true, ROT> : mclip_dws_bwd_s2_kernel<K, false, ROT>;
   static bool attr[2] = {false, false};
   if (!attr[bn]) { MCLIP_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM)); attr[bn] = true; }
   kern<<<p.n_chunks * p.slots, 256, Cfg::SMEM, stream>>>(tmIn, tmDy, p);
