@@ -412,6 +412,17 @@ class _EncoderFn(torch.autograd.Function):
         return (None, None, None, None, None, *out)
 
 
+def choose_view_plan(keep_bytes, lean_bytes, free_bytes, reserve=40 << 30):
+    """Memory plan of a multi-view step: the cheapest plan whose saved state leaves `reserve` bytes for the transients of the
+    backward (U, dA2, A2, dY1, dV0 of the largest block: <= 35 GB at c3).  keep: every view's full state; lean: without the expand
+    convs' outputs (re-made by one GEMM each in the backward); recompute: one view resident at a time (two extra forwards)."""
+    if keep_bytes + reserve <= free_bytes:
+        return "keep"
+    if lean_bytes + reserve <= free_bytes:
+        return "lean"
+    return "recompute"
+
+
 class _MultiViewFn(torch.autograd.Function):
     """Memory plan for the multi-view loss (loss/breast_clip.py: two image views per step, clip.py:103-112) at the metric
     scale: the saved pre-BN tensors of ONE EN-B5 view at B = 64, 1520x912 are 91.5 GB, two do not fit 180 GB.  The forward
@@ -609,7 +620,7 @@ class EfficientNet(nn.Module):
             need = sum(self.saved_bytes(v.shape[0], v.shape[2], v.shape[3]) for v in views) if grad else 0
             lean = sum(self.saved_bytes(v.shape[0], v.shape[2], v.shape[3], keep_y0=False) for v in views) if grad else 0
             free = torch.cuda.mem_get_info(views[0].device)[0] + torch.cuda.memory_reserved(views[0].device) - torch.cuda.memory_allocated(views[0].device)
-            plan = "keep" if need + (40 << 30) <= free else "lean" if lean + (40 << 30) <= free else "recompute"
+            plan = choose_view_plan(need, lean, free)
         object.__setattr__(self, "last_plan", plan)
         if plan in ("keep", "lean") or not (self.training and torch.is_grad_enabled()):
             _DROP_Y0[0] = plan == "lean"

@@ -164,3 +164,16 @@ def test_bench_reference_arm_prints_the_contract_line():
     assert line["cpu_baseline"]["kind"] in ("port", "reference") and line["cpu_baseline"]["cores"] >= 1 and "sample" in line["cpu_baseline"]
     assert line["e2e"] == {"value": line["value"], "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert line["gpu_launches"] == 0 and "workload" in line["config"]
+
+
+def test_multi_view_memory_plan_choice():
+    """Host logic of the multi-view memory plan at the metric scale (EN-B5, B = 64, 1520x912, two views) on a 180 GB device."""
+    from mammoclip_b200.model.modules.efficientnet_custom import EfficientNet, choose_view_plan
+    enc = EfficientNet.from_name("efficientnet-b5", num_classes=1)
+    keep, lean = enc.saved_bytes(64, 1520, 912), enc.saved_bytes(64, 1520, 912, keep_y0=False)
+    assert 92e9 < keep < 94e9 and 54e9 < lean < 56e9            # 92.9 GB per view, 55.0 GB without the expand outputs (DESIGN 5)
+    free = 175 << 30
+    assert choose_view_plan(keep, lean, free) == "keep"                      # one view
+    assert choose_view_plan(2 * keep, 2 * lean, free) == "lean"              # the shipped YAML's two views
+    assert choose_view_plan(4 * keep, 4 * lean, free) == "recompute"
+    assert choose_view_plan(0, 0, free) == "keep"                            # eval / no_grad: nothing is saved
