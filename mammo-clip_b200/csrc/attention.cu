@@ -51,12 +51,12 @@ __device__ __forceinline__ void store_row32(uint8_t* tile, int row, int c0, cons
 }
 
 // keep-mask multipliers of 32 consecutive keys starting at kj0 (row pointer dm; nullptr: no dropout): two 16-byte loads when the
-// row is 16-byte aligned (L % 16 == 0), byte loads otherwise
+// row is 16-byte aligned (L % 16 == 0 and an aligned mask tensor), byte loads otherwise
 __device__ __forceinline__ void load_mask32(const uint8_t* dm, int kj0, int L, float scale, float* mk) {
   if (!dm) {
 #pragma unroll
     for (int e = 0; e < 32; ++e) mk[e] = 1.0f;
-  } else if ((L & 15) == 0 && kj0 + 32 <= L) {
+  } else if ((L & 15) == 0 && kj0 + 32 <= L && (reinterpret_cast<uintptr_t>(dm + kj0) & 15) == 0) {
     const uint4 a = *reinterpret_cast<const uint4*>(dm + kj0), b = *reinterpret_cast<const uint4*>(dm + kj0 + 16);
     const uint32_t w[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
 #pragma unroll
