@@ -277,7 +277,9 @@ int mclip_bert_embed_ln(const mclip_bert_embed_args* args, void* stream);
 int mclip_layernorm(const void* x_bf16, const float* gamma, const float* beta, float eps, void* out_bf16, int rows, int hidden, void* stream);
 /* qkv: bf16 [batch*seq_len, 3*heads*head_dim] (Q | K | V); attention_mask int64 [batch, seq_len] (1 = attend);
  * dropmask uint8 [batch, heads, seq_len, seq_len] or NULL; out bf16 [batch*seq_len, heads*head_dim];
- * lse fp32 [batch, heads, seq_len] or NULL: log-sum-exp of the scaled masked scores, saved for the backward pass. */
+ * lse fp32 [batch, heads, seq_len] or NULL: log-sum-exp of the scaled masked scores, saved for the backward pass.
+ * seq_len <= 256 (head_dim 64): tcgen05 kernels (csrc/attention.cu: TMA-staged tiles, scores in TMEM, one thread per query row);
+ * longer sequences: the SIMT kernels of csrc/bert.cu.  Replaces transformers' BertSelfAttention (SDPA, modeling_bert.py:168-207). */
 int mclip_bert_attention(const void* qkv, const void* attention_mask, const void* dropmask, float drop_scale, void* out, float* lse,
                          int batch, int seq_len, int heads, int head_dim, void* stream);
 
@@ -296,8 +298,9 @@ int mclip_layernorm_backward(const void* x_bf16, const void* dy_bf16, const floa
 int mclip_gelu_forward(const void* x_bf16, void* y_bf16, long long n, void* stream);
 int mclip_gelu_backward(const void* dy_bf16, const void* x_bf16, void* dx_bf16, long long n, void* stream);
 /* d qkv (bf16 [batch*seq_len, 3*heads*head_dim]) from d_out (bf16 [batch*seq_len, heads*head_dim]) and the saved lse;
- * probabilities are recomputed per 64x64 tile; delta_ws fp32 [batch, heads, seq_len] receives sum_k P dP of a pre-pass
- * (fp32, not the bf16-rounded <dO, O>); every output element is written exactly once (deterministic). */
+ * probabilities are recomputed from Q, K and the lse; delta = sum_k P dP is the exact fp32 row sum (not the bf16-rounded <dO, O>);
+ * delta_ws fp32 [batch, heads, seq_len] is the pre-pass buffer of the SIMT path (seq_len > 256; the tcgen05 path keeps delta in
+ * registers); every output element is written exactly once (deterministic). */
 int mclip_bert_attention_backward(const void* qkv, const void* d_out, const float* lse, const void* attention_mask, const void* dropmask,
                                   float drop_scale, float* delta_ws, void* dqkv, int batch, int seq_len, int heads, int head_dim, void* stream);
 /* Embeddings backward (BertEmbeddings): LayerNorm backward of (dout o keep-mask*scale) with the pre-LN sum recomputed from
